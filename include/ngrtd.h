@@ -1,0 +1,149 @@
+/*
+ * ngrtd.h -- C ABI of libngrtd.so: the B200-native (sm_100a) batched likelihood hot path of
+ * uz226/NobleGas_RTD_MCMC (lumped-parameter convolution integral + closed-equilibrium noble-gas
+ * model + log-likelihood + device-resident Metropolis step).
+ *
+ * The reference is pure Python and has no FFI; each entry point below names the reference
+ * interface it replaces (paths relative to the reference root).  The reference-side binding a
+ * maintainer would add is a ctypes stub -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative NGRTD_E* code otherwise, never throws;
+ *     ngrtd_last_error() returns a thread-local message for the last failure.
+ *   - `*_dev` entry points take DEVICE pointers plus a CUDA stream handle (cudaStream_t cast to
+ *     void*; NULL = default stream); they enqueue work and return without synchronising.
+ *   - `*_host` entry points take HOST pointers (pinned or pageable), copy in, run, copy out and
+ *     synchronise before returning.
+ *   - all floating point data is IEEE double; matrices are row-major; batches are [B, n].
+ *   - numerical pathologies propagate as NaN / the -9999 sentinel exactly like the reference
+ *     (no error is raised for bad parameter values).
+ */
+#ifndef NGRTD_H_
+#define NGRTD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGRTD_VERSION 100
+
+/* error codes */
+#define NGRTD_OK 0
+#define NGRTD_EINVAL (-1)   /* bad argument (unknown model, too many columns, null pointer ...) */
+#define NGRTD_ECUDA (-2)    /* CUDA runtime error; see ngrtd_last_error() */
+#define NGRTD_ENOMEM (-3)
+
+/* RTD model types: `mod_type` strings of utils/convolution_integral_utils.py:178-196 */
+#define NGRTD_MOD_NONE 0            /* mod_type2 = False */
+#define NGRTD_MOD_PISTON 1          /* 'piston'        :178-181 */
+#define NGRTD_MOD_EXPONENTIAL 2     /* 'exponential'   :183-184 */
+#define NGRTD_MOD_EXP_PIST_FLOW 3   /* 'exp_pist_flow' :186-190 */
+#define NGRTD_MOD_DISPERSION 4      /* 'dispersion'    :192-196 */
+
+/* parameter slots = keys of ForwardMod.p_dict, age_ens_runs_mcmc/run_age_mcmc_utils.py:73-79 */
+#define NGRTD_P_TAU1 0
+#define NGRTD_P_TAU2 1
+#define NGRTD_P_F1 2
+#define NGRTD_P_F2 3
+#define NGRTD_P_ETA1 4
+#define NGRTD_P_ETA2 5
+#define NGRTD_P_D1 6
+#define NGRTD_P_D2 7
+#define NGRTD_P_J 8            /* log10 of the 4He production rate (run_age_mcmc_utils.py:101) */
+#define NGRTD_P_THALF_CFC 9    /* CFC-12 first-order decay half life (:107-109) */
+#define NGRTD_P_LAMSF6 10      /* SF6 contamination factor (:160-161) */
+#define NGRTD_NSLOT 11
+
+/* rad_accum modes of tracer_conv_integral.update_pars (utils/convolution_integral_utils.py:123,313-333) */
+#define NGRTD_ACC_NONE 0
+#define NGRTD_ACC_3HE 1   /* g *= 1 - exp(-lambda tp) */
+#define NGRTD_ACC_4HE 2   /* C_t += index * J        */
+
+/* One modelled tracer = one ForwardMod instance of the reference (run_age_mcmc_utils.py:52-79,
+ * conv_kwgs built at run_age_mcmc.py:200-224). */
+typedef struct ngrtd_tracer {
+    int32_t series;          /* column of the input-series matrix, or -1 for an all-zero series */
+    int32_t rad_accum;       /* NGRTD_ACC_* */
+    double lambda;           /* decay constant from thalf_2_lambda(t_half); 0 = no decay */
+    int32_t use_thalf_cfc;   /* 1: lambda = ln2 / theta[thalf_cfc] per chain (the CFC12 rule, :107-109) */
+    int32_t use_lamsf6;      /* 1: output *= 1 + theta[lamsf6]                (the SF6 rule, :160-161) */
+} ngrtd_tracer;
+
+/* likelihood kinds (pymc3 call sites run_age_mcmc_utils.py:389-396, ng_interp/noble_gas_mcmc.py:264-266) */
+#define NGRTD_LIK_NORMAL 0
+#define NGRTD_LIK_STUDENTT 1
+
+typedef struct ngrtd_plan ngrtd_plan;   /* opaque: input series + lag tables resident in HBM */
+
+int ngrtd_version(void);
+const char* ngrtd_last_error(void);
+
+/* ---- plan: replaces tracer_conv_integral.__init__(C_t, t_samp) (conv utils :105-108) and the
+ *      per-call C_t.copy() of ForwardMod.perform (run_age_mcmc_utils.py:94) for ALL tracers at once.
+ *  series      host [L, nseries], row k = concentrations k lags before sampling (i.e. after the
+ *              reference's np.flip, conv utils :336)
+ *  lag_index   host [L] DataFrame index values after the flip (used by '4He': C_t + index*J, :323);
+ *              NULL = 0,1,2,...
+ *  dtp         floor(t_samp - C_t.index[-1]) (:172); 0 at every call site of the reference
+ *  device      CUDA device ordinal (-1 = current device)                                           */
+int ngrtd_plan_create(ngrtd_plan** plan, int32_t L, int32_t nseries, const double* series,
+                      const double* lag_index, double dtp, int32_t ntracer, const ngrtd_tracer* tracers,
+                      int32_t mod_type1, int32_t mod_type2, int32_t device);
+int ngrtd_plan_destroy(ngrtd_plan* plan);
+int ngrtd_plan_ntracer(const ngrtd_plan* plan);
+
+/* ---- batched ForwardMod.perform (run_age_mcmc_utils.py:81-163) for every tracer of the plan.
+ *  theta        [B, ndim]; column i is parameter slot slot_of_col[i] (= par_names order)
+ *  slot_of_col  HOST int32[ndim], values NGRTD_P_*
+ *  out          [B, ntracer] modelled concentrations                                               */
+int ngrtd_forward_dev(ngrtd_plan* plan, const double* theta_d, int64_t B, int32_t ndim,
+                      const int32_t* slot_of_col, double* out_d, void* stream);
+int ngrtd_forward_host(ngrtd_plan* plan, const double* theta_h, int64_t B, int32_t ndim,
+                       const int32_t* slot_of_col, double* out_h);
+
+/* ---- fused forward model + log-likelihood (the MCMC likelihood evaluation).
+ *  obs_mu, obs_sd  HOST double[ntracer]  (run_age_mcmc_utils.py:353-356)
+ *  nu_d            [B] Student-T degrees of freedom (ignored for NGRTD_LIK_NORMAL; may be NULL)
+ *  logp            [B]; model_out optional [B, ntracer] (NULL to skip)                              */
+int ngrtd_forward_loglik_dev(ngrtd_plan* plan, const double* theta_d, int64_t B, int32_t ndim,
+                             const int32_t* slot_of_col, int32_t lik_kind, const double* obs_mu,
+                             const double* obs_sd, const double* nu_d, double* logp_d, double* model_out_d,
+                             void* stream);
+int ngrtd_forward_loglik_host(ngrtd_plan* plan, const double* theta_h, int64_t B, int32_t ndim,
+                              const int32_t* slot_of_col, int32_t lik_kind, const double* obs_mu,
+                              const double* obs_sd, const double* nu_h, double* logp_h, double* model_out_h);
+
+/* ---- tracer_conv_integral.gen_g_tp() (conv utils :155-281): normalised RTD weights g[B, L],
+ *      one model, parameters tau/eta/D [B] (eta, D may be NULL when unused).                        */
+int ngrtd_rtd_weights_dev(int32_t mod_type, int32_t L, double dtp, const double* tau_d, const double* eta_d,
+                          const double* D_d, int64_t B, double* g_d, void* stream);
+/* ---- tracer_conv_integral.convolve(g_tau=...) tail (:305-340): decay/ingrowth + input assembly + dot
+ *      for externally supplied weights g[B, L]; series [L] newest-first, lag_index [L] or NULL.      */
+int ngrtd_convolve_g_dev(int32_t L, double dtp, const double* g_d, int64_t B, const double* series_d,
+                         const double* lag_index_d, const double* lambda_d /*[B]*/, int32_t rad_accum,
+                         const double* J_d /*[B] linear J or NULL*/, double* out_d, void* stream);
+
+/* ---- closed-equilibrium noble-gas model: noble_gas_fun(...).ce_exc / equil_conc[_dry]
+ *      (utils/noble_gas_utils.py:103-253).  gases: HOST int32[ngas] with 0=He 1=Ne 2=Ar 3=Kr 4=Xe.
+ *  what: 0 = ce_exc(add_eq_conc=True), 1 = ce_exc(False), 2 = equil_conc_dry(), 3 = equil_conc(),
+ *        4 = solubility K
+ *  E, T, Ae, F, P: [B]; P may be NULL = 'lapse_rate' (:97-98, :112);  S = salinity            */
+int ngrtd_ce_dev(int32_t what, int32_t ngas, const int32_t* gases, const double* E_d, const double* T_d,
+                 const double* Ae_d, const double* F_d, const double* P_d, double S, int64_t B,
+                 double* out_d /*[B, ngas]*/, void* stream);
+int ngrtd_ce_host(int32_t what, int32_t ngas, const int32_t* gases, const double* E_h, const double* T_h,
+                  const double* Ae_h, const double* F_h, const double* P_h, double S, int64_t B, double* out_h);
+/* ce_exc_wrapper(theta) of ng_interp/noble_gas_mcmc.py:205-213: theta[B,4] = log10 Ae, log10 F, E, T */
+int ngrtd_ce_wrapper_dev(int32_t ngas, const int32_t* gases, const double* theta_d, int64_t B, double* out_d,
+                         void* stream);
+
+/* ---- stand-alone log-likelihood over model outputs mu[B, T] (pymc3 Normal / StudentT logp). */
+int ngrtd_loglik_dev(int32_t lik_kind, int32_t T, const double* mu_d, const double* obs_mu, const double* obs_sd,
+                     const double* nu_d, int64_t B, double* logp_d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGRTD_H_ */

@@ -1,0 +1,185 @@
+"""ctypes binding of libngrtd.so (C ABI declared in include/ngrtd.h).
+
+There is NO CPU fallback: importing this module without the compiled CUDA library raises.
+PyTorch is used by the callers only for device memory and streams (tensor.data_ptr(),
+torch.cuda.current_stream().cuda_stream); no torch type crosses this boundary.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("NGRTD_LIB", os.path.join(_HERE, "libngrtd.so"))
+
+MOD = {"piston": 1, "exponential": 2, "exp_pist_flow": 3, "dispersion": 4}
+SLOT = {"tau1": 0, "tau2": 1, "f1": 2, "f2": 3, "eta1": 4, "eta2": 5, "D1": 6, "D2": 7, "J": 8,
+        "thalf_cfc": 9, "lamsf6": 10}
+ACC = {False: 0, None: 0, "3He": 1, "4He": 2}
+GAS = {"He": 0, "Ne": 1, "Ar": 2, "Kr": 3, "Xe": 4}
+LIK = {"normal": 0, "studentt": 1}
+
+
+class NgrtdError(RuntimeError):
+    pass
+
+
+class Tracer(ctypes.Structure):
+    _fields_ = [("series", ctypes.c_int32), ("rad_accum", ctypes.c_int32), ("lam", ctypes.c_double),
+                ("use_thalf_cfc", ctypes.c_int32), ("use_lamsf6", ctypes.c_int32)]
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "libngrtd.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+        "or noblegas_rtd_mcmc_b200/build.py; there is no CPU fallback." % LIB_PATH)
+
+lib = ctypes.CDLL(LIB_PATH)
+
+_vp, _i32, _i64, _dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+_PROTOS = {
+    "ngrtd_version": ([], ctypes.c_int),
+    "ngrtd_last_error": ([], ctypes.c_char_p),
+    "ngrtd_plan_create": ([ctypes.POINTER(_vp), _i32, _i32, _vp, _vp, _dbl, _i32, ctypes.POINTER(Tracer), _i32, _i32, _i32], ctypes.c_int),
+    "ngrtd_plan_destroy": ([_vp], ctypes.c_int),
+    "ngrtd_plan_ntracer": ([_vp], ctypes.c_int),
+    "ngrtd_forward_dev": ([_vp, _vp, _i64, _i32, _vp, _vp, _vp], ctypes.c_int),
+    "ngrtd_forward_host": ([_vp, _vp, _i64, _i32, _vp, _vp], ctypes.c_int),
+    "ngrtd_forward_loglik_dev": ([_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "ngrtd_forward_loglik_host": ([_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "ngrtd_rtd_weights_dev": ([_i32, _i32, _dbl, _vp, _vp, _vp, _i64, _vp, _vp], ctypes.c_int),
+    "ngrtd_convolve_g_dev": ([_i32, _dbl, _vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp], ctypes.c_int),
+    "ngrtd_ce_dev": ([_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _vp, _vp], ctypes.c_int),
+    "ngrtd_ce_host": ([_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _vp], ctypes.c_int),
+    "ngrtd_ce_wrapper_dev": ([_i32, _vp, _vp, _i64, _vp, _vp], ctypes.c_int),
+    "ngrtd_loglik_dev": ([_i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp], ctypes.c_int),
+}
+for _name, (_args, _res) in _PROTOS.items():
+    _fn = getattr(lib, _name)
+    _fn.argtypes = _args
+    _fn.restype = _res
+
+EXPORTED = tuple(_PROTOS)
+
+
+def check(rc):
+    if rc != 0:
+        raise NgrtdError("libngrtd error %d: %s" % (rc, lib.ngrtd_last_error().decode()))
+
+
+def hptr(a):
+    """Host pointer of a C-contiguous float64/int32 numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def slot_array(par_names):
+    try:
+        return i32([SLOT[p] for p in par_names])
+    except KeyError as e:
+        raise ValueError("unknown parameter name %s (known: %s)" % (e, sorted(SLOT)))
+
+
+def stream_ptr(stream=None):
+    """cudaStream_t of a torch stream (default: torch's current stream)."""
+    import torch
+    s = torch.cuda.current_stream() if stream is None else stream
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def dptr(t):
+    """Device pointer of a contiguous float64 CUDA tensor (or None)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "need a contiguous CUDA tensor"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class Plan:
+    """Owns an ngrtd_plan: input series + lag tables of one (model pair, tracer set) resident in HBM."""
+
+    def __init__(self, series, tracers, mod_type1, mod_type2=False, lag_index=None, dtp=0.0, device=-1):
+        series = f64(series)
+        if series.ndim == 1:
+            series = series.reshape(-1, 1)
+        self.L, self.nseries = series.shape
+        for m in (mod_type1, mod_type2):
+            if m and m not in MOD:
+                raise ValueError("unknown mod_type %r (known: %s)" % (m, sorted(MOD)))
+        if not mod_type1:
+            raise ValueError("mod_type1 is required")
+        arr = (Tracer * len(tracers))()
+        for i, t in enumerate(tracers):
+            ra = t.get("rad_accum", False)
+            if ra not in ACC:
+                raise ValueError("unknown rad_accum %r" % (ra,))
+            arr[i] = Tracer(int(t.get("series", -1)), ACC[ra], float(t.get("lam", 0.0)),
+                            int(bool(t.get("use_thalf_cfc", False))), int(bool(t.get("use_lamsf6", False))))
+        li = None if lag_index is None else f64(lag_index)
+        h = ctypes.c_void_p()
+        check(lib.ngrtd_plan_create(ctypes.byref(h), self.L, self.nseries, hptr(series), hptr(li), float(dtp),
+                                    len(tracers), arr, MOD[mod_type1], MOD[mod_type2] if mod_type2 else 0, device))
+        self.handle = h
+        self.ntracer = len(tracers)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib.ngrtd_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- host buffers (numpy in / numpy out) ----
+    def forward_host(self, theta, par_names):
+        theta = f64(np.atleast_2d(theta))
+        B, ndim = theta.shape
+        assert ndim == len(par_names)
+        out = np.empty((B, self.ntracer))
+        check(lib.ngrtd_forward_host(self.handle, hptr(theta), B, ndim, hptr(slot_array(par_names)), hptr(out)))
+        return out
+
+    def forward_loglik_host(self, theta, par_names, obs_mu, obs_sd, kind="normal", nu=None, want_model=False,
+                            logp_out=None):
+        theta = f64(np.atleast_2d(theta))
+        B, ndim = theta.shape
+        logp = np.empty(B) if logp_out is None else logp_out
+        model = np.empty((B, self.ntracer)) if want_model else None
+        nu_a = None if nu is None else f64(np.broadcast_to(nu, (B,)))
+        check(lib.ngrtd_forward_loglik_host(self.handle, hptr(theta), B, ndim, hptr(slot_array(par_names)), LIK[kind],
+                                            hptr(f64(obs_mu)), hptr(f64(obs_sd)), hptr(nu_a), hptr(logp), hptr(model)))
+        return (logp, model) if want_model else logp
+
+    # ---- device buffers (torch CUDA tensors in / out, no synchronisation) ----
+    def forward_dev(self, theta_t, par_names, out_t=None, stream=None):
+        import torch
+        B, ndim = theta_t.shape
+        if out_t is None:
+            out_t = torch.empty((B, self.ntracer), dtype=torch.float64, device=theta_t.device)
+        check(lib.ngrtd_forward_dev(self.handle, dptr(theta_t), B, ndim, hptr(slot_array(par_names)), dptr(out_t),
+                                    stream_ptr(stream)))
+        return out_t
+
+    def forward_loglik_dev(self, theta_t, par_names, obs_mu, obs_sd, kind="normal", nu_t=None, logp_t=None,
+                           model_t=None, stream=None):
+        import torch
+        B, ndim = theta_t.shape
+        if logp_t is None:
+            logp_t = torch.empty((B,), dtype=torch.float64, device=theta_t.device)
+        check(lib.ngrtd_forward_loglik_dev(self.handle, dptr(theta_t), B, ndim, hptr(slot_array(par_names)), LIK[kind],
+                                           hptr(f64(obs_mu)), hptr(f64(obs_sd)), dptr(nu_t), dptr(logp_t),
+                                           dptr(model_t), stream_ptr(stream)))
+        return logp_t

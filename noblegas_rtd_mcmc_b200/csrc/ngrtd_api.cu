@@ -1,0 +1,655 @@
+// ngrtd_api.cu -- C ABI of libngrtd.so (include/ngrtd.h): plan management, kernel dispatch, host-buffer variants.
+// No torch types anywhere; device pointers and a stream handle come from the caller.
+#include "../../include/ngrtd.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "ngrtd_common.cuh"
+#include "ngrtd_forward.cuh"
+#include "ngrtd_ce.cuh"
+
+using namespace ngrtd;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(x)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e__ = (x);                                                                        \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(NGRTD_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e__));               \
+    } while (0)
+
+struct ngrtd_plan {
+    int device = 0;
+    int nsm = 0;
+    int L = 0, Lpad = 0;
+    int mod1 = 0, mod2 = 0;
+    int cls1 = 0, cls2 = 0;
+    bool dyn = false;
+    PlanView pv{};
+    double *dXf = nullptr, *dXd = nullptr, *ditp = nullptr, *dxraw = nullptr, *dxrawd = nullptr, *dtbl = nullptr;
+    unsigned int* dcounter = nullptr;
+    // workspace of the *_host entry points
+    double *w_theta = nullptr, *w_out = nullptr, *w_logp = nullptr, *w_nu = nullptr;
+    size_t w_theta_n = 0, w_out_n = 0, w_logp_n = 0, w_nu_n = 0;
+    cudaStream_t hstream = nullptr;
+};
+
+static int cls_of(int mod) {
+    switch (mod) {
+        case NGRTD_MOD_NONE: return CLS_NONE;
+        case NGRTD_MOD_PISTON: return CLS_P;
+        case NGRTD_MOD_EXPONENTIAL:
+        case NGRTD_MOD_EXP_PIST_FLOW: return CLS_G;
+        case NGRTD_MOD_DISPERSION: return CLS_D;
+        default: return -1;
+    }
+}
+
+extern "C" int ngrtd_version(void) { return NGRTD_VERSION; }
+extern "C" const char* ngrtd_last_error(void) { return g_err.c_str(); }
+
+static double j_flux(double Del, double rho_r, double rho_w, double U, double Th, double phi) {
+    const double PU = 1.19e-13, PTh = 2.88e-14;   // utils/noble_gas_utils.py:335-348
+    return Del * rho_r / rho_w * (U * PU + Th * PTh) * ((1 - phi) / phi);
+}
+
+extern "C" int ngrtd_plan_create(ngrtd_plan** out, int32_t L, int32_t nseries, const double* series,
+                                 const double* lag_index, double dtp, int32_t ntracer, const ngrtd_tracer* tracers,
+                                 int32_t mod_type1, int32_t mod_type2, int32_t device) {
+    if (!out) return fail(NGRTD_EINVAL, "plan: null output pointer");
+    *out = nullptr;
+    if (L < 1) return fail(NGRTD_EINVAL, "plan: L must be >= 1");
+    if (nseries < 0 || (nseries > 0 && !series)) return fail(NGRTD_EINVAL, "plan: series is null");
+    if (ntracer < 1 || ntracer > MAX_TRACER) return fail(NGRTD_EINVAL, "plan: ntracer must be in 1..8");
+    if (!tracers) return fail(NGRTD_EINVAL, "plan: tracers is null");
+    int c1 = cls_of(mod_type1), c2 = cls_of(mod_type2);
+    if (c1 <= 0) return fail(NGRTD_EINVAL, "plan: unknown mod_type1 " + std::to_string(mod_type1));
+    if (c2 < 0) return fail(NGRTD_EINVAL, "plan: unknown mod_type2 " + std::to_string(mod_type2));
+    if (dtp != std::floor(dtp)) return fail(NGRTD_EINVAL, "plan: dtp must be integer valued (np.floor in the reference)");
+    if (device >= 0) CUDA_TRY(cudaSetDevice(device));
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+
+    auto* P = new ngrtd_plan();
+    P->device = dev;
+    CUDA_TRY(cudaDeviceGetAttribute(&P->nsm, cudaDevAttrMultiProcessorCount, dev));
+    P->L = L;
+    P->Lpad = (L + 3) & ~3;
+    P->mod1 = mod_type1;
+    P->mod2 = mod_type2;
+    P->cls1 = c1;
+    P->cls2 = c2;
+    const int Lpad = P->Lpad;
+
+    // lag grid exactly as the reference builds it: arange -> tp[0] += 1e-5 -> tp += dtp (conv utils :168-173)
+    std::vector<double> tp(Lpad, 0.0), p15(Lpad, 0.0), itp(Lpad, 0.0);
+    for (int k = 0; k < L; k++) {
+        double t = (double)k;
+        if (k == 0) t += 1e-5;
+        t += dtp;
+        tp[k] = t;
+        itp[k] = 1.0 / t;
+        p15[k] = 1.0 / (t * std::sqrt(t));
+    }
+    // folded columns
+    struct ColKey { int series; int mode; double lambda; };   // mode 0 decay, 1 ingrowth, 2 lag-index*decay
+    std::vector<ColKey> cols;
+    cols.push_back({-2, 0, 0.0});   // column 0: ones
+    auto find_col = [&](int s, int mode, double lam) -> int {
+        for (size_t i = 1; i < cols.size(); i++)
+            if (cols[i].series == s && cols[i].mode == mode && cols[i].lambda == lam) return (int)i;
+        cols.push_back({s, mode, lam});
+        return (int)cols.size() - 1;
+    };
+    int ndyn = 0, dyn_series = -1;
+    for (int t = 0; t < ntracer; t++) {
+        const ngrtd_tracer& tr = tracers[t];
+        if (tr.series >= nseries) { delete P; return fail(NGRTD_EINVAL, "plan: tracer series index out of range"); }
+        TracerDev td{-1, -1, 0, tr.use_lamsf6 ? 1 : 0};
+        bool zero_series = tr.series < 0;
+        if (!zero_series) {
+            zero_series = true;
+            for (int k = 0; k < L && zero_series; k++) zero_series = (series[(size_t)k * nseries + tr.series] == 0.0);
+        }
+        if (tr.use_thalf_cfc) {
+            if (tr.rad_accum != NGRTD_ACC_NONE) { delete P; return fail(NGRTD_EINVAL, "plan: use_thalf_cfc with rad_accum is not supported"); }
+            if (ndyn && dyn_series != tr.series) { delete P; return fail(NGRTD_EINVAL, "plan: only one per-chain-lambda series per plan"); }
+            ndyn++;
+            dyn_series = tr.series;
+            td.dyn = 1;
+        } else if (tr.rad_accum == NGRTD_ACC_3HE) {
+            if (!zero_series) td.col_a = find_col(tr.series, 1, tr.lambda);
+        } else if (tr.rad_accum == NGRTD_ACC_4HE) {
+            if (!zero_series) td.col_a = find_col(tr.series, 0, tr.lambda);
+            td.col_b = find_col(-1, 2, tr.lambda);
+        } else if (tr.rad_accum == NGRTD_ACC_NONE) {
+            if (!zero_series) td.col_a = find_col(tr.series, 0, tr.lambda);
+        } else {
+            delete P;
+            return fail(NGRTD_EINVAL, "plan: unknown rad_accum");
+        }
+        P->pv.tr[t] = td;
+    }
+    if ((int)cols.size() > NCOL) {
+        delete P;
+        return fail(NGRTD_EINVAL, "plan: more than 7 distinct folded columns; split the tracers over two plans");
+    }
+    P->dyn = ndyn > 0;
+    std::vector<double> Xf((size_t)Lpad * NCOL, 0.0), Xd((size_t)Lpad * NCOL, 0.0), xraw(Lpad, 0.0), xrawd(Lpad, 0.0);
+    for (int k = 0; k < L; k++) {
+        for (size_t c = 0; c < cols.size(); c++) {
+            double v;
+            const ColKey& ck = cols[c];
+            if (c == 0) {
+                v = 1.0;
+            } else {
+                double dec = std::exp(-ck.lambda * tp[k]);                       // conv utils :316
+                if (ck.mode == 1) v = series[(size_t)k * nseries + ck.series] * (1 - dec);   // :314
+                else if (ck.mode == 2) v = (lag_index ? lag_index[k] : (double)k) * dec;     // :323 index * J
+                else v = series[(size_t)k * nseries + ck.series] * dec;
+            }
+            Xf[(size_t)k * NCOL + c] = v;
+            Xd[(size_t)k * NCOL + c] = v * p15[k];
+        }
+        if (P->dyn && dyn_series >= 0) {
+            xraw[k] = series[(size_t)k * nseries + dyn_series];
+            xrawd[k] = xraw[k] * p15[k];
+        }
+    }
+    std::vector<double> tbl(TBL_DOUBLES);
+    {
+        uint32_t* w = reinterpret_cast<uint32_t*>(tbl.data());
+        for (int i = 0; i < TBL_N; i++) {
+            double v = std::exp2((double)i / TBL_N);
+            uint64_t b;
+            std::memcpy(&b, &v, 8);
+            w[i] = (uint32_t)(b >> 32) - ((uint32_t)i << 15);
+            w[TBL_N + i] = (uint32_t)(b & 0xffffffffu);
+        }
+    }
+
+    auto up = [&](double** d, const std::vector<double>& h) -> cudaError_t {
+        cudaError_t e = cudaMalloc((void**)d, h.size() * sizeof(double));
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice);
+    };
+    cudaError_t e = cudaSuccess;
+    if ((e = up(&P->dXf, Xf)) != cudaSuccess || (e = up(&P->dXd, Xd)) != cudaSuccess ||
+        (e = up(&P->ditp, itp)) != cudaSuccess || (e = up(&P->dxraw, xraw)) != cudaSuccess ||
+        (e = up(&P->dxrawd, xrawd)) != cudaSuccess || (e = up(&P->dtbl, tbl)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&P->dcounter, 64)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&P->hstream, cudaStreamNonBlocking)) != cudaSuccess) {
+        ngrtd_plan_destroy(P);
+        return fail(NGRTD_ECUDA, std::string("plan upload: ") + cudaGetErrorString(e));
+    }
+    PlanView& pv = P->pv;
+    pv.L = L;
+    pv.Lpad = Lpad;
+    pv.dtp = dtp;
+    pv.Xf = P->dXf;
+    pv.Xd = P->dXd;
+    pv.itp = P->ditp;
+    pv.xraw = P->dxraw;
+    pv.xrawd = P->dxrawd;
+    pv.tbl = P->dtbl;
+    pv.ntracer = ntracer;
+    pv.eta1_is_one = (mod_type1 == NGRTD_MOD_EXPONENTIAL);
+    pv.eta2_is_one = (mod_type2 == NGRTD_MOD_EXPONENTIAL);
+    pv.default_log10J = std::log10(j_flux(1., 2700, 1000, 3.0, 10.0, 0.05));   // run_age_mcmc_utils.py:90-91
+    *out = P;
+    return NGRTD_OK;
+}
+
+extern "C" int ngrtd_plan_destroy(ngrtd_plan* P) {
+    if (!P) return NGRTD_OK;
+    cudaFree(P->dXf); cudaFree(P->dXd); cudaFree(P->ditp); cudaFree(P->dxraw); cudaFree(P->dxrawd);
+    cudaFree(P->dtbl); cudaFree(P->dcounter);
+    cudaFree(P->w_theta); cudaFree(P->w_out); cudaFree(P->w_logp); cudaFree(P->w_nu);
+    if (P->hstream) cudaStreamDestroy(P->hstream);
+    delete P;
+    return NGRTD_OK;
+}
+
+extern "C" int ngrtd_plan_ntracer(const ngrtd_plan* P) { return P ? P->pv.ntracer : NGRTD_EINVAL; }
+
+// ------------------------------------------------------------------------------------------- forward dispatch
+struct FwdTune { int warps, nt, ua; };
+
+static FwdTune env_tune() {
+    auto geti = [](const char* k) { const char* v = getenv(k); return v ? atoi(v) : 0; };
+    return FwdTune{geti("NGRTD_FWD_WARPS"), geti("NGRTD_FWD_NT"), geti("NGRTD_FWD_UA")};
+}
+
+static int pick_warps(long long nunits, int nsm, int maxw) {
+    // static schedule: what matters is warps per sub-partition; use the maximum the register budget allows
+    // unless there are fewer units than warps.
+    long long per_cta = (nunits + nsm - 1) / nsm;
+    int w = maxw;
+    while (w > 4 && (long long)(w - 4) >= per_cta) w -= 4;
+    if (per_cta < 4) w = (int)std::max<long long>(1, per_cta);
+    return w;
+}
+
+template <int C1, int C2, bool DYN, int NT, int UA, int MAXW>
+static int launch_forward_t(ngrtd_plan* P, const SlotMap& sm, const double* theta, long long B, double* out,
+                            double* logp, const LikPar& lik, cudaStream_t st, int warps_req) {
+    using WT = WarpTiles<C1, C2, DYN, NT, UA>;
+    int lc_cap = WT::ANY_LOOP ? std::min(P->Lpad, LC_MAX) : 0;
+    long long nunits = (B + NT * 8 - 1) / (NT * 8);
+    int warps = warps_req > 0 ? std::min(warps_req, MAXW) : pick_warps(nunits, P->nsm, MAXW);
+    if (warps > 4) warps &= ~3;
+    size_t sh = (size_t)TBL_DOUBLES + (size_t)warps * NT * 8 * NCOL;
+    sh += (size_t)lc_cap * NCOL;
+    if (WT::ANY_D) sh += (size_t)lc_cap * NCOL + lc_cap;
+    if (DYN) sh += lc_cap + (WT::ANY_D ? lc_cap : 0);
+    sh *= sizeof(double);
+    auto kern = k_forward<C1, C2, DYN, NT, UA, MAXW>;
+    static thread_local size_t configured = 0;
+    if (configured < sh) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        configured = sh;
+    }
+    long long want = (nunits + warps - 1) / warps;
+    int grid = (int)std::min<long long>(want, P->nsm);
+    if (grid < 1) grid = 1;
+    kern<<<grid, warps * 32, sh, st>>>(P->pv, sm, theta, B, out, logp, lik, lc_cap);
+    CUDA_TRY(cudaGetLastError());
+    return NGRTD_OK;
+}
+
+constexpr int FWD_NT = 2, FWD_UA = 1, FWD_MAXW = 16;
+
+template <int C1, int C2, bool DYN>
+static int launch_forward(ngrtd_plan* P, const SlotMap& sm, const double* theta, long long B, double* out,
+                          double* logp, const LikPar& lik, cudaStream_t st) {
+    FwdTune t = env_tune();
+#ifdef NGRTD_TUNE
+    // development build: every (NT, UA) variant of the looped kernels is compiled and selectable by env var
+    if constexpr (!DYN && C1 != CLS_P && C2 != CLS_P) {
+        int mw = (t.warps > 8) ? 16 : 8;
+#define NGRTD_VARIANT(NT_, UA_, MW_) \
+        if (t.nt == NT_ && t.ua == UA_ && mw == MW_) return launch_forward_t<C1, C2, DYN, NT_, UA_, MW_>(P, sm, theta, B, out, logp, lik, st, t.warps);
+        NGRTD_VARIANT(1, 2, 8) NGRTD_VARIANT(2, 1, 8) NGRTD_VARIANT(2, 2, 8) NGRTD_VARIANT(4, 1, 8)
+        NGRTD_VARIANT(1, 1, 16) NGRTD_VARIANT(1, 2, 16) NGRTD_VARIANT(2, 2, 16) NGRTD_VARIANT(3, 1, 16)
+#undef NGRTD_VARIANT
+    }
+#endif
+    return launch_forward_t<C1, C2, DYN, FWD_NT, FWD_UA, FWD_MAXW>(P, sm, theta, B, out, logp, lik, st, t.warps);
+}
+
+template <int C1, bool DYN>
+static int dispatch_c2(ngrtd_plan* P, const SlotMap& sm, const double* theta, long long B, double* out, double* logp,
+                       const LikPar& lik, cudaStream_t st) {
+#ifdef NGRTD_EXP   /* timing-experiment build: only the three looped kernels of the benchmark */
+    if (P->cls2 == CLS_NONE) return launch_forward<C1, CLS_NONE, DYN>(P, sm, theta, B, out, logp, lik, st);
+    if constexpr (C1 == CLS_G) if (P->cls2 == CLS_D) return launch_forward<C1, CLS_D, DYN>(P, sm, theta, B, out, logp, lik, st);
+    return fail(NGRTD_EINVAL, "experiment build: model pair not compiled");
+#else
+    switch (P->cls2) {
+        case CLS_NONE: return launch_forward<C1, CLS_NONE, DYN>(P, sm, theta, B, out, logp, lik, st);
+        case CLS_P: return launch_forward<C1, CLS_P, DYN>(P, sm, theta, B, out, logp, lik, st);
+        case CLS_G: return launch_forward<C1, CLS_G, DYN>(P, sm, theta, B, out, logp, lik, st);
+        case CLS_D: return launch_forward<C1, CLS_D, DYN>(P, sm, theta, B, out, logp, lik, st);
+    }
+    return fail(NGRTD_EINVAL, "bad model class");
+#endif
+}
+
+template <bool DYN>
+static int dispatch_c1(ngrtd_plan* P, const SlotMap& sm, const double* theta, long long B, double* out, double* logp,
+                       const LikPar& lik, cudaStream_t st) {
+    switch (P->cls1) {
+#ifdef NGRTD_EXP
+        case CLS_P: return fail(NGRTD_EINVAL, "experiment build: model pair not compiled");
+#else
+        case CLS_P: return dispatch_c2<CLS_P, DYN>(P, sm, theta, B, out, logp, lik, st);
+#endif
+        case CLS_G: return dispatch_c2<CLS_G, DYN>(P, sm, theta, B, out, logp, lik, st);
+        case CLS_D: return dispatch_c2<CLS_D, DYN>(P, sm, theta, B, out, logp, lik, st);
+    }
+    return fail(NGRTD_EINVAL, "bad model class");
+}
+
+static int make_slotmap(SlotMap& sm, int ndim, const int32_t* slot_of_col, bool dyn) {
+    if (ndim < 1 || ndim > 32 || !slot_of_col) return fail(NGRTD_EINVAL, "theta: ndim must be in 1..32 with a slot map");
+    sm.ndim = ndim;
+    for (int s = 0; s < NSLOT; s++) sm.col_of_slot[s] = -1;
+    for (int i = 0; i < ndim; i++) {
+        int s = slot_of_col[i];
+        if (s < 0 || s >= NSLOT) return fail(NGRTD_EINVAL, "theta: unknown parameter slot " + std::to_string(s));
+        sm.col_of_slot[s] = (signed char)i;
+    }
+    if (sm.col_of_slot[NGRTD_P_TAU1] < 0) return fail(NGRTD_EINVAL, "theta: tau1 is required");
+    (void)dyn;
+    return NGRTD_OK;
+}
+
+static int forward_common(ngrtd_plan* P, const double* theta, long long B, int ndim, const int32_t* slot_of_col,
+                          double* out, double* logp, const LikPar& lik, cudaStream_t st) {
+    if (!P) return fail(NGRTD_EINVAL, "null plan");
+    if (B < 0) return fail(NGRTD_EINVAL, "B < 0");
+    if (B == 0) return NGRTD_OK;
+    if (!theta) return fail(NGRTD_EINVAL, "theta is null");
+    SlotMap sm;
+    int rc = make_slotmap(sm, ndim, slot_of_col, P->dyn);
+    if (rc) return rc;
+    // the per-chain-lambda path is only needed when thalf_cfc is actually sampled (run_age_mcmc_utils.py:107:
+    // `'thalf_cfc' in self.p_names`); otherwise those tracers fall back to lambda = 0 through the same path.
+#ifndef NGRTD_EXP
+    if (P->dyn) return dispatch_c1<true>(P, sm, theta, B, out, logp, lik, st);
+#endif
+    return dispatch_c1<false>(P, sm, theta, B, out, logp, lik, st);
+}
+
+extern "C" int ngrtd_forward_dev(ngrtd_plan* P, const double* theta_d, int64_t B, int32_t ndim,
+                                 const int32_t* slot_of_col, double* out_d, void* stream) {
+    if (!out_d) return fail(NGRTD_EINVAL, "out is null");
+    LikPar lik{};
+    lik.kind = -1;
+    return forward_common(P, theta_d, B, ndim, slot_of_col, out_d, nullptr, lik, (cudaStream_t)stream);
+}
+
+static int fill_lik(LikPar& lik, const ngrtd_plan* P, int kind, const double* obs_mu, const double* obs_sd,
+                    const double* nu_d) {
+    if (kind != NGRTD_LIK_NORMAL && kind != NGRTD_LIK_STUDENTT) return fail(NGRTD_EINVAL, "unknown likelihood kind");
+    if (!obs_mu || !obs_sd) return fail(NGRTD_EINVAL, "obs_mu / obs_sd is null");
+    if (kind == NGRTD_LIK_STUDENTT && !nu_d) return fail(NGRTD_EINVAL, "student-t needs nu");
+    lik.kind = kind;
+    for (int t = 0; t < MAX_TRACER; t++) {
+        lik.obs[t] = t < P->pv.ntracer ? obs_mu[t] : 0.0;
+        lik.sd[t] = t < P->pv.ntracer ? obs_sd[t] : 1.0;
+    }
+    lik.nu = nu_d;
+    return NGRTD_OK;
+}
+
+extern "C" int ngrtd_forward_loglik_dev(ngrtd_plan* P, const double* theta_d, int64_t B, int32_t ndim,
+                                        const int32_t* slot_of_col, int32_t lik_kind, const double* obs_mu,
+                                        const double* obs_sd, const double* nu_d, double* logp_d,
+                                        double* model_out_d, void* stream) {
+    if (!P) return fail(NGRTD_EINVAL, "null plan");
+    if (!logp_d) return fail(NGRTD_EINVAL, "logp is null");
+    LikPar lik{};
+    int rc = fill_lik(lik, P, lik_kind, obs_mu, obs_sd, nu_d);
+    if (rc) return rc;
+    return forward_common(P, theta_d, B, ndim, slot_of_col, model_out_d, logp_d, lik, (cudaStream_t)stream);
+}
+
+static int grow(double** p, size_t* have, size_t need) {
+    if (*have >= need) return NGRTD_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    cudaError_t e = cudaMalloc((void**)p, need * sizeof(double));
+    if (e != cudaSuccess) return fail(NGRTD_ENOMEM, std::string("workspace: ") + cudaGetErrorString(e));
+    *have = need;
+    return NGRTD_OK;
+}
+
+extern "C" int ngrtd_forward_host(ngrtd_plan* P, const double* theta_h, int64_t B, int32_t ndim,
+                                  const int32_t* slot_of_col, double* out_h) {
+    if (!P) return fail(NGRTD_EINVAL, "null plan");
+    if (!theta_h || !out_h) return fail(NGRTD_EINVAL, "null host buffer");
+    if (B <= 0) return B == 0 ? NGRTD_OK : fail(NGRTD_EINVAL, "B < 0");
+    CUDA_TRY(cudaSetDevice(P->device));
+    int rc;
+    if ((rc = grow(&P->w_theta, &P->w_theta_n, (size_t)B * ndim))) return rc;
+    if ((rc = grow(&P->w_out, &P->w_out_n, (size_t)B * P->pv.ntracer))) return rc;
+    cudaStream_t st = P->hstream;
+    CUDA_TRY(cudaMemcpyAsync(P->w_theta, theta_h, (size_t)B * ndim * sizeof(double), cudaMemcpyHostToDevice, st));
+    if ((rc = ngrtd_forward_dev(P, P->w_theta, B, ndim, slot_of_col, P->w_out, st))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_h, P->w_out, (size_t)B * P->pv.ntracer * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return NGRTD_OK;
+}
+
+extern "C" int ngrtd_forward_loglik_host(ngrtd_plan* P, const double* theta_h, int64_t B, int32_t ndim,
+                                         const int32_t* slot_of_col, int32_t lik_kind, const double* obs_mu,
+                                         const double* obs_sd, const double* nu_h, double* logp_h,
+                                         double* model_out_h) {
+    if (!P) return fail(NGRTD_EINVAL, "null plan");
+    if (!theta_h || !logp_h) return fail(NGRTD_EINVAL, "null host buffer");
+    if (B <= 0) return B == 0 ? NGRTD_OK : fail(NGRTD_EINVAL, "B < 0");
+    CUDA_TRY(cudaSetDevice(P->device));
+    int rc;
+    if ((rc = grow(&P->w_theta, &P->w_theta_n, (size_t)B * ndim))) return rc;
+    if ((rc = grow(&P->w_logp, &P->w_logp_n, (size_t)B))) return rc;
+    if (model_out_h && (rc = grow(&P->w_out, &P->w_out_n, (size_t)B * P->pv.ntracer))) return rc;
+    cudaStream_t st = P->hstream;
+    CUDA_TRY(cudaMemcpyAsync(P->w_theta, theta_h, (size_t)B * ndim * sizeof(double), cudaMemcpyHostToDevice, st));
+    const double* nu_d = nullptr;
+    if (lik_kind == NGRTD_LIK_STUDENTT) {
+        if (!nu_h) return fail(NGRTD_EINVAL, "student-t needs nu");
+        if ((rc = grow(&P->w_nu, &P->w_nu_n, (size_t)B))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(P->w_nu, nu_h, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, st));
+        nu_d = P->w_nu;
+    }
+    if ((rc = ngrtd_forward_loglik_dev(P, P->w_theta, B, ndim, slot_of_col, lik_kind, obs_mu, obs_sd, nu_d, P->w_logp,
+                                       model_out_h ? P->w_out : nullptr, st)))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(logp_h, P->w_logp, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (model_out_h)
+        CUDA_TRY(cudaMemcpyAsync(model_out_h, P->w_out, (size_t)B * P->pv.ntracer * sizeof(double),
+                                 cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return NGRTD_OK;
+}
+
+// ------------------------------------------------------------------------------------------- class-API helpers
+// gen_g_tp(): materialised, normalised weights -- one CTA per chain, direct per-lag formulae of the reference
+// (utils/convolution_integral_utils.py:178-196,270).  API-parity path (plots, g_tau=...), not the hot loop.
+__global__ void k_rtd_weights(int mod, int L, double dtp, const double* __restrict__ tau_, const double* __restrict__ eta_,
+                              const double* __restrict__ D_, double* __restrict__ g) {
+    const long long b = blockIdx.x;
+    const double tau = tau_[b];
+    const double eta = eta_ ? eta_[b] : 1.0;
+    const double D = D_ ? D_[b] : 0.0;
+    double* row = g + b * (long long)L;
+    __shared__ double red[32];
+    __shared__ int s_ix;
+    if (mod == NGRTD_MOD_PISTON) {
+        if (threadIdx.x == 0) {
+            Comp<CLS_P> c;
+            c.init(tau, 0.0, 0.0, dtp, L);
+            s_ix = c.ix;
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < L; k += blockDim.x) row[k] = (k == s_ix) ? 1.0 : 0.0;
+        return;
+    }
+    double part = 0.0;
+    const double thr = __dmul_rn(tau, __dsub_rn(1.0, __ddiv_rn(1.0, eta)));
+    for (int k = threadIdx.x; k < L; k += blockDim.x) {
+        double tp = ((k == 0) ? 1e-5 : (double)k) + dtp;
+        double w;
+        if (mod == NGRTD_MOD_EXPONENTIAL) {
+            w = (1.0 / tau) * exp(-tp / tau);
+        } else if (mod == NGRTD_MOD_EXP_PIST_FLOW) {
+            w = (tp >= thr) ? (eta / tau) * exp(-(eta * tp / tau) + eta - 1.0) : 0.0;
+        } else {
+            double x = tp / tau;
+            double f1 = (1.0 / tau) / sqrt(4.0 * 3.14159265358979323846 * D * x);
+            double om = 1.0 - x;
+            double f2 = (1.0 / x) * exp(-1.0 * ((om * om) / (4.0 * D * x)));
+            w = f1 * f2;
+        }
+        row[k] = w;
+        part += w;
+    }
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) red[0] = v;
+    }
+    __syncthreads();
+    const double S = red[0];
+    for (int k = threadIdx.x; k < L; k += blockDim.x) row[k] = row[k] / S;
+}
+
+extern "C" int ngrtd_rtd_weights_dev(int32_t mod_type, int32_t L, double dtp, const double* tau_d, const double* eta_d,
+                                     const double* D_d, int64_t B, double* g_d, void* stream) {
+    if (cls_of(mod_type) <= 0) return fail(NGRTD_EINVAL, "rtd_weights: unknown mod_type " + std::to_string(mod_type));
+    if (L < 1 || !tau_d || !g_d) return fail(NGRTD_EINVAL, "rtd_weights: bad arguments");
+    if (mod_type == NGRTD_MOD_EXP_PIST_FLOW && !eta_d) return fail(NGRTD_EINVAL, "rtd_weights: exp_pist_flow needs eta");
+    if (mod_type == NGRTD_MOD_DISPERSION && !D_d) return fail(NGRTD_EINVAL, "rtd_weights: dispersion needs D");
+    if (B <= 0) return B == 0 ? NGRTD_OK : fail(NGRTD_EINVAL, "B < 0");
+    k_rtd_weights<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(mod_type, L, dtp, tau_d,
+                                                                 mod_type == NGRTD_MOD_EXPONENTIAL ? nullptr : eta_d, D_d, g_d);
+    CUDA_TRY(cudaGetLastError());
+    return NGRTD_OK;
+}
+
+// convolve(g_tau=g) tail: decay/ingrowth (:313-316), input assembly (:320-333), dot (:336-337); one CTA per row
+__global__ void k_convolve_g(int L, double dtp, const double* __restrict__ g, const double* __restrict__ series,
+                             const double* __restrict__ lag_index, const double* __restrict__ lambda, int rad_accum,
+                             const double* __restrict__ J, double* __restrict__ out) {
+    const long long b = blockIdx.x;
+    const double* row = g + b * (long long)L;
+    const double lam = lambda ? lambda[b] : 0.0;
+    const double Jb = (J && rad_accum == NGRTD_ACC_4HE) ? J[b] : 0.0;
+    __shared__ double red[32];
+    double part = 0.0;
+    for (int k = threadIdx.x; k < L; k += blockDim.x) {
+        double tp = ((k == 0) ? 1e-5 : (double)k) + dtp;
+        double dec = exp(-lam * tp);
+        double gd = row[k] * (rad_accum == NGRTD_ACC_3HE ? (1 - dec) : dec);
+        double c = series[k];
+        if (rad_accum == NGRTD_ACC_4HE) c = c + (lag_index ? lag_index[k] : (double)k) * Jb;
+        part += c * gd;
+    }
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) out[b] = v;
+    }
+}
+
+extern "C" int ngrtd_convolve_g_dev(int32_t L, double dtp, const double* g_d, int64_t B, const double* series_d,
+                                    const double* lag_index_d, const double* lambda_d, int32_t rad_accum,
+                                    const double* J_d, double* out_d, void* stream) {
+    if (L < 1 || !g_d || !series_d || !out_d) return fail(NGRTD_EINVAL, "convolve_g: bad arguments");
+    if (rad_accum < 0 || rad_accum > 2) return fail(NGRTD_EINVAL, "convolve_g: unknown rad_accum");
+    if (B <= 0) return B == 0 ? NGRTD_OK : fail(NGRTD_EINVAL, "B < 0");
+    k_convolve_g<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(L, dtp, g_d, series_d, lag_index_d, lambda_d, rad_accum,
+                                                                J_d, out_d);
+    CUDA_TRY(cudaGetLastError());
+    return NGRTD_OK;
+}
+
+// ------------------------------------------------------------------------------------------- CE model
+static int make_gases(GasList& gl, int ngas, const int32_t* gases) {
+    if (ngas < 1 || ngas > 5 || !gases) return fail(NGRTD_EINVAL, "ce: ngas must be in 1..5");
+    gl.n = ngas;
+    for (int i = 0; i < ngas; i++) {
+        if (gases[i] < 0 || gases[i] > 4) return fail(NGRTD_EINVAL, "ce: gas id must be 0..4 (He,Ne,Ar,Kr,Xe)");
+        gl.id[i] = gases[i];
+    }
+    return NGRTD_OK;
+}
+
+extern "C" int ngrtd_ce_dev(int32_t what, int32_t ngas, const int32_t* gases, const double* E_d, const double* T_d,
+                            const double* Ae_d, const double* F_d, const double* P_d, double S, int64_t B,
+                            double* out_d, void* stream) {
+    GasList gl;
+    int rc = make_gases(gl, ngas, gases);
+    if (rc) return rc;
+    if (what < 0 || what > 4) return fail(NGRTD_EINVAL, "ce: unknown output selector");
+    if (!T_d || !out_d) return fail(NGRTD_EINVAL, "ce: T / out is null");
+    if (!P_d && !E_d && what != 4) return fail(NGRTD_EINVAL, "ce: need E (lapse rate) or P");
+    if (what <= 1 && (!Ae_d || !F_d)) return fail(NGRTD_EINVAL, "ce: ce_exc needs Ae and F");
+    if (B <= 0) return B == 0 ? NGRTD_OK : fail(NGRTD_EINVAL, "B < 0");
+    unsigned grid = (unsigned)((B + 127) / 128);
+    k_ce<<<grid, 128, 0, (cudaStream_t)stream>>>(what, gl, E_d, T_d, Ae_d, F_d, P_d, S, B, out_d);
+    CUDA_TRY(cudaGetLastError());
+    return NGRTD_OK;
+}
+
+extern "C" int ngrtd_ce_wrapper_dev(int32_t ngas, const int32_t* gases, const double* theta_d, int64_t B,
+                                    double* out_d, void* stream) {
+    GasList gl;
+    int rc = make_gases(gl, ngas, gases);
+    if (rc) return rc;
+    if (!theta_d || !out_d) return fail(NGRTD_EINVAL, "ce_wrapper: null pointer");
+    if (B <= 0) return B == 0 ? NGRTD_OK : fail(NGRTD_EINVAL, "B < 0");
+    unsigned grid = (unsigned)((B + 127) / 128);
+    k_ce_wrapper<<<grid, 128, 0, (cudaStream_t)stream>>>(gl, theta_d, B, out_d);
+    CUDA_TRY(cudaGetLastError());
+    return NGRTD_OK;
+}
+
+extern "C" int ngrtd_ce_host(int32_t what, int32_t ngas, const int32_t* gases, const double* E_h, const double* T_h,
+                             const double* Ae_h, const double* F_h, const double* P_h, double S, int64_t B,
+                             double* out_h) {
+    if (B <= 0) return B == 0 ? NGRTD_OK : fail(NGRTD_EINVAL, "B < 0");
+    if (!T_h || !out_h) return fail(NGRTD_EINVAL, "ce: T / out is null");
+    if (ngas < 1 || ngas > 5) return fail(NGRTD_EINVAL, "ce: ngas must be in 1..5");
+    double* buf = nullptr;
+    size_t n = (size_t)B;
+    CUDA_TRY(cudaMalloc((void**)&buf, (5 + ngas) * n * sizeof(double)));
+    const double* src[5] = {E_h, T_h, Ae_h, F_h, P_h};
+    double* dev[5];
+    for (int i = 0; i < 5; i++) {
+        dev[i] = src[i] ? buf + i * n : nullptr;
+        if (src[i]) {
+            cudaError_t e = cudaMemcpy(dev[i], src[i], n * sizeof(double), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { cudaFree(buf); return fail(NGRTD_ECUDA, cudaGetErrorString(e)); }
+        }
+    }
+    double* dout = buf + 5 * n;
+    int rc = ngrtd_ce_dev(what, ngas, gases, dev[0], dev[1], dev[2], dev[3], dev[4], S, B, dout, nullptr);
+    if (rc == NGRTD_OK) {
+        cudaError_t e = cudaMemcpy(out_h, dout, (size_t)ngas * n * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(NGRTD_ECUDA, cudaGetErrorString(e));
+    }
+    cudaFree(buf);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------- stand-alone loglik
+struct ObsPar { int T; double obs[16]; double sd[16]; };
+
+__global__ void k_loglik(int kind, ObsPar op, const double* __restrict__ mu, const double* __restrict__ nu,
+                         long long B, double* __restrict__ logp) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    double acc = 0.0;
+    if (kind == NGRTD_LIK_STUDENTT) {
+        double n = nu[i], cst = lik_studentt_const(n);
+        for (int t = 0; t < op.T; t++) acc += lik_term_studentt(op.obs[t], mu[i * op.T + t], op.sd[t], n, cst);
+    } else {
+        for (int t = 0; t < op.T; t++) acc += lik_term_normal(op.obs[t], mu[i * op.T + t], op.sd[t]);
+    }
+    logp[i] = acc;
+}
+
+extern "C" int ngrtd_loglik_dev(int32_t lik_kind, int32_t T, const double* mu_d, const double* obs_mu,
+                                const double* obs_sd, const double* nu_d, int64_t B, double* logp_d, void* stream) {
+    if (lik_kind != NGRTD_LIK_NORMAL && lik_kind != NGRTD_LIK_STUDENTT) return fail(NGRTD_EINVAL, "unknown likelihood kind");
+    if (T < 1 || T > 16) return fail(NGRTD_EINVAL, "loglik: T must be in 1..16");
+    if (!mu_d || !obs_mu || !obs_sd || !logp_d) return fail(NGRTD_EINVAL, "loglik: null pointer");
+    if (lik_kind == NGRTD_LIK_STUDENTT && !nu_d) return fail(NGRTD_EINVAL, "student-t needs nu");
+    if (B <= 0) return B == 0 ? NGRTD_OK : fail(NGRTD_EINVAL, "B < 0");
+    ObsPar op;
+    op.T = T;
+    for (int t = 0; t < 16; t++) { op.obs[t] = t < T ? obs_mu[t] : 0.0; op.sd[t] = t < T ? obs_sd[t] : 1.0; }
+    unsigned grid = (unsigned)((B + 127) / 128);
+    k_loglik<<<grid, 128, 0, (cudaStream_t)stream>>>(lik_kind, op, mu_d, nu_d, B, logp_d);
+    CUDA_TRY(cudaGetLastError());
+    return NGRTD_OK;
+}

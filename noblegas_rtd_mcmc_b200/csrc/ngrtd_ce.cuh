@@ -1,0 +1,98 @@
+// ngrtd_ce.cuh -- closed-equilibrium noble-gas model (K3), one chain per thread.
+// Restates utils/noble_gas_utils.py:103-253 of the reference (lapse_rate, solubility, vapor_pressure,
+// equil_conc, equil_conc_dry, ce_exc) with the same operation order so results agree to a few ulp.
+#pragma once
+#include "ngrtd_common.cuh"
+
+namespace ngrtd {
+
+// gas ids: 0 He, 1 Ne, 2 Ar, 3 Kr, 4 Xe
+__constant__ double c_atm_std[5] = {5.24e-6, 1.818e-5, 9.34e-3, 1.14e-6, 8.7e-8};   // noble_gas_utils.py:38-49
+__constant__ double c_sol[5][4] = {{-0.00953, 0.107722, 0.001969, -0.043825},        // :138-142
+                                   {-7.259, 6.95, -1.3826, 0.0538},
+                                   {-9.52, 8.83, -1.8959, 0.0698},
+                                   {-6.292, 5.612, -0.8881, -0.0458},
+                                   {-3.902, 2.439, 0.3863, -0.221}};
+__constant__ double c_setch[5][3] = {{-10.081, 15.1068, 4.8127},                     // :145-149
+                                     {-11.9556, 18.4062, 5.5464},
+                                     {-10.6951, 16.7513, 4.9551},
+                                     {-9.9787, 15.7619, 4.6181},
+                                     {-14.5524, 22.5255, 6.7513}};
+
+__device__ __forceinline__ double ce_lapse_rate(double E) {   // :112
+    return pow(1.0 - .0065 * E / 288.15, 5.2561) * 0.000101325;
+}
+
+__device__ __forceinline__ double ce_poly(const double* A, double T_k) {   // A0 + A1/t + A2/t^2 + A3/t^3, t = .001 T_k
+    double t = .001 * T_k;
+    return A[0] + (A[1] / t) + (A[2] / (t * t)) + (A[3] / (t * t * t));
+}
+
+__device__ __forceinline__ double ce_solubility(int gas, double T, double S) {   // :117-180
+    double T_k = T + 273.15;
+    double gamma = 1.0;
+    if (T < 65.0) {
+        double setch = c_setch[gas][0] + (c_setch[gas][1] / (.01 * T_k)) + (c_setch[gas][2] * log(.01 * T_k));
+        gamma = exp(S * setch);
+    }
+    double K_h;
+    if (gas == 0) {
+        double F = exp(ce_poly(c_sol[0], T_k));
+        double Frac_He_gas = 5.24e-6 / 9.31e-3;
+        double X_Ar_water = 1.0 / exp(ce_poly(c_sol[2], T_k)) * 9.31e-3;
+        double X_he_water = F * Frac_He_gas * X_Ar_water;
+        K_h = 5.24e-6 / X_he_water;
+    } else {
+        K_h = exp(ce_poly(c_sol[gas], T_k));
+    }
+    return gamma * K_h;
+}
+
+__device__ __forceinline__ double ce_vapor_pressure(double T) {   // :184-199
+    double A, Bc, C;
+    if (T <= 99.0) { A = 8.07131; Bc = 1730.63; C = 233.426; }
+    else { A = 8.14019; Bc = 1810.94; C = 244.485; }
+    double P = exp10(A - (Bc / (C + T)));
+    P = P / 760. * 101325;
+    return P / 1.0e9;
+}
+
+// what: 0 ce_exc(True), 1 ce_exc(False), 2 equil_conc_dry, 3 equil_conc (wet), 4 solubility
+__device__ __forceinline__ double ce_eval(int what, int gas, double E, double T, double Ae, double F, double P,
+                                          double S) {
+    double K = ce_solubility(gas, T, S);
+    if (what == 4) return K;
+    double z = c_atm_std[gas];
+    if (what == 3) return (z * P / K) * (22414. / 18.);                        // :209-211
+    double pv = ce_vapor_pressure(T);
+    double p_i = z * (P - pv);                                                  // :225
+    double C_eq = (T < 0.0) ? -9999.0 : (p_i / K) * (22414. / 18.);            // :226-230
+    if (what == 2) return C_eq;
+    double C_ex = ((1 - F) * Ae * z) / (1 + ((F * Ae * z) / C_eq));            // :248
+    return what == 0 ? C_ex + C_eq : C_ex;
+}
+
+struct GasList { int n; int id[5]; };
+
+__global__ void k_ce(int what, GasList gl, const double* __restrict__ E, const double* __restrict__ T,
+                     const double* __restrict__ Ae, const double* __restrict__ F, const double* __restrict__ P,
+                     double S, long long B, double* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    double e = E ? E[i] : 0.0, t = T[i];
+    double ae = Ae ? Ae[i] : 0.0, f = F ? F[i] : 0.0;
+    double p = P ? P[i] : ce_lapse_rate(e);
+    for (int g = 0; g < gl.n; g++) out[i * gl.n + g] = ce_eval(what, gl.id[g], e, t, ae, f, p, S);
+}
+
+// ce_exc_wrapper (ng_interp/noble_gas_mcmc.py:205-213): theta = [log10 Ae, log10 F, E, T]
+__global__ void k_ce_wrapper(GasList gl, const double* __restrict__ theta, long long B, double* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    double ae = exp10(theta[i * 4 + 0]), f = exp10(theta[i * 4 + 1]);
+    double e = theta[i * 4 + 2], t = theta[i * 4 + 3];
+    double p = ce_lapse_rate(e);
+    for (int g = 0; g < gl.n; g++) out[i * gl.n + g] = ce_eval(0, gl.id[g], e, t, ae, f, p, 0.0);
+}
+
+}  // namespace ngrtd

@@ -1,0 +1,136 @@
+// ngrtd_common.cuh -- shared constants, device-side plan view and small device helpers.
+// sm_100a only.  See DESIGN.md for the data layout and the roofline of each kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace ngrtd {
+
+constexpr int NCOL = 8;                 // folded input columns per lag: col 0 = ones (normalisation), 1..7 tracers
+constexpr int NSLOT = 11;               // ForwardMod.p_dict slots
+constexpr int MAX_TRACER = 8;
+constexpr int LC_MAX = 1024;            // lags resident in shared memory per chunk
+
+// table-driven exp(): exp(e) = 2^(n/32) * p(r),  n = rint(e*32/ln2),  |r| <= ln2/64.
+// The 32-entry table is stored as two 32-bit arrays (high / low words): any 32-lane gather from a 128-byte
+// array is bank-conflict free (one 4-byte slot per bank, equal slots broadcast), so a lookup costs exactly two
+// shared-memory wavefronts.  (A 2048-entry double table measured 8 wavefronts per lookup and made the kernel
+// LSU-bound: profiles/r1_notes.md.)
+constexpr int TBL_BITS = 5;
+constexpr int TBL_N = 1 << TBL_BITS;
+constexpr int TBL_DOUBLES = TBL_N;      // shared-memory footprint in doubles (hi[32] + lo[32] as uint32)
+constexpr double LN2 = 0.693147180559945309417232121458;
+constexpr double EXP_K = TBL_N / LN2;
+constexpr double EXP_C1 = LN2 / TBL_N;
+constexpr double EXP_C2 = EXP_C1 * EXP_C1 / 2.0;
+constexpr double EXP_C3 = EXP_C1 * EXP_C1 * EXP_C1 / 6.0;
+constexpr double EXP_C4 = EXP_C1 * EXP_C1 * EXP_C1 * EXP_C1 / 24.0;
+constexpr int EXP_NMIN = -1022 * TBL_N;             // below 2^-1022: flush to zero (see DESIGN.md "underflow")
+
+enum Cls : int { CLS_NONE = 0, CLS_P = 1, CLS_G = 2, CLS_D = 3 };
+
+struct TracerDev {
+    int col_a;   // folded series column (or -1)
+    int col_b;   // folded lag-index column for '4He' (or -1)
+    int dyn;     // 1: per-chain lambda (thalf_cfc) -> uses the dyn accumulators
+    int sf6;     // 1: *= 1 + lamsf6
+};
+
+// Device view of a plan (passed by value to kernels).
+struct PlanView {
+    int L;          // true number of lags
+    int Lpad;       // padded to a multiple of 4 (pad rows are zero)
+    double dtp;     // integer-valued shift of the lag grid
+    const double* Xf;     // [Lpad, 8] folded columns
+    const double* Xd;     // [Lpad, 8] Xf * tp^-1.5 (dispersion component)
+    const double* itp;    // [Lpad] 1/tp (pad: 0)
+    const double* xraw;   // [Lpad] raw series of the per-chain-lambda tracer
+    const double* xrawd;  // [Lpad] xraw * tp^-1.5
+    const double* tbl;    // [32] doubles = hi[32], lo[32] words of 2^(j/32)
+    int ntracer;
+    TracerDev tr[MAX_TRACER];
+    int eta1_is_one, eta2_is_one;   // 'exponential' == exp_pist_flow with eta = 1 (bit-identical in the reference)
+    double default_log10J;          // run_age_mcmc_utils.py:90-91
+};
+
+struct SlotMap {
+    int ndim;
+    signed char col_of_slot[NSLOT];   // -1: not in par_names -> p_dict default
+};
+
+struct ChainPar {
+    double tau1, tau2, f1, f2, eta1, eta2, D1, D2, Jlin, lam_cfc, lamsf6;
+};
+
+__device__ __forceinline__ ChainPar load_chain_par(const double* __restrict__ theta, const SlotMap& sm,
+                                                   long long chain, const PlanView& pv, bool need_J) {
+    const double* row = theta + chain * sm.ndim;
+    auto get = [&](int slot, double dflt) -> double {
+        int c = sm.col_of_slot[slot];
+        return c >= 0 ? row[c] : dflt;
+    };
+    ChainPar p;
+    p.tau1 = get(0, 0.0);
+    p.tau2 = get(1, 0.0);     // p_dict default 0.0
+    p.f1 = get(2, 1.0);       // default 1.0
+    p.f2 = get(3, 0.0);       // default 0.0
+    p.eta1 = pv.eta1_is_one ? 1.0 : get(4, 0.0);
+    p.eta2 = pv.eta2_is_one ? 1.0 : get(5, 0.0);
+    p.D1 = get(6, 0.0);
+    p.D2 = get(7, 0.0);
+    p.Jlin = 0.0;
+    if (need_J) p.Jlin = exp10(get(8, pv.default_log10J));       // J = 10**p_dict['J'] (:101)
+    {
+        int c = sm.col_of_slot[9];
+        p.lam_cfc = c >= 0 ? (LN2 / row[c]) : 0.0;               // thalf_2_lambda (:146-152)
+    }
+    p.lamsf6 = get(10, 0.0);   // False -> x(1+0)
+    return p;
+}
+
+// exp(e) for e <= ~0 given ep = e * 32/ln2.  FP64-pipe cost: 1 DADD + 4 DFMA + 1 DMUL; rounding and its inverse
+// run on the conversion unit (F2I/I2F); degree-4 Taylor in r (truncation <= 1.3e-12 relative).
+// tbl points at hi'[32] (uint32) followed by lo[32] (uint32), hi'[j] = hi(2^(j/32)) - (j << 15), so that the
+// exponent insertion is ONE integer multiply-add:  hi'[j] + n*2^15 = hi[j] + ((n >> 5) << 20).
+// n is clamped at EXP_NMIN (result 2^-1022 * p, i.e. ~2e-308) instead of flushing to zero: one IMNMX instead of
+// a compare and two selects.  Chains whose largest weight would be below 2^-1022 are declared dead (NaN) in
+// Comp<CLS_D>::init, which reproduces the reference's 0/0 = NaN when every weight underflows.
+__device__ __forceinline__ double exp_scaled(double ep, const double* __restrict__ tbl) {
+    const unsigned int* th = reinterpret_cast<const unsigned int*>(tbl);
+#if defined(NGRTD_EXP) && NGRTD_EXP == 1   /* timing experiment: magic-number rounding instead of F2I/I2F */
+    double tm = fmax(ep, -2.0e6) + 6755399441055744.0;
+    int n = __double2loint(tm);
+    double r = ep - (tm - 6755399441055744.0);
+#else
+    int n = __double2int_rn(ep);                 // saturates; NaN -> 0
+    double r = ep - __int2double_rn(n);
+#endif
+#if defined(NGRTD_EXP) && NGRTD_EXP == 2   /* timing experiment: degree-2 polynomial */
+    double p = fma(r, fma(r, EXP_C2, EXP_C1), 1.0);
+#else
+    double p = fma(r, fma(r, fma(r, fma(r, EXP_C4, EXP_C3), EXP_C2), EXP_C1), 1.0);
+#endif
+    int nc = max(n, EXP_NMIN);
+    int off = (nc << 2) & ((TBL_N - 1) << 2);    // byte offset of the table slot
+    const char* tb = reinterpret_cast<const char*>(th);
+#if defined(NGRTD_EXP) && NGRTD_EXP == 3   /* timing experiment: no table gather */
+    int hi = 0x3ff00000 + nc * 32768;
+    return __hiloint2double(hi, off) * p;
+#else
+    int hi = (int)*reinterpret_cast<const unsigned int*>(tb + off) + nc * 32768;
+    int lo = (int)*reinterpret_cast<const unsigned int*>(tb + off + TBL_N * 4);
+    return __hiloint2double(hi, lo) * p;
+#endif
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+#if defined(NGRTD_EXP) && NGRTD_EXP == 4   /* timing experiment: no DMMA */
+    c0 += a; c1 = fma(a, b, c1); return;
+#endif
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+}  // namespace ngrtd

@@ -1,0 +1,478 @@
+// ngrtd_forward.cuh -- fused RTD-weight generation (K1) + lag-axis reduction (K2) + mixing/likelihood epilogue.
+//
+// Restates (as a different algorithm, same arithmetic result to ~1e-13):
+//   utils/convolution_integral_utils.py:168-196,270   gen_g_tp   (weights, normalisation)
+//   utils/convolution_integral_utils.py:300-340       convolve   (decay/ingrowth, 4He input, dot)
+//   age_ens_runs_mcmc/run_age_mcmc_utils.py:81-163    ForwardMod.perform (two components, f1/f2, SF6/CFC rules)
+//
+// Mapping to the machine:
+//   out[chain, col] = sum_k W[chain, k] * X[k, col] is a skinny GEMM (N = 8 folded columns shared by all
+//   chains, K = lags).  tcgen05 has no FP64 kind, so the reduction runs on the FP64 pipe as
+//   mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4): one warp instruction = 8 chains x 4 lags x 8 columns.  Lane
+//   (r = lane>>2, j = lane&3) GENERATES the weight of chain r at lag 4g+j in registers (A fragment), loads
+//   X[4g+j][r] from shared memory (B fragment, conflict-free 256 B row group), and owns output columns
+//   2j, 2j+1 of chain r (C fragment).  Weights never touch memory.
+//     * exponential / exp_pist_flow: geometric recurrence v <- v*r^4, re-anchored by a true exp() at every
+//       chunk start; the mask tp >= tau(1-1/eta) is an integer compare against k0.
+//     * dispersion: w = tp^-1.5 * exp(-(1-x)^2/(4Dx)); the tp^-1.5 factor is folded into a second copy of X
+//       (Xd), the exponent is two FMAs on per-lag tables, exp() is the table-driven exp_scaled().
+//     * piston: a gather of one row of X in the epilogue.
+//   Normalisation sum = column 0 (ones) of the same MMA.
+#pragma once
+#include "ngrtd_common.cuh"
+
+namespace ngrtd {
+
+struct SmemView {
+    double* Xf;
+    double* Xd;
+    double* itp;
+    double* xraw;
+    double* xrawd;
+    double* tbl;
+    double* scratch;   // [warps][NT][8 chains][8 cols]
+};
+
+struct LikPar {
+    int kind;                  // -1 none, 0 normal, 1 student-t
+    double obs[MAX_TRACER];
+    double sd[MAX_TRACER];
+    const double* nu;          // [B] (student-t)
+};
+
+// ---------------------------------------------------------------- per-component lane state
+template <int CLS>
+struct Comp {};
+
+template <>
+struct Comp<CLS_NONE> {
+    __device__ __forceinline__ void init(double, double, double, double, int) {}
+};
+
+template <>
+struct Comp<CLS_P> {
+    int ix;
+    __device__ __forceinline__ void init(double tau, double, double, double dtp, int L) {
+        // argmin_k |tp_k - tau| with tp_0 = 1e-5 + dtp, tp_k = k + dtp; first index wins ties (numpy argmin)
+        double s = tau - dtp;
+        if (s >= 1.0) {
+            double n = ceil(s - 0.5);
+            n = fmin(n, (double)(L - 1));
+            ix = (int)n;
+        } else {
+            double d0 = fabs((1e-5 + dtp) - tau);
+            double d1 = fabs((1.0 + dtp) - tau);
+            ix = (L > 1 && !(d0 <= d1) && d1 == d1) ? 1 : 0;
+        }
+    }
+};
+
+template <>
+struct Comp<CLS_G> {
+    double v, r4, er, tpk0;
+    int k0;
+    __device__ __forceinline__ void init(double tau, double eta, double, double dtp, int) {
+        // mask threshold with the reference's operation order and roundings (conv utils :189)
+        double thr = __dmul_rn(tau, __dsub_rn(1.0, __ddiv_rn(1.0, eta)));
+        double tp0 = 1e-5 + dtp;
+        if (thr <= tp0) {
+            k0 = 0;
+        } else {
+            double c = ceil(thr - dtp);
+            k0 = (c >= 1073741824.0) ? 1073741824 : max(1, (int)c);
+        }
+        tpk0 = (k0 == 0) ? tp0 : (double)k0 + dtp;
+        er = eta / tau;
+        r4 = exp(-4.0 * er);
+        v = 0.0;
+    }
+    // direct evaluation at lag k (first group of a chunk); primes the recurrence for lag k+4
+    __device__ __forceinline__ double first(int k, double dtp) {
+        double vk = exp(-er * (((double)k + dtp) - tpk0));
+        v = vk * r4;
+        return (k >= k0) ? ((k == 0) ? 1.0 : vk) : 0.0;
+    }
+    __device__ __forceinline__ double next(int k) {
+        double w = (k >= k0) ? v : 0.0;
+        v *= r4;
+        return w;
+    }
+};
+
+template <>
+struct Comp<CLS_D> {
+    double ap, bp, cp, u;
+    __device__ __forceinline__ void init(double tau, double, double D, double dtp, int L) {
+        bool ok = (tau > 0.0) && (D > 0.0);
+        double i4D = 1.0 / (4.0 * D);
+        // e = -(1-x)^2/(4Dx), x = tp/tau  ==  -(tau/4D)/tp + 1/(2D) - tp/(4D tau); pre-scaled by 32/ln2
+        ap = -EXP_K * tau * i4D;
+        bp = -EXP_K * i4D / tau;
+        cp = EXP_K * 2.0 * i4D;
+        u = 0.0;
+        // Largest exponent over the lag grid: e(x) peaks (e = 0) at x = 1; if tau lies beyond the last lag the
+        // maximum is at the last lag.  Below 2^-1022 every reference weight is (sub)denormal or exactly zero and
+        // g/g.sum() is NaN or precision-less: the chain is declared dead -> NaN output.
+        double tpl = (double)(L - 1) + dtp + ((L == 1) ? 1e-5 : 0.0);
+        if (ok && tau > tpl) {
+            double emax = fma(ap, 1.0 / tpl, fma(bp, tpl, cp));
+            ok = emax >= (double)EXP_NMIN;
+        }
+        if (!ok) ap = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    __device__ __forceinline__ double first(int k, double dtp, double itpk, const double* tbl) {
+        double tp = ((k == 0) ? 1e-5 : (double)k) + dtp;
+        double w = exp_scaled(fma(ap, itpk, fma(bp, tp, cp)), tbl);
+        u = fma(bp, (double)(k + 4) + dtp, cp);
+        return w;
+    }
+    __device__ __forceinline__ double next(double itpk, const double* tbl) {
+        double w = exp_scaled(fma(ap, itpk, u), tbl);
+        u = fma(bp, 4.0, u);
+        return w;
+    }
+};
+
+// ---------------------------------------------------------------- one warp = NT tiles of 8 chains
+template <int C1, int C2, bool DYN, int NT, int UA>
+struct WarpTiles {
+    static constexpr bool LOOP1 = (C1 == CLS_G || C1 == CLS_D);
+    static constexpr bool LOOP2 = (C2 == CLS_G || C2 == CLS_D);
+    static constexpr bool ANY_LOOP = LOOP1 || LOOP2;
+    static constexpr bool ANY_D = (C1 == CLS_D || C2 == CLS_D);
+    static constexpr bool ANY_G = (C1 == CLS_G || C2 == CLS_G);
+
+    Comp<C1> c1[NT];
+    Comp<C2> c2[NT];
+    double a1[NT][UA][2], a2[NT][UA][2];   // UA independent DMMA accumulator chains per tile and component
+    double dv[NT], d4[NT], lam[NT], ad1[NT], ad2[NT];
+
+    __device__ __forceinline__ void begin(const ChainPar (&p)[NT], const PlanView& pv) {
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+            c1[t].init(p[t].tau1, p[t].eta1, p[t].D1, pv.dtp, pv.L);
+            c2[t].init(p[t].tau2, p[t].eta2, p[t].D2, pv.dtp, pv.L);
+#pragma unroll
+            for (int u = 0; u < UA; u++) a1[t][u][0] = a1[t][u][1] = a2[t][u][0] = a2[t][u][1] = 0.0;
+            if (DYN) {
+                lam[t] = p[t].lam_cfc;
+                d4[t] = exp(-4.0 * lam[t]);
+                dv[t] = 0.0;
+                ad1[t] = ad2[t] = 0.0;
+            }
+        }
+    }
+
+    // accumulate lags [kc, kc + 4*ngroups); shared memory holds that range at local index 0
+    __device__ __forceinline__ void chunk(const SmemView& s, const PlanView& pv, int kc, int ngroups, int lane) {
+        if (!ANY_LOOP) return;
+        const int j = lane & 3, r = lane >> 2;
+        int k = kc + j;
+        const double* pf = s.Xf + j * NCOL + r;
+        const double* pd = s.Xd + j * NCOL + r;
+        const double* pi = s.itp + j;
+        const double* px = s.xraw + j;
+        const double* pxd = s.xrawd + j;
+        const double dtp = pv.dtp;
+        {   // first group of the chunk: direct evaluation (handles tp_0 = 1e-5 and re-anchors the recurrences)
+            double bf = pf[0];
+            double bd = ANY_D ? pd[0] : 0.0;
+            double it = ANY_D ? pi[0] : 0.0;
+            double xr = DYN ? px[0] : 0.0;
+            double xrd = (DYN && ANY_D) ? pxd[0] : 0.0;
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+                double w1 = 0.0, w2 = 0.0;
+                if constexpr (C1 == CLS_G) { w1 = c1[t].first(k, dtp); dmma884(a1[t][0][0], a1[t][0][1], w1, bf); }
+                if constexpr (C1 == CLS_D) { w1 = c1[t].first(k, dtp, it, s.tbl); dmma884(a1[t][0][0], a1[t][0][1], w1, bd); }
+                if constexpr (C2 == CLS_G) { w2 = c2[t].first(k, dtp); dmma884(a2[t][0][0], a2[t][0][1], w2, bf); }
+                if constexpr (C2 == CLS_D) { w2 = c2[t].first(k, dtp, it, s.tbl); dmma884(a2[t][0][0], a2[t][0][1], w2, bd); }
+                if constexpr (DYN) {
+                    double dvk = exp(-lam[t] * ((double)k + dtp));
+                    double du = (k == 0) ? exp(-lam[t] * (1e-5 + dtp)) : dvk;
+                    dv[t] = dvk * d4[t];
+                    if constexpr (LOOP1) ad1[t] = fma(w1 * du, (C1 == CLS_D) ? xrd : xr, ad1[t]);
+                    if constexpr (LOOP2) ad2[t] = fma(w2 * du, (C2 == CLS_D) ? xrd : xr, ad2[t]);
+                }
+            }
+        }
+        // steady state: UA groups per iteration, each group feeding its own accumulator set so that
+        // consecutive DMMAs of one tile are independent (hides the DMMA dependent-issue latency)
+        int g = 1;
+        for (; g + UA <= ngroups; g += UA) {
+#pragma unroll
+            for (int u = 0; u < UA; u++) {
+                k += 4;
+                pf += 4 * NCOL;
+                double bf = pf[0];
+                double bd = 0.0, it = 0.0, xr = 0.0, xrd = 0.0;
+                if constexpr (ANY_D) { pd += 4 * NCOL; pi += 4; bd = pd[0]; it = pi[0]; }
+                if constexpr (DYN) { px += 4; xr = px[0]; if constexpr (ANY_D) { pxd += 4; xrd = pxd[0]; } }
+#pragma unroll
+                for (int t = 0; t < NT; t++) {
+                    double w1 = 0.0, w2 = 0.0;
+                    if constexpr (C1 == CLS_G) { w1 = c1[t].next(k); dmma884(a1[t][u][0], a1[t][u][1], w1, bf); }
+                    if constexpr (C1 == CLS_D) { w1 = c1[t].next(it, s.tbl); dmma884(a1[t][u][0], a1[t][u][1], w1, bd); }
+                    if constexpr (C2 == CLS_G) { w2 = c2[t].next(k); dmma884(a2[t][u][0], a2[t][u][1], w2, bf); }
+                    if constexpr (C2 == CLS_D) { w2 = c2[t].next(it, s.tbl); dmma884(a2[t][u][0], a2[t][u][1], w2, bd); }
+                    if constexpr (DYN) {
+                        double du = dv[t];
+                        dv[t] *= d4[t];
+                        if constexpr (LOOP1) ad1[t] = fma(w1 * du, (C1 == CLS_D) ? xrd : xr, ad1[t]);
+                        if constexpr (LOOP2) ad2[t] = fma(w2 * du, (C2 == CLS_D) ? xrd : xr, ad2[t]);
+                    }
+                }
+            }
+        }
+        for (; g < ngroups; g++) {   // remainder groups
+            k += 4;
+            pf += 4 * NCOL;
+            double bf = pf[0];
+            double bd = 0.0, it = 0.0, xr = 0.0, xrd = 0.0;
+            if constexpr (ANY_D) { pd += 4 * NCOL; pi += 4; bd = pd[0]; it = pi[0]; }
+            if constexpr (DYN) { px += 4; xr = px[0]; if constexpr (ANY_D) { pxd += 4; xrd = pxd[0]; } }
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+                double w1 = 0.0, w2 = 0.0;
+                if constexpr (C1 == CLS_G) { w1 = c1[t].next(k); dmma884(a1[t][0][0], a1[t][0][1], w1, bf); }
+                if constexpr (C1 == CLS_D) { w1 = c1[t].next(it, s.tbl); dmma884(a1[t][0][0], a1[t][0][1], w1, bd); }
+                if constexpr (C2 == CLS_G) { w2 = c2[t].next(k); dmma884(a2[t][0][0], a2[t][0][1], w2, bf); }
+                if constexpr (C2 == CLS_D) { w2 = c2[t].next(it, s.tbl); dmma884(a2[t][0][0], a2[t][0][1], w2, bd); }
+                if constexpr (DYN) {
+                    double du = dv[t];
+                    dv[t] *= d4[t];
+                    if constexpr (LOOP1) ad1[t] = fma(w1 * du, (C1 == CLS_D) ? xrd : xr, ad1[t]);
+                    if constexpr (LOOP2) ad2[t] = fma(w2 * du, (C2 == CLS_D) ? xrd : xr, ad2[t]);
+                }
+            }
+        }
+    }
+
+    // normalise, mix the two components, apply tracer rules; lane (r, j) returns the outputs of tracers
+    // j, j+4 of chain r in val[0..1] (NaN-propagating exactly like f1*cout1 + f2*cout2 of the reference)
+    __device__ __forceinline__ void end(const ChainPar (&p)[NT], const PlanView& pv, double* scratch_warp, int lane,
+                                        double (&val)[NT][2]) {
+        const int j = lane & 3, r = lane >> 2;
+        const unsigned full = 0xffffffffu;
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+#pragma unroll
+            for (int u = 1; u < UA; u++) {
+                a1[t][0][0] += a1[t][u][0]; a1[t][0][1] += a1[t][u][1];
+                a2[t][0][0] += a2[t][u][0]; a2[t][0][1] += a2[t][u][1];
+            }
+            double m[2], md = 0.0;
+            double x1[2], x2[2] = {0.0, 0.0}, xd1 = 0.0, xd2 = 0.0;
+            // component 1
+            if constexpr (C1 == CLS_P) {
+                int ix = c1[t].ix;
+                x1[0] = pv.Xf[ix * NCOL + 2 * j];
+                x1[1] = pv.Xf[ix * NCOL + 2 * j + 1];
+                if (DYN) {
+                    double tp = ((ix == 0) ? 1e-5 : (double)ix) + pv.dtp;
+                    xd1 = pv.xraw[ix] * exp(-p[t].lam_cfc * tp);
+                }
+            } else {
+                double S = __shfl_sync(full, a1[t][0][0], lane & ~3);
+                x1[0] = a1[t][0][0] / S;
+                x1[1] = a1[t][0][1] / S;
+                if (DYN) {
+                    double s = ad1[t];
+                    s += __shfl_xor_sync(full, s, 1);
+                    s += __shfl_xor_sync(full, s, 2);
+                    xd1 = s / S;
+                }
+            }
+            if constexpr (C2 == CLS_P) {
+                int ix = c2[t].ix;
+                x2[0] = pv.Xf[ix * NCOL + 2 * j];
+                x2[1] = pv.Xf[ix * NCOL + 2 * j + 1];
+                if (DYN) {
+                    double tp = ((ix == 0) ? 1e-5 : (double)ix) + pv.dtp;
+                    xd2 = pv.xraw[ix] * exp(-p[t].lam_cfc * tp);
+                }
+            } else if constexpr (C2 != CLS_NONE) {
+                double S = __shfl_sync(full, a2[t][0][0], lane & ~3);
+                x2[0] = a2[t][0][0] / S;
+                x2[1] = a2[t][0][1] / S;
+                if (DYN) {
+                    double s = ad2[t];
+                    s += __shfl_xor_sync(full, s, 1);
+                    s += __shfl_xor_sync(full, s, 2);
+                    xd2 = s / S;
+                }
+            }
+            // cout = f1*cout1 + f2*cout2 (run_age_mcmc_utils.py:154); cout2 = 0.0 without a second component
+            m[0] = p[t].f1 * x1[0] + p[t].f2 * x2[0];
+            m[1] = p[t].f1 * x1[1] + p[t].f2 * x2[1];
+            if (DYN) md = p[t].f1 * xd1 + p[t].f2 * xd2;
+            double* sc = scratch_warp + (t * 8 + r) * NCOL;
+            sc[2 * j] = m[0];
+            sc[2 * j + 1] = m[1];
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                int tr = j + 4 * q;
+                double v = 0.0;
+                if (tr < pv.ntracer) {
+                    TracerDev td = pv.tr[tr];
+                    if (td.dyn) {
+                        v = md;
+                    } else {
+                        double va = td.col_a >= 0 ? sc[td.col_a] : 0.0;
+                        v = td.col_b >= 0 ? va + p[t].Jlin * sc[td.col_b] : va;
+                    }
+                    if (td.sf6) v *= (1.0 + p[t].lamsf6);
+                }
+                val[t][q] = v;
+            }
+            __syncwarp();
+        }
+    }
+};
+
+// ---------------------------------------------------------------- likelihood terms (pymc3 3.11.2 formulae)
+__device__ __forceinline__ double lik_term_normal(double obs, double mu, double sd) {
+    double z = (obs - mu) / sd;
+    return -0.5 * log(2.0 * 3.14159265358979323846 * sd * sd) - 0.5 * z * z;
+}
+// Student-T with lam = sd^-2: lgamma((nu+1)/2) - lgamma(nu/2) + 0.5 log(lam/(nu pi)) - (nu+1)/2 log1p(lam (x-mu)^2/nu)
+__device__ __forceinline__ double lik_studentt_const(double nu) {
+    return lgamma(0.5 * (nu + 1.0)) - lgamma(0.5 * nu);
+}
+__device__ __forceinline__ double lik_term_studentt(double obs, double mu, double sd, double nu, double cst) {
+    double lam = 1.0 / (sd * sd);
+    double d = obs - mu;
+    return cst + 0.5 * log(lam / (nu * 3.14159265358979323846)) - 0.5 * (nu + 1.0) * log1p(lam * d * d / nu);
+}
+
+// ---------------------------------------------------------------- the forward (+ likelihood) kernel
+template <int C1, int C2, bool DYN, int NT, int UA, int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 1)
+k_forward(PlanView pv, SlotMap sm, const double* __restrict__ theta, long long B, double* __restrict__ out,
+          double* __restrict__ logp, LikPar lik, int lc_cap) {
+    using WT = WarpTiles<C1, C2, DYN, NT, UA>;
+    const int nwarps = blockDim.x >> 5, nthreads = blockDim.x;
+    extern __shared__ __align__(128) double smem[];
+    SmemView s;
+    {
+        double* p = smem;
+        s.tbl = p; p += TBL_DOUBLES;       // first: keeps the 128-byte bank alignment of the two word arrays
+        s.scratch = p; p += nwarps * NT * 8 * NCOL;
+        s.Xf = p; p += (size_t)lc_cap * NCOL;
+        s.Xd = p; if (WT::ANY_D) p += (size_t)lc_cap * NCOL;
+        s.itp = p; if (WT::ANY_D) p += lc_cap;
+        s.xraw = p; if (DYN) p += lc_cap;
+        s.xrawd = p; if (DYN && WT::ANY_D) p += lc_cap;
+    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int j = lane & 3, r = lane >> 2;
+    double* scratch_warp = s.scratch + warp * NT * 8 * NCOL;
+    if (WT::ANY_D) {
+        for (int i = tid; i < TBL_DOUBLES; i += nthreads) s.tbl[i] = pv.tbl[i];
+    }
+    auto load_chunk = [&](int kc, int len) {
+        if (!WT::ANY_LOOP) return;
+        const double2* gf = reinterpret_cast<const double2*>(pv.Xf + (size_t)kc * NCOL);
+        double2* sf = reinterpret_cast<double2*>(s.Xf);
+        for (int i = tid; i < len * NCOL / 2; i += nthreads) sf[i] = gf[i];
+        if (WT::ANY_D) {
+            const double2* gd = reinterpret_cast<const double2*>(pv.Xd + (size_t)kc * NCOL);
+            double2* sd = reinterpret_cast<double2*>(s.Xd);
+            for (int i = tid; i < len * NCOL / 2; i += nthreads) sd[i] = gd[i];
+            for (int i = tid; i < len; i += nthreads) s.itp[i] = pv.itp[kc + i];
+        }
+        if (DYN) {
+            for (int i = tid; i < len; i += nthreads) s.xraw[i] = pv.xraw[kc + i];
+            if (WT::ANY_D)
+                for (int i = tid; i < len; i += nthreads) s.xrawd[i] = pv.xrawd[kc + i];
+        }
+    };
+    const long long nunits = (B + NT * 8 - 1) / (NT * 8);
+    const int nchunks = WT::ANY_LOOP ? (pv.Lpad + lc_cap - 1) / lc_cap : 1;
+    bool need_J = false;
+    for (int t = 0; t < pv.ntracer; t++) need_J |= (pv.tr[t].col_b >= 0);
+
+    auto run_unit = [&](long long u, bool active, bool lockstep) {
+        WT w;
+        ChainPar par[NT];
+        long long chain[NT];
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+            chain[t] = (u * NT + t) * 8 + r;
+            long long cl = chain[t] < B ? chain[t] : B - 1;
+            par[t] = load_chain_par(theta, sm, active ? cl : 0, pv, need_J);
+        }
+        w.begin(par, pv);
+        if (!lockstep) {
+            w.chunk(s, pv, 0, pv.Lpad / 4, lane);
+        } else {
+            for (int c = 0; c < nchunks; c++) {
+                int kc = c * lc_cap;
+                int len = min(lc_cap, pv.Lpad - kc);
+                __syncthreads();
+                load_chunk(kc, len);
+                __syncthreads();
+                if (active) w.chunk(s, pv, kc, len / 4, lane);
+            }
+        }
+        if (!active) return;
+        double val[NT][2];
+        w.end(par, pv, scratch_warp, lane, val);
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+            bool ok = chain[t] < B;
+            if (out != nullptr && ok) {
+                if (j < pv.ntracer) out[chain[t] * pv.ntracer + j] = val[t][0];
+                if (j + 4 < pv.ntracer) out[chain[t] * pv.ntracer + j + 4] = val[t][1];
+            }
+            if (logp != nullptr) {
+                double nu = 0.0, cst = 0.0, acc = 0.0;
+                if (lik.kind == 1) {
+                    nu = lik.nu[ok ? chain[t] : B - 1];
+                    cst = lik_studentt_const(nu);
+                }
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    int tr = j + 4 * q;
+                    if (tr < pv.ntracer) {
+                        acc += (lik.kind == 1) ? lik_term_studentt(lik.obs[tr], val[t][q], lik.sd[tr], nu, cst)
+                                               : lik_term_normal(lik.obs[tr], val[t][q], lik.sd[tr]);
+                    }
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                if (j == 0 && ok) logp[chain[t]] = acc;
+            }
+        }
+    };
+
+    if (nchunks == 1) {
+        // Resident tables: load once, then a static, balanced schedule.  Units are dealt round-robin to the
+        // 4*gridDim.x SM sub-partitions (warp & 3 selects the sub-partition), and within a sub-partition
+        // round-robin to its warps.  All units cost the same, so every sub-partition carries floor or ceil of
+        // nunits/(4*grid) units and its FP64 pipe stays shared by >= 3 warps until the end (a dynamic counter let
+        // the last partial round pile onto random sub-partitions: profiles/r1_notes.md).
+        load_chunk(0, pv.Lpad);
+        __syncthreads();
+        const int spc = nwarps >= 4 ? 4 : nwarps;
+        const int wq = nwarps / spc;
+        const long long slot = (long long)blockIdx.x * spc + (warp % spc);
+        const long long nslots = (long long)gridDim.x * spc;
+        for (long long i = warp / spc;; i += wq) {
+            long long u = slot + i * nslots;
+            if (u >= nunits) break;
+            run_unit(u, true, false);
+        }
+    } else {
+        // long lag axis: the CTA streams X chunk by chunk, all warps in lock step
+        __syncthreads();
+        const long long ncta_units = (nunits + nwarps - 1) / nwarps;
+        for (long long cu = blockIdx.x; cu < ncta_units; cu += gridDim.x) {
+            long long u = cu * nwarps + warp;
+            run_unit(u, u < nunits, true);
+        }
+    }
+}
+
+}  // namespace ngrtd

@@ -61,3 +61,38 @@ def rel_err(a, b):
     aa, bb = a[m][~inf], b[m][~inf]
     den = np.maximum(np.abs(bb), 1e-300)
     return float(np.max(np.abs(aa - bb) / den)) if aa.size else 0.0
+
+
+def synth_plan(mod1, mod2, par_names, tracers=None, L=840, seed=0):
+    """Plan over the synthetic monthly series for the given tracers (default: the seven cfg-3 tracers)."""
+    from noblegas_rtd_mcmc_b200 import _lib, synthetic
+    tracers = list(synthetic.TRACERS_CFG3) if tracers is None else list(tracers)
+    series = synthetic.input_series(L, seed)
+    names = list(synthetic.SERIES_NAMES)
+    X = np.stack([series[n] for n in names], axis=1)
+    tab = synthetic.tracer_table_cfg3()
+    descs = []
+    for t in tracers:
+        d = tab[t]
+        descs.append(dict(series=names.index(d["series"]) if d["series"] is not None else -1,
+                          rad_accum=d.get("rad_accum", False),
+                          lam=float(np.log(2.0) / d["t_half"]) if "t_half" in d else 0.0,
+                          use_thalf_cfc=(t == "CFC12" and "thalf_cfc" in par_names),
+                          use_lamsf6=(t == "SF6")))
+    return _lib.Plan(X, descs, mod1, mod2), series, tab
+
+
+def real_plan(mod1, mod2, par_names, tracers, L=None):
+    """Plan over the reference's yearly series (rebuilt from the committed head + constant background)."""
+    from noblegas_rtd_mcmc_b200 import _lib
+    C = load_c_in(L)
+    names = ["CFC11", "CFC12", "CFC113", "SF6", "H3"]
+    X = np.stack([C[n] for n in names], axis=1)
+    descs = []
+    for t in tracers:
+        s, th, ra = REAL_TRACERS[t]
+        descs.append(dict(series=names.index(s) if s is not None else -1, rad_accum=ra,
+                          lam=float(-1.0 * np.log(0.5) / th) if th else 0.0,
+                          use_thalf_cfc=(t == "CFC12" and "thalf_cfc" in par_names),
+                          use_lamsf6=(t == "SF6")))
+    return _lib.Plan(X, descs, mod1, mod2), C
