@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native likelihood hot path (BASELINE.json config 3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one pass of the hot path over one batch: the fused RTD-weight + convolution + Gaussian log-likelihood
+kernel for 65,536 chains x (EPM + dispersion mixture) x 840 monthly lags x 6 counted tracers (+ the He4_ter k*J
+column, computed but not counted: SURVEY.md section 8d) on each GPU (weak scaling: chains shard, no collective on
+the data path).  Prints ONE JSON line (rank 0).
+
+metric  : likelihood evals/s = chains x steps x tracers / seconds (whole job, all GPUs)
+value   : inputs resident in HBM, CUDA events on the launching stream, max over ranks
+e2e     : the same metric through the host-buffer C-ABI call (pinned host theta -> H2D -> kernel -> D2H logp)
+roofline: algorithmic FP64 flops (F_step = 2*L*(T+1)*n_comp per chain) / mean kernel time vs the measured FP64 peak
+cpu_baseline / --impl reference: the plain-C oracle port of the reference arithmetic on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+CHAINS_PER_GPU = 65536
+L = 840
+T_COUNTED = 6
+N_COMP = 2
+F_STEP = 2.0 * L * (T_COUNTED + 1) * N_COMP          # 23,520 algorithmic flops per chain-proposal
+# Measured on this pool's B200 with tools/microbench/fp64_peak.cu (profiles/r1_fp64_peak_microbench.txt):
+# DFMA 36.2-36.5 TFLOP/s burst and sustained, DMMA.8x8x4 36.96; MEASURED_PEAKS.json carries no FP64 entry.
+FP64_PEAK_TFLOPS = 36.45
+# dram__bytes_read.sum + dram__bytes_write.sum of k_forward at this workload, one `ncu --set full` capture
+# (profiles/r1_ncu_forward_summary.txt); per launch.
+NCU_DRAM_BYTES_PER_LAUNCH = 3.87e6
+METRIC = "likelihood evals/sec (chains x draws x tracers)"
+UNIT = "tracer-likelihood evals/s"
+
+
+def workload_config(n_gpus, extra=None):
+    cfg = {"workload": "cfg3: synthetic batch, 65,536 chains/GPU x EPM+dispersion RTDs x 840-month input x 6 tracers "
+                       "(+He4_ter column computed, not counted)",
+           "chains_per_gpu": CHAINS_PER_GPU, "lags": L, "tracers_counted": T_COUNTED, "tracers_computed": 7,
+           "n_comp": N_COMP, "likelihood": "normal", "parallelism": "chains sharded x%d, no data-path collective" % n_gpus,
+           "l2": "inputs larger than L2: 40 rotating theta batches (147 MB) per GPU"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            load = [s for s in sm if s > 0.5 * max(mx)] or sm
+            out.update(sm_mhz=float(np.median(load)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_port_rate(seconds_target, nthreads=0):
+    """Time the plain-C oracle port (oracle/ngrtd_oracle.c) on a bounded sample of the cfg-3 workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle
+    from helpers import synth_descs
+    from noblegas_rtd_mcmc_b200 import synthetic
+    pn = list(synthetic.PAR_NAMES_CFG3)
+    X, descs = synth_descs(pn)
+    cores = nthreads or c_oracle.max_threads()
+    probe = synthetic.theta_cfg3(32 * cores, 0)
+    t0 = time.perf_counter()
+    c_oracle.forward(X, descs, "exp_pist_flow", "dispersion", probe, pn, nthreads=cores)
+    dt = max(time.perf_counter() - t0, 1e-4)
+    n = int(min(CHAINS_PER_GPU, max(64 * cores, probe.shape[0] * seconds_target / dt)))
+    theta = synthetic.theta_cfg3(n, 0)
+
+    def step():
+        t0 = time.perf_counter()
+        out = c_oracle.forward(X, descs, "exp_pist_flow", "dispersion", theta, pn, nthreads=cores)
+        dt = time.perf_counter() - t0
+        # the likelihood itself is O(T) per chain and is included for completeness
+        c_oracle.loglik("normal", out, np.ones(7), np.ones(7) * 0.05)
+        return dt
+    return step, n, cores
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU implementation of the same path (C oracle port), all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    step, n, cores = cpu_port_rate(seconds_target=max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup))))
+    for _ in range(args.warmup):
+        step()
+    t = 0.0
+    for _ in range(args.steps):
+        t += step()
+    value = n * T_COUNTED * args.steps / t
+    sample = "%d of %d chains per step (same theta prior, L=840, 7 tracers computed / 6 counted), %d threads" % (
+        n, CHAINS_PER_GPU, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus, {"note": "reference is pure Python (cannot travel to the GPU box); timed "
+                                                           "arm is the plain-C port of its arithmetic, oracle/ngrtd_oracle.c"}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from helpers import synth_plan
+    from noblegas_rtd_mcmc_b200 import _lib, synthetic
+
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    pn = list(synthetic.PAR_NAMES_CFG3)
+    plan, _, _ = synth_plan("exp_pist_flow", "dispersion", pn, device=local)
+    B = CHAINS_PER_GPU
+    NBUF = 40
+    # chains are sharded by global chain id: rank r owns ids [r*B, (r+1)*B) of every rotating batch
+    thetas = [torch.from_numpy(synthetic.theta_cfg3(B, seed=1000 * i + rank)).to(dev) for i in range(NBUF)]
+    obs = np.array([8.0, 40.0, 150.0, 300.0, 50.0, 5.0, 1e-8])
+    sd = 0.05 * obs
+    logp = torch.empty(B, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        plan.forward_loglik_dev(thetas[i % NBUF], pn, obs, sd, "normal", logp_t=logp, stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    # ---- timed region: K steps, per-launch CUDA events on the launching stream ----
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        ev[i][0].record(stream)
+        step(i)
+        ev[i][1].record(stream)
+    e1.record(stream)
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    checksum = float(torch.nansum(logp))
+    # keep the GPU under the same load long enough for nvidia-smi to see the clocks of this kernel
+    t_probe = time.perf_counter()
+    i = 0
+    while rank == 0 and time.perf_counter() - t_probe < 1.0:
+        for _ in range(50):
+            step(i); i += 1
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, kern_ms = float(t[0]), float(t[1])
+    value = world * B * T_COUNTED * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers through the C-ABI host entry point (H2D + kernel + D2H inside the timed region) ----
+    host_thetas = [torch.from_numpy(synthetic.theta_cfg3(B, seed=77 + 1000 * i + rank)).pin_memory() for i in range(8)]
+    host_logp = torch.empty(B, dtype=torch.float64).pin_memory()
+    hl = host_logp.numpy()
+
+    def e2e_step(i):
+        plan.forward_loglik_host(host_thetas[i % 8].numpy(), pn, obs, sd, "normal", logp_out=hl)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e_value = world * B * T_COUNTED * args.steps / e2e_s
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cstep, n, cores = cpu_port_rate(seconds_target=12.0)
+        cstep()
+        dt, passes = 0.0, 0
+        while dt < 10.0 and passes < 1000:          # bounded sample: about 10 s of CPU work
+            dt += cstep()
+            passes += 1
+        cpu = {"value": passes * n * T_COUNTED / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d passes over %d of %d chains, oracle/ngrtd_oracle.c (pthreads), %.1f s" % (passes, n, B, dt)}
+    if rank == 0:
+        achieved = F_STEP * B / (kern_ms * 1e-3) / 1e12
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * len(pn) * 8, "d2h_bytes_per_step": B * 8,
+                        "ms_per_step": 1e3 * e2e_s / args.steps},
+                "gpu_launches": args.steps,
+                "clocks": clocks,
+                "roofline": {"bound": "tensor", "pipe": "fp64: DMMA.8x8x4 (tensor sub-pipe) shares the FP64 pipe with DFMA",
+                             "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                             "frac": achieved / FP64_PEAK_TFLOPS, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                             "peak_source": "measured FP64 DFMA peak on this pool (tools/microbench/fp64_peak.cu); "
+                                            "MEASURED_PEAKS.json has no FP64 entry",
+                             "kernel": "k_forward<G,D>", "kernel_ms": kern_ms, "flops_per_chain": F_STEP},
+                "cpu_baseline": cpu, "checksum_logp": checksum}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,110 @@
+"""Drop-in for the hot-path part of the reference's utils/noble_gas_utils.py: `atm_std`, `noble_gas_fun`
+(closed-equilibrium model, :75-261) and `J_flux` (:335-348), evaluated on the B200 through libngrtd.so.
+
+Scalar arguments give scalar results exactly as in the reference; array-valued E/T/Ae/F of shape [B] give
+ndarray results of shape [B] per gas (additive behaviour).
+"""
+import numpy as np
+
+from . import _lib
+
+# Dry air mixing ratios, Porcelli et al. 2002 (utils/noble_gas_utils.py:38-73 of the reference)
+atm_std = {'N2': 0.781, 'O2': 0.209, 'Ar': 9.34e-3, 'CO2': 3.7e-4, 'Ne': 1.818e-5, 'He': 5.24e-6, 'CH4': 1.5e-6,
+           'Kr': 1.14e-6, 'H2': 7e-7, 'N2O': 3e-7, 'CO': 1e-7, 'Xe': 8.7e-8, 'Rn': 6e-20,
+           'He3': 5.24e-6 * 0.000140 / 100, 'He4': 5.24e-6,
+           'Ne20': 1.818e-5 * 90.50 / 100, 'Ne21': 1.818e-5 * 0.268 / 100, 'Ne22': 1.818e-5 * 9.23 / 100,
+           'Ar36': 9.34e-3 * 0.3364 / 100, 'Ar38': 9.34e-3 * 0.0632 / 100, 'Ar40': 9.34e-3 * 99.60 / 100,
+           'Kr78': 1.14e-6 * 0.3469 / 100, 'Kr80': 1.14e-6 * 2.2571 / 100, 'Kr82': 1.14e-6 * 11.523 / 100,
+           'Kr83': 1.14e-6 * 11.477 / 100, 'Kr84': 1.14e-6 * 57.00 / 100, 'Kr86': 1.14e-6 * 17.398 / 100,
+           'Xe124': 8.7e-8 * 0.0951 / 100, 'Xe126': 8.7e-8 * 0.0887 / 100, 'Xe128': 8.7e-8 * 1.919 / 100,
+           'Xe129': 8.7e-8 * 26.44 / 100, 'Xe130': 8.7e-8 * 4.070 / 100, 'Xe131': 8.7e-8 * 21.22 / 100,
+           'Xe132': 8.7e-8 * 26.89 / 100, 'Xe134': 8.7e-8 * 10.430 / 100, 'Xe136': 8.7e-8 * 8.857 / 100}
+
+_WHAT = {"ce_true": 0, "ce_false": 1, "eq_dry": 2, "eq_wet": 3, "K": 4}
+
+
+def _gas_id(gas):
+    g = gas[0:2]                                   # the reference keys solubility on the first two letters (:135)
+    if g not in _lib.GAS:
+        raise ValueError("unknown noble gas %r (known: He, Ne, Ar, Kr, Xe)" % (gas,))
+    return _lib.GAS[g]
+
+
+class noble_gas_fun():
+    def __init__(self, gases, E, T, Ae, F, P, S=0.0):
+        self.gases = gases
+        self.E = E
+        self.T = T
+        self.Ae = Ae
+        self.F = F
+        self.S = S
+        self.P = self.parse_P(P)
+        self.obs_dict = None
+        self.err_dict = None
+
+    def parse_P(self, P):                          # :91-100
+        if isinstance(P, str):
+            if P == '1atm':
+                return 0.000101325
+            if P == 'lapse_rate':
+                return self.lapse_rate()
+            raise ValueError("P must be '1atm', 'lapse_rate' or a pressure in GPa")
+        return P
+
+    def lapse_rate(self):                          # :103-113
+        return ((1 - .0065 * np.asarray(self.E, dtype=np.float64) / 288.15) ** 5.2561) * 0.000101325 \
+            if np.ndim(self.E) else ((1 - .0065 * self.E / 288.15) ** 5.2561) * 0.000101325
+
+    def _run(self, what, gases):
+        ids = _lib.i32([_gas_id(g) for g in gases])
+        args = [self.E, self.T, self.Ae, self.F, self.P]
+        B = 1
+        scalar = True
+        for a in args:
+            if np.ndim(a) > 0:
+                scalar = False
+                B = max(B, np.size(a))
+        E, T, Ae, F, P = [_lib.f64(np.broadcast_to(np.asarray(0.0 if a is None else a, dtype=np.float64), (B,))) for a in args]
+        out = np.empty((B, len(gases)))
+        _lib.check(_lib.lib.ngrtd_ce_host(_WHAT[what], len(gases), _lib.hptr(ids), _lib.hptr(E), _lib.hptr(T), _lib.hptr(Ae),
+                                          _lib.hptr(F), _lib.hptr(P), float(self.S), B, _lib.hptr(out)))
+        return out, scalar
+
+    def _as_dict(self, what, gases):
+        out, scalar = self._run(what, gases)
+        return {g: (float(out[0, i]) if scalar else out[:, i].copy()) for i, g in enumerate(gases)}
+
+    def solubility(self, gas):                     # :117-180
+        out, scalar = self._run("K", [gas])
+        return float(out[0, 0]) if scalar else out[:, 0]
+
+    def vapor_pressure(self):                      # :184-199 (host arithmetic: a scalar property used for display)
+        T = np.asarray(self.T, dtype=np.float64)
+        lo = T <= 99.0
+        A, B, C = np.where(lo, 8.07131, 8.14019), np.where(lo, 1730.63, 1810.94), np.where(lo, 233.426, 244.485)
+        P = 10 ** (A - (B / (C + T)))
+        P = P / 760. * 101325 / 1.0e9
+        return float(P) if np.ndim(self.T) == 0 else P
+
+    def equil_conc(self):                          # :202-213
+        return self._as_dict("eq_wet", list(self.gases))
+
+    def equil_conc_dry(self):                      # :216-232
+        return self._as_dict("eq_dry", list(self.gases))
+
+    def ce_exc(self, add_eq_conc):                 # :235-253
+        return self._as_dict("ce_true" if add_eq_conc else "ce_false", list(self.gases))
+
+    def update_pars(self, T, Ae, F, E):            # :256-261
+        self.T = T
+        self.Ae = Ae
+        self.F = F
+        self.E = E
+        self.P = self.lapse_rate()
+
+
+def J_flux(Del, rho_r, rho_w, U, Th, phi):
+    """He accumulation rate (ccSTP/g_water/yr), Porcelli 2002 p. 648 (utils/noble_gas_utils.py:335-348)."""
+    PU = 1.19e-13
+    PTh = 2.88e-14
+    return Del * rho_r / rho_w * (U * PU + Th * PTh) * ((1 - phi) / phi)

@@ -1,0 +1,107 @@
+"""Operator boundary of the age model: drop-in for `ForwardMod` of the reference's
+age_ens_runs_mcmc/run_age_mcmc_utils.py:47-163, plus the batched joint operator the device sampler uses.
+
+`ForwardMod(conv_kwgs, par_names, tracer)` keeps the reference constructor and `perform(node, inputs, outputs)`
+(one theta -> one scalar); `perform_batch(theta[B, ndim]) -> out[B]` is the additive batched form.
+`JointForwardMod(conv_kwgs_by_tracer, par_names, tracers)` evaluates every tracer of a joint inversion in ONE
+kernel launch (the RTD of a chain is generated once and shared by its tracers).
+"""
+import numpy as np
+
+from . import _lib
+from .convolution_integral_utils import _as_series
+
+P_NAMES = ("tau1", "tau2", "f1", "f2", "eta1", "eta2", "D1", "D2", "J", "thalf_cfc", "lamsf6")
+
+
+def _tracer_desc(kw, tracer, par_names, series_col):
+    t_half = kw.get('t_half', False)
+    ra = kw.get('rad_accum', False)
+    if ra not in (False, None, '3He', '4He'):
+        raise ValueError("unknown rad_accum %r for tracer %s" % (ra, tracer))
+    use_cfc = ('thalf_cfc' in par_names and tracer == 'CFC12')          # run_age_mcmc_utils.py:107-109
+    if use_cfc and ra:
+        raise ValueError("thalf_cfc on a rad_accum tracer is not supported")
+    return dict(series=series_col, rad_accum=ra if ra else False,
+                lam=float(-1 * np.log(0.5) / t_half) if t_half else 0.0,   # update_pars -> thalf_2_lambda
+                use_thalf_cfc=use_cfc, use_lamsf6=(tracer == 'SF6'))       # :160-161
+
+
+class JointForwardMod(object):
+    """All tracers of one well/model pair in one plan (input series resident in HBM)."""
+
+    def __init__(self, conv_kwgs, par_names, tracers, device=-1):
+        self.p_names = list(par_names)
+        self.tracers = list(tracers)
+        for p in self.p_names:
+            if p not in P_NAMES:
+                raise ValueError("unknown parameter %r (known: %s)" % (p, ", ".join(P_NAMES)))
+        mod1 = mod2 = None
+        cols, descs, lag_index, dtp, L = [], [], None, None, None
+        for t in self.tracers:
+            kw = conv_kwgs[t]
+            if kw.get('bbar', False) or kw.get('Phi_im', False):
+                raise NotImplementedError("fracture/matrix-diffusion parameters are outside the B200 hot path")
+            m1 = kw.get('mod_type1', conv_kwgs.get('mod_type1', False))
+            m2 = kw.get('mod_type2', conv_kwgs.get('mod_type2', False))
+            if mod1 is None:
+                mod1, mod2 = m1, m2
+            elif (m1, m2) != (mod1, mod2):
+                raise ValueError("all tracers of a joint operator share mod_type1/mod_type2")
+            vals, idx, last = _as_series(kw['C_t'])
+            d = float(np.floor(last - last))                              # t_samp = C_t.index[-1] (:94)
+            if L is None:
+                L, lag_index, dtp = len(vals), idx, d
+            elif len(vals) != L or not np.array_equal(idx, lag_index):
+                raise ValueError("all tracers of a joint operator share the lag grid")
+            col = -1
+            if np.any(vals != 0.0):
+                for i, c in enumerate(cols):
+                    if np.array_equal(c, vals):
+                        col = i
+                        break
+                else:
+                    cols.append(vals)
+                    col = len(cols) - 1
+            descs.append(_tracer_desc(kw, t, self.p_names, col))
+        X = np.stack(cols, axis=1) if cols else np.zeros((L, 1))
+        self.plan = _lib.Plan(X, descs, mod1, mod2 if mod2 else False, lag_index=lag_index, dtp=dtp, device=device)
+        self.mod_type1, self.mod_type2 = mod1, mod2
+
+    def perform_batch(self, theta):
+        """theta [B, ndim] ordered by par_names -> modelled concentrations [B, ntracer] (host numpy)."""
+        return self.plan.forward_host(np.atleast_2d(theta), self.p_names)
+
+    def perform_batch_device(self, theta_t, out_t=None, stream=None):
+        """torch CUDA tensor in / out, no synchronisation."""
+        return self.plan.forward_dev(theta_t, self.p_names, out_t, stream)
+
+    def logp_batch(self, theta, obs_mu, obs_err, kind="studentt", nu=None):
+        return self.plan.forward_loglik_host(np.atleast_2d(theta), self.p_names, obs_mu, obs_err, kind, nu)
+
+
+class ForwardMod(object):
+    '''Single-tracer operator with the reference's constructor and perform() (Theano Op protocol).'''
+
+    def __init__(self, conv_kwgs, par_names, tracer):
+        kwargs = conv_kwgs.copy()
+        self.C_t = kwargs.get('C_t', False)
+        self.mod_type1 = kwargs.get('mod_type1', False)
+        self.mod_type2 = kwargs.get('mod_type2', False)
+        self.t_half = kwargs.get('t_half', False)
+        self.rad_accum = kwargs.get('rad_accum', False)
+        self.J = kwargs.get('J', False)
+        self.eta = kwargs.get('eta', False)
+        self.D = kwargs.get('D', False)
+        self.bbar = kwargs.get('bbar', False)
+        self.Phi_im = kwargs.get('Phi_im', False)
+        self.t = tracer
+        self.p_names = par_names
+        self._joint = JointForwardMod({tracer: kwargs}, par_names, [tracer])
+
+    def perform_batch(self, theta):
+        return self._joint.perform_batch(theta)[:, 0]
+
+    def perform(self, node, inputs, outputs):
+        """Forward model for one parameter vector (inputs[0]), result in outputs[0][0] as in the reference."""
+        outputs[0][0] = np.array(self.perform_batch(np.asarray(inputs[0], dtype=np.float64).reshape(1, -1))[0])

@@ -72,3 +72,21 @@ def tracer_table_cfg3():
         "SF6": dict(series="SF6"),
         "He4_ter": dict(series=None, rad_accum="4He"),
     }
+
+
+def series_matrix_and_descs(par_names, tracers=None, L=840, seed=0):
+    """(X [L, nseries] newest-first, tracer descriptor dicts) for the C ABI / the oracle, cfg-3 tracer table."""
+    tracers = list(TRACERS_CFG3) if tracers is None else list(tracers)
+    series = input_series(L, seed)
+    names = list(SERIES_NAMES)
+    X = np.ascontiguousarray(np.stack([series[n] for n in names], axis=1))
+    tab = tracer_table_cfg3()
+    descs = []
+    for t in tracers:
+        d = tab[t]
+        descs.append(dict(series=names.index(d["series"]) if d["series"] is not None else -1,
+                          rad_accum=d.get("rad_accum", False),
+                          lam=float(np.log(2.0) / d["t_half"]) if "t_half" in d else 0.0,
+                          use_thalf_cfc=(t == "CFC12" and "thalf_cfc" in par_names),
+                          use_lamsf6=(t == "SF6")))
+    return X, descs

@@ -63,23 +63,16 @@ def rel_err(a, b):
     return float(np.max(np.abs(aa - bb) / den)) if aa.size else 0.0
 
 
-def synth_plan(mod1, mod2, par_names, tracers=None, L=840, seed=0):
+def synth_descs(par_names, tracers=None, L=840, seed=0):
+    from noblegas_rtd_mcmc_b200 import synthetic
+    return synthetic.series_matrix_and_descs(par_names, tracers, L, seed)
+
+
+def synth_plan(mod1, mod2, par_names, tracers=None, L=840, seed=0, device=-1):
     """Plan over the synthetic monthly series for the given tracers (default: the seven cfg-3 tracers)."""
     from noblegas_rtd_mcmc_b200 import _lib, synthetic
-    tracers = list(synthetic.TRACERS_CFG3) if tracers is None else list(tracers)
-    series = synthetic.input_series(L, seed)
-    names = list(synthetic.SERIES_NAMES)
-    X = np.stack([series[n] for n in names], axis=1)
-    tab = synthetic.tracer_table_cfg3()
-    descs = []
-    for t in tracers:
-        d = tab[t]
-        descs.append(dict(series=names.index(d["series"]) if d["series"] is not None else -1,
-                          rad_accum=d.get("rad_accum", False),
-                          lam=float(np.log(2.0) / d["t_half"]) if "t_half" in d else 0.0,
-                          use_thalf_cfc=(t == "CFC12" and "thalf_cfc" in par_names),
-                          use_lamsf6=(t == "SF6")))
-    return _lib.Plan(X, descs, mod1, mod2), series, tab
+    X, descs = synth_descs(par_names, tracers, L, seed)
+    return _lib.Plan(X, descs, mod1, mod2, device=device), synthetic.input_series(L, seed), synthetic.tracer_table_cfg3()
 
 
 def real_plan(mod1, mod2, par_names, tracers, L=None):

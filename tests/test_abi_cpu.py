@@ -1,0 +1,74 @@
+"""CPU: the C-ABI library loads and exports every symbol include/ngrtd.h declares (no compute calls without a GPU);
+host-side argument validation that does not need a device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "noblegas_rtd_mcmc_b200", "libngrtd.so")
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "ngrtd.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ngrtd_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(SO):
+        import __graft_entry__
+        __graft_entry__.build()
+    return ctypes.CDLL(SO)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = _declared()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), "libngrtd.so does not export %s" % n
+    lib.ngrtd_version.restype = ctypes.c_int
+    assert lib.ngrtd_version() == 100
+
+
+def test_binding_covers_header(lib):
+    from noblegas_rtd_mcmc_b200 import _lib
+    assert sorted(_lib.EXPORTED) == _declared()
+
+
+def test_argument_validation_without_device(lib):
+    """Invalid arguments are rejected before any CUDA call, with a message."""
+    from noblegas_rtd_mcmc_b200 import _lib
+    h = ctypes.c_void_p()
+    tr = (_lib.Tracer * 1)(_lib.Tracer(0, 0, 0.0, 0, 0))
+    x = np.ones((8, 1))
+    rc = _lib.lib.ngrtd_plan_create(ctypes.byref(h), 8, 1, _lib.hptr(x), None, 0.0, 1, tr, 99, 0, -1)
+    assert rc == -1 and b"mod_type1" in _lib.lib.ngrtd_last_error()
+    rc = _lib.lib.ngrtd_plan_create(ctypes.byref(h), 0, 1, _lib.hptr(x), None, 0.0, 1, tr, 2, 0, -1)
+    assert rc == -1
+    rc = _lib.lib.ngrtd_plan_create(ctypes.byref(h), 8, 1, _lib.hptr(x), None, 0.5, 1, tr, 2, 0, -1)
+    assert rc == -1 and b"dtp" in _lib.lib.ngrtd_last_error()
+    with pytest.raises(ValueError):
+        _lib.Plan(x, [dict(series=0)], "gamma")
+    with pytest.raises(ValueError):
+        _lib.slot_array(["tau1", "nope"])
+    rc = _lib.lib.ngrtd_ce_dev(0, 9, None, None, None, None, None, None, 0.0, 1, None, None)
+    assert rc == -1
+
+
+def test_dropin_signatures_match_reference():
+    """Same public names / kwargs as the reference classes."""
+    import inspect
+    from noblegas_rtd_mcmc_b200 import convolution_integral_utils as conv, noble_gas_utils as ng, run_age_mcmc_utils as ram
+    assert list(inspect.signature(conv.tracer_conv_integral.__init__).parameters) == ["self", "C_t", "t_samp"]
+    for m in ("update_pars", "thalf_2_lambda", "gen_g_tp", "convolve"):
+        assert hasattr(conv.tracer_conv_integral, m)
+    assert list(inspect.signature(ng.noble_gas_fun.__init__).parameters) == ["self", "gases", "E", "T", "Ae", "F", "P", "S"]
+    for m in ("parse_P", "lapse_rate", "solubility", "vapor_pressure", "equil_conc", "equil_conc_dry", "ce_exc", "update_pars"):
+        assert hasattr(ng.noble_gas_fun, m)
+    assert list(inspect.signature(ram.ForwardMod.__init__).parameters) == ["self", "conv_kwgs", "par_names", "tracer"]
+    assert list(inspect.signature(ram.ForwardMod.perform).parameters) == ["self", "node", "inputs", "outputs"]
+    assert ng.J_flux(1, 2700, 1000, 3.7, 10.2, 0.05) == 3.7657277999999995e-11

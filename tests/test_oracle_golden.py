@@ -180,3 +180,43 @@ def test_oracle_matches_live_reference():
         want = m.convolve()
         got = O.convolve(series, tp, O.gen_g_tp(mt, tp, tau, eta, D), O.thalf_2_lambda(9.0))[0]
         assert abs(got - want) <= 1e-13 * abs(want), mt
+
+
+# ----------------------------------------------------------------------------- plain-C oracle
+def _real_descs(tracers, par_names):
+    names = ["CFC11", "CFC12", "CFC113", "SF6", "H3"]
+    descs = []
+    for t in tracers:
+        s, th, ra = REAL_TRACERS[t]
+        descs.append(dict(series=names.index(s) if s is not None else -1, rad_accum=ra,
+                          lam=float(-1.0 * np.log(0.5) / th) if th else 0.0,
+                          use_thalf_cfc=(t == "CFC12" and "thalf_cfc" in par_names), use_lamsf6=(t == "SF6")))
+    return names, descs
+
+
+@pytest.mark.parametrize("name", sorted(MODEL_CFGS))
+def test_c_oracle_forward_real_series(name):
+    import c_oracle
+    z = np.load(os.path.join(GOLD, "forward_real.npz"))
+    C = load_c_in()
+    m1, m2, pn = MODEL_CFGS[name]
+    tracers = ["CFC12", "SF6", "H3", "He4_ter", "He3", "CFC11"]
+    names, descs = _real_descs(tracers, pn)
+    X = np.stack([C[n] for n in names], axis=1)
+    out = c_oracle.forward(X, descs, m1, m2, z[name + "/theta"], pn)
+    for i, t in enumerate(tracers):
+        assert rel_err(out[:, i], z[name + "/" + t]) < 1e-11, (name, t)
+
+
+def test_c_oracle_ce_and_loglik():
+    import c_oracle
+    z = np.load(os.path.join(GOLD, "ce_model.npz"))
+    gases = ["He", "Ne", "Ar", "Kr", "Xe"]
+    for what, key in ((0, "ce_true"), (1, "ce_false"), (2, "eq_dry"), (3, "eq_wet"), (4, "K")):
+        got = c_oracle.ce(what, gases, z["E"], z["T"], z["Ae"], z["F"])
+        assert rel_err(got, z[key]) < 1e-13, key
+    rng = np.random.default_rng(3)
+    mu = rng.normal(1.0, 0.5, (50, 4))
+    obs = np.array([1.1, 0.7, 1.3, 0.9]); sd = np.array([0.1, 0.2, 0.05, 0.3]); nu = rng.uniform(1.0, 30.0, 50)
+    assert np.allclose(c_oracle.loglik("normal", mu, obs, sd), O.logp_normal(obs, mu, sd), rtol=1e-13)
+    assert np.allclose(c_oracle.loglik("studentt", mu, obs, sd, nu), O.logp_studentt(obs, mu, sd, nu), rtol=1e-12)
