@@ -143,6 +143,72 @@ int ngrtd_ce_wrapper_dev(int32_t ngas, const int32_t* gases, const double* theta
 int ngrtd_loglik_dev(int32_t lik_kind, int32_t T, const double* mu_d, const double* obs_mu, const double* obs_sd,
                      const double* nu_d, int64_t B, double* logp_d, void* stream);
 
+/* ---- device-resident batched sampler: replaces pymc3's DEMetropolisZ / metrop_select loop that the reference
+ *      configures at age_ens_runs_mcmc/run_age_mcmc_utils.py:412-417 and ng_interp/noble_gas_mcmc.py:408-415, and the
+ *      model assembly (priors, transforms, likelihood) of run_age_mcmc_utils.py:275-397 / noble_gas_mcmc.py:216-267.
+ *      pymc3 3.11.2 is a third-party dependency absent from the reference tree; semantics: SURVEY.md App. B.      */
+#define NGRTD_PRIOR_UNIFORM 0      /* mc.Uniform(p0, p1)          -> interval transform          */
+#define NGRTD_PRIOR_BETA 1         /* mc.Beta(p0, p1) mapped affinely onto [lo, hi] -> log-odds  */
+#define NGRTD_PRIOR_NORMAL 2       /* mc.Normal(p0, p1)           -> untransformed               */
+#define NGRTD_PRIOR_HALFNORMAL 3   /* mc.HalfNormal(p0)           -> log transform               */
+#define NGRTD_VAL_NU 11            /* value register of the Student-T nu_ variable (after NGRTD_P_* 0..10) */
+/* noble-gas model value registers (ng_interp/noble_gas_mcmc.py:224-250) */
+#define NGRTD_NG_LOG10AE 0
+#define NGRTD_NG_LOG10F 1
+#define NGRTD_NG_E 2
+#define NGRTD_NG_M 3
+#define NGRTD_NG_B 4
+#define NGRTD_MAX_DIM 10
+
+typedef struct ngrtd_prior {
+    int32_t kind;      /* NGRTD_PRIOR_* */
+    int32_t target;    /* value register: NGRTD_P_* / NGRTD_VAL_NU (age model) or NGRTD_NG_* / NGRTD_VAL_NU (noble-gas model) */
+    double p0, p1;
+    double lo, hi;     /* beta only */
+} ngrtd_prior;
+
+typedef struct ngrtd_sampler_cfg {
+    int32_t ndim;
+    ngrtd_prior prior[NGRTD_MAX_DIM];
+    int32_t lik_kind;              /* NGRTD_LIK_* */
+    int32_t nu_sampled;            /* 1: nu = nu_lo + (nu_hi - nu_lo) * nu_  (run_age_mcmc_utils.py:291-292) */
+    double nu_lo, nu_hi, nu_fixed;
+    int32_t nobs;                  /* tracers of the plan, or gases of the noble-gas model */
+    double obs_mu[8], obs_sd[8];
+    int32_t f2_from_f1;            /* f2 = 1 - f1 (run_age_mcmc_utils.py:304) */
+    int32_t proposal_dist;         /* 0 Uniform(-1,1) (pymc3 DEMetropolisZ default), 1 Normal(0,1) */
+    int32_t de_mcz;                /* 1 DE-MC-Z, 0 random-walk Metropolis */
+    int32_t tune_target;           /* 0 lambda (pymc3 default for DEMetropolisZ), 1 scaling */
+    int32_t tune_interval;
+    double scaling;                /* 0.001 in pymc3 */
+    double lamb;                   /* <= 0: 2.38 / sqrt(2 ndim) */
+    double tune_drop_fraction;     /* 0.9 in pymc3 */
+    int32_t hist_cap;              /* history ring capacity per chain; >= tune+draws reproduces pymc3 exactly */
+    uint64_t seed;
+    int64_t chain_offset;          /* global id of local chain 0 (multi-GPU sharding; Philox counters use global ids) */
+    int32_t ngas;                  /* noble-gas model only */
+    int32_t gases[5];
+} ngrtd_sampler_cfg;
+
+typedef struct ngrtd_sampler ngrtd_sampler;
+
+/* plan == NULL selects the noble-gas closed-equilibrium model.  q0: HOST [ndim] start in transformed space or NULL
+ * for pymc3's model.test_point.  All chains start at the same point, as in the reference. */
+int ngrtd_sampler_create(ngrtd_sampler** s, const ngrtd_sampler_cfg* cfg, ngrtd_plan* plan, int64_t nchains,
+                         const double* q0, int32_t device);
+int ngrtd_sampler_destroy(ngrtd_sampler* s);
+/* advance every chain by nsteps Metropolis steps in ONE kernel launch.  tune: tuning phase; record: update the
+ * per-chain Welford statistics and, if trace_d != NULL, write natural-space draws trace_d[ceil(nsteps/thin), B, ndim]. */
+int ngrtd_sampler_run(ngrtd_sampler* s, int64_t nsteps, int32_t tune, int32_t record, int32_t thin, double* trace_d,
+                      void* stream);
+int ngrtd_sampler_stop_tuning(ngrtd_sampler* s);   /* DEMetropolisZ.stop_tuning: drop the oldest fraction of the history */
+/* what: 0 q [B,ndim] (transformed), 1 logp [B], 2 lamb [B], 3 scaling [B], 4 accepted count [B], 5 mean [B,ndim],
+ *       6 M2 [B,ndim] (Welford, natural values) -- copied to out_d (device) on `stream` */
+int ngrtd_sampler_get(ngrtd_sampler* s, int32_t what, double* out_d, void* stream);
+int ngrtd_sampler_set(ngrtd_sampler* s, int32_t what, const double* in_d, void* stream);   /* what 0..3: checkpoint restore */
+int ngrtd_sampler_info(const ngrtd_sampler* s, int64_t* step, int64_t* ndraws, int64_t* hist_start);
+int ngrtd_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);   /* known-answer hook */
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,26 @@ class Tracer(ctypes.Structure):
                 ("use_thalf_cfc", ctypes.c_int32), ("use_lamsf6", ctypes.c_int32)]
 
 
+class Prior(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("target", ctypes.c_int32), ("p0", ctypes.c_double), ("p1", ctypes.c_double),
+                ("lo", ctypes.c_double), ("hi", ctypes.c_double)]
+
+
+class SamplerCfg(ctypes.Structure):
+    _fields_ = [("ndim", ctypes.c_int32), ("prior", Prior * 10), ("lik_kind", ctypes.c_int32), ("nu_sampled", ctypes.c_int32),
+                ("nu_lo", ctypes.c_double), ("nu_hi", ctypes.c_double), ("nu_fixed", ctypes.c_double),
+                ("nobs", ctypes.c_int32), ("obs_mu", ctypes.c_double * 8), ("obs_sd", ctypes.c_double * 8),
+                ("f2_from_f1", ctypes.c_int32), ("proposal_dist", ctypes.c_int32), ("de_mcz", ctypes.c_int32),
+                ("tune_target", ctypes.c_int32), ("tune_interval", ctypes.c_int32), ("scaling", ctypes.c_double),
+                ("lamb", ctypes.c_double), ("tune_drop_fraction", ctypes.c_double), ("hist_cap", ctypes.c_int32),
+                ("seed", ctypes.c_uint64), ("chain_offset", ctypes.c_int64), ("ngas", ctypes.c_int32),
+                ("gases", ctypes.c_int32 * 5)]
+
+
+PRIOR_KIND = {"uniform": 0, "beta": 1, "normal": 2, "halfnormal": 3}
+VAL_NU = 11
+NG_TARGET = {"log10Ae": 0, "log10F": 1, "E": 2, "m": 3, "b": 4, "nu_": VAL_NU}
+
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         "libngrtd.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -53,6 +73,14 @@ _PROTOS = {
     "ngrtd_ce_host": ([_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _vp], ctypes.c_int),
     "ngrtd_ce_wrapper_dev": ([_i32, _vp, _vp, _i64, _vp, _vp], ctypes.c_int),
     "ngrtd_loglik_dev": ([_i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp], ctypes.c_int),
+    "ngrtd_sampler_create": ([ctypes.POINTER(_vp), ctypes.POINTER(SamplerCfg), _vp, _i64, _vp, _i32], ctypes.c_int),
+    "ngrtd_sampler_destroy": ([_vp], ctypes.c_int),
+    "ngrtd_sampler_run": ([_vp, _i64, _i32, _i32, _i32, _vp, _vp], ctypes.c_int),
+    "ngrtd_sampler_stop_tuning": ([_vp], ctypes.c_int),
+    "ngrtd_sampler_get": ([_vp, _i32, _vp, _vp], ctypes.c_int),
+    "ngrtd_sampler_set": ([_vp, _i32, _vp, _vp], ctypes.c_int),
+    "ngrtd_sampler_info": ([_vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64), ctypes.POINTER(_i64)], ctypes.c_int),
+    "ngrtd_philox4x32_10": ([_vp, _vp, _vp], ctypes.c_int),
 }
 for _name, (_args, _res) in _PROTOS.items():
     _fn = getattr(lib, _name)

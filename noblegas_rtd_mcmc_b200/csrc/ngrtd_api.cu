@@ -12,6 +12,7 @@
 #include "ngrtd_common.cuh"
 #include "ngrtd_forward.cuh"
 #include "ngrtd_ce.cuh"
+#include "ngrtd_mcmc.cuh"
 
 using namespace ngrtd;
 
@@ -651,5 +652,330 @@ extern "C" int ngrtd_loglik_dev(int32_t lik_kind, int32_t T, const double* mu_d,
     unsigned grid = (unsigned)((B + 127) / 128);
     k_loglik<<<grid, 128, 0, (cudaStream_t)stream>>>(lik_kind, op, mu_d, nu_d, B, logp_d);
     CUDA_TRY(cudaGetLastError());
+    return NGRTD_OK;
+}
+
+// ------------------------------------------------------------------------------------------- sampler
+struct ngrtd_sampler {
+    int device = 0;
+    ngrtd_plan* plan = nullptr;
+    SamplerView sv{};
+    double tune_drop_fraction = 0.9;
+    long long step = 0, ndraws = 0, hist_start = 0;
+    size_t n_q = 0;
+};
+
+static double lbeta(double a, double b) { return std::lgamma(a) + std::lgamma(b) - std::lgamma(a + b); }
+
+template <int C1, int C2, bool DYN>
+static int launch_mcmc_age(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st) {
+    constexpr int NT = FWD_NT, UA = FWD_UA, MAXW = FWD_MAXW;
+    using WT = WarpTiles<C1, C2, DYN, NT, UA>;
+    ngrtd_plan* P = S->plan;
+    const long long B = S->sv.B;
+    long long nunits = (B + NT * 8 - 1) / (NT * 8);
+    int warps = pick_warps(nunits, P->nsm, MAXW);
+    if (warps > 4) warps &= ~3;
+    // shared memory: forward tables + one CH_REC record per resident chain; shrink the lag chunk until it fits
+    int lc_cap = WT::ANY_LOOP ? std::min(P->Lpad, LC_MAX) : 0;
+    size_t sh = 0;
+    for (;;) {
+        sh = (size_t)TBL_DOUBLES + (size_t)warps * NT * 8 * NCOL + (size_t)lc_cap * NCOL;
+        if (WT::ANY_D) sh += (size_t)lc_cap * NCOL + lc_cap;
+        if (DYN) sh += lc_cap + (WT::ANY_D ? lc_cap : 0);
+        sh += (size_t)warps * NT * 8 * CH_REC;
+        sh *= sizeof(double);
+        if (sh <= 227 * 1024 || lc_cap <= 64) break;
+        lc_cap = (lc_cap / 2 + 3) & ~3;
+    }
+    if (sh > 227 * 1024) return fail(NGRTD_EINVAL, "sampler: shared-memory budget exceeded");
+    auto kern = k_mcmc_age<C1, C2, DYN, NT, UA, MAXW>;
+    static thread_local size_t configured = 0;
+    if (configured < sh) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        configured = sh;
+    }
+    long long want = (nunits + warps - 1) / warps;
+    int grid = (int)std::max<long long>(1, std::min<long long>(want, P->nsm));
+    kern<<<grid, warps * 32, sh, st>>>(P->pv, S->sv, ra, lc_cap);
+    CUDA_TRY(cudaGetLastError());
+    return NGRTD_OK;
+}
+
+template <int C1, bool DYN>
+static int mcmc_c2(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st) {
+#ifdef NGRTD_EXP
+    if (S->plan->cls2 == CLS_NONE) return launch_mcmc_age<C1, CLS_NONE, DYN>(S, ra, st);
+    if constexpr (C1 == CLS_G) if (S->plan->cls2 == CLS_D) return launch_mcmc_age<C1, CLS_D, DYN>(S, ra, st);
+    return fail(NGRTD_EINVAL, "experiment build: model pair not compiled");
+#else
+    switch (S->plan->cls2) {
+        case CLS_NONE: return launch_mcmc_age<C1, CLS_NONE, DYN>(S, ra, st);
+        case CLS_P: return launch_mcmc_age<C1, CLS_P, DYN>(S, ra, st);
+        case CLS_G: return launch_mcmc_age<C1, CLS_G, DYN>(S, ra, st);
+        case CLS_D: return launch_mcmc_age<C1, CLS_D, DYN>(S, ra, st);
+    }
+    return fail(NGRTD_EINVAL, "bad model class");
+#endif
+}
+
+template <bool DYN>
+static int mcmc_c1(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st) {
+    switch (S->plan->cls1) {
+#ifndef NGRTD_EXP
+        case CLS_P: return mcmc_c2<CLS_P, DYN>(S, ra, st);
+#endif
+        case CLS_G: return mcmc_c2<CLS_G, DYN>(S, ra, st);
+        case CLS_D: return mcmc_c2<CLS_D, DYN>(S, ra, st);
+    }
+    return fail(NGRTD_EINVAL, "bad model class");
+}
+
+static int sampler_launch(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st) {
+    if (S->sv.model == 1) {
+        unsigned grid = (unsigned)((S->sv.B + 63) / 64);
+        k_mcmc_ng<<<grid, 64, 0, st>>>(S->sv, ra);
+        CUDA_TRY(cudaGetLastError());
+        return NGRTD_OK;
+    }
+#ifndef NGRTD_EXP
+    if (S->plan->dyn) return mcmc_c1<true>(S, ra, st);
+#endif
+    return mcmc_c1<false>(S, ra, st);
+}
+
+extern "C" int ngrtd_sampler_destroy(ngrtd_sampler* S) {
+    if (!S) return NGRTD_OK;
+    SamplerView& v = S->sv;
+    cudaFree(v.q); cudaFree(v.logp); cudaFree(v.lamb); cudaFree(v.scal); cudaFree(v.acc_win); cudaFree(v.acc_tot);
+    cudaFree(v.hist); cudaFree(v.wf_mean); cudaFree(v.wf_m2);
+    delete S;
+    return NGRTD_OK;
+}
+
+extern "C" int ngrtd_sampler_create(ngrtd_sampler** out, const ngrtd_sampler_cfg* cfg, ngrtd_plan* plan, int64_t nchains,
+                                    const double* q0, int32_t device) {
+    if (!out || !cfg) return fail(NGRTD_EINVAL, "sampler: null pointer");
+    *out = nullptr;
+    if (cfg->ndim < 1 || cfg->ndim > ND_MAX) return fail(NGRTD_EINVAL, "sampler: ndim must be in 1..10");
+    if (nchains < 1) return fail(NGRTD_EINVAL, "sampler: nchains must be >= 1");
+    if (cfg->tune_interval < 1) return fail(NGRTD_EINVAL, "sampler: tune_interval must be >= 1");
+    if (cfg->hist_cap < 2) return fail(NGRTD_EINVAL, "sampler: hist_cap must be >= 2");
+    if (cfg->lik_kind != NGRTD_LIK_NORMAL && cfg->lik_kind != NGRTD_LIK_STUDENTT) return fail(NGRTD_EINVAL, "sampler: unknown likelihood");
+    if (cfg->nobs < 1 || cfg->nobs > MAX_TRACER) return fail(NGRTD_EINVAL, "sampler: nobs must be in 1..8");
+    if (plan && cfg->nobs != plan->pv.ntracer) return fail(NGRTD_EINVAL, "sampler: nobs must equal the plan's tracer count");
+    if (!plan && (cfg->ngas < 1 || cfg->ngas > 5 || cfg->ngas != cfg->nobs)) return fail(NGRTD_EINVAL, "sampler: noble-gas model needs 1..5 gases = nobs");
+    if (plan) CUDA_TRY(cudaSetDevice(plan->device));
+    else if (device >= 0) CUDA_TRY(cudaSetDevice(device));
+    auto* S = new ngrtd_sampler();
+    CUDA_TRY(cudaGetDevice(&S->device));
+    S->plan = plan;
+    S->tune_drop_fraction = cfg->tune_drop_fraction;
+    SamplerView& v = S->sv;
+    v.nd = cfg->ndim;
+    v.model = plan ? 0 : 1;
+    v.sampled_mask = 0;
+    std::vector<double> start(cfg->ndim);
+    for (int d = 0; d < cfg->ndim; d++) {
+        const ngrtd_prior& pr = cfg->prior[d];
+        PriorDev pd{pr.kind, pr.target, pr.p0, pr.p1, pr.lo, pr.hi, 0.0};
+        if (pr.target < 0 || pr.target >= NVAL) { delete S; return fail(NGRTD_EINVAL, "sampler: prior target out of range"); }
+        switch (pr.kind) {
+            case NGRTD_PRIOR_UNIFORM:
+                if (!(pr.p1 > pr.p0)) { delete S; return fail(NGRTD_EINVAL, "sampler: uniform needs p1 > p0"); }
+                start[d] = 0.0;                                               // logit(1/2)
+                break;
+            case NGRTD_PRIOR_BETA: {
+                if (!(pr.p0 > 0 && pr.p1 > 0)) { delete S; return fail(NGRTD_EINVAL, "sampler: beta needs positive shapes"); }
+                pd.c = lbeta(pr.p0, pr.p1);
+                double m = pr.p0 / (pr.p0 + pr.p1);                           // test value = mean
+                start[d] = std::log(m / (1.0 - m));
+                break;
+            }
+            case NGRTD_PRIOR_NORMAL:
+                if (!(pr.p1 > 0)) { delete S; return fail(NGRTD_EINVAL, "sampler: normal needs sigma > 0"); }
+                pd.c = -0.5 * std::log(2.0 * M_PI * pr.p1 * pr.p1);
+                start[d] = pr.p0;
+                break;
+            case NGRTD_PRIOR_HALFNORMAL:
+                if (!(pr.p0 > 0)) { delete S; return fail(NGRTD_EINVAL, "sampler: halfnormal needs sigma > 0"); }
+                pd.c = 0.5 * std::log(2.0 / M_PI) - std::log(pr.p0);
+                start[d] = std::log(pr.p0 * std::sqrt(2.0 / M_PI));           // test value = mean
+                break;
+            default:
+                delete S;
+                return fail(NGRTD_EINVAL, "sampler: unknown prior kind");
+        }
+        v.pr[d] = pd;
+        v.sampled_mask |= 1u << pr.target;
+        if (q0) start[d] = q0[d];
+    }
+    v.lik_kind = cfg->lik_kind;
+    v.nu_sampled = cfg->nu_sampled;
+    v.nu_lo = cfg->nu_lo; v.nu_hi = cfg->nu_hi; v.nu_fixed = cfg->nu_fixed;
+    v.ntr = cfg->nobs;
+    for (int t = 0; t < MAX_TRACER; t++) { v.obs[t] = t < cfg->nobs ? cfg->obs_mu[t] : 0.0; v.sd[t] = t < cfg->nobs ? cfg->obs_sd[t] : 1.0; }
+    v.f2_from_f1 = cfg->f2_from_f1;
+    v.proposal_dist = cfg->proposal_dist;
+    v.de_mcz = cfg->de_mcz;
+    v.tune_target = cfg->tune_target;
+    v.tune_interval = cfg->tune_interval;
+    v.seed = cfg->seed;
+    v.chain_offset = cfg->chain_offset;
+    v.B = nchains;
+    v.hist_cap = cfg->hist_cap;
+    for (int i = 0; i < NVAL; i++) v.val_defaults[i] = 0.0;
+    if (plan) {
+        v.val_defaults[NGRTD_P_F1] = 1.0;                                     // p_dict defaults, run_age_mcmc_utils.py:73-79
+        v.val_defaults[NGRTD_P_J] = plan->pv.default_log10J;
+    } else {
+        v.gases.n = cfg->ngas;
+        for (int g = 0; g < cfg->ngas; g++) {
+            if (cfg->gases[g] < 0 || cfg->gases[g] > 4) { delete S; return fail(NGRTD_EINVAL, "sampler: gas id must be 0..4"); }
+            v.gases.id[g] = cfg->gases[g];
+        }
+    }
+    const size_t B = (size_t)nchains, nd = (size_t)cfg->ndim;
+    S->n_q = B * nd;
+    size_t hist_bytes = (size_t)cfg->hist_cap * B * nd * sizeof(double);
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    if (hist_bytes > free_b / 2) {
+        delete S;
+        return fail(NGRTD_ENOMEM, "sampler: history ring (" + std::to_string(hist_bytes >> 20) + " MiB) exceeds half of free device memory; lower hist_cap");
+    }
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&v.q, B * nd * 8)) || (e = cudaMalloc((void**)&v.logp, B * 8)) ||
+        (e = cudaMalloc((void**)&v.lamb, B * 8)) || (e = cudaMalloc((void**)&v.scal, B * 8)) ||
+        (e = cudaMalloc((void**)&v.acc_win, B * 4)) || (e = cudaMalloc((void**)&v.acc_tot, B * 8)) ||
+        (e = cudaMalloc((void**)&v.hist, hist_bytes)) || (e = cudaMalloc((void**)&v.wf_mean, B * nd * 8)) ||
+        (e = cudaMalloc((void**)&v.wf_m2, B * nd * 8))) {
+        ngrtd_sampler_destroy(S);
+        return fail(NGRTD_ENOMEM, std::string("sampler alloc: ") + cudaGetErrorString(e));
+    }
+    {
+        std::vector<double> hq(B * nd), hl(B, cfg->lamb > 0 ? cfg->lamb : 2.38 / std::sqrt(2.0 * cfg->ndim)), hs(B, cfg->scaling);
+        for (size_t b = 0; b < B; b++) for (size_t d = 0; d < nd; d++) hq[b * nd + d] = start[d];
+        CUDA_TRY(cudaMemcpy(v.q, hq.data(), B * nd * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(v.lamb, hl.data(), B * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(v.scal, hs.data(), B * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemset(v.logp, 0, B * 8));
+        CUDA_TRY(cudaMemset(v.acc_win, 0, B * 4));
+        CUDA_TRY(cudaMemset(v.acc_tot, 0, B * 8));
+        CUDA_TRY(cudaMemset(v.wf_mean, 0, B * nd * 8));
+        CUDA_TRY(cudaMemset(v.wf_m2, 0, B * nd * 8));
+    }
+    RunArgs ra{};
+    ra.mode = 1;                    // logp of the starting point
+    ra.nsteps = 1;
+    ra.thin = 1;
+    int rc = sampler_launch(S, ra, nullptr);
+    if (rc == NGRTD_OK) {
+        cudaError_t e2 = cudaDeviceSynchronize();
+        if (e2 != cudaSuccess) rc = fail(NGRTD_ECUDA, std::string("sampler init: ") + cudaGetErrorString(e2));
+    }
+    if (rc) { ngrtd_sampler_destroy(S); return rc; }
+    *out = S;
+    return NGRTD_OK;
+}
+
+extern "C" int ngrtd_sampler_run(ngrtd_sampler* S, int64_t nsteps, int32_t tune, int32_t record, int32_t thin,
+                                 double* trace_d, void* stream) {
+    if (!S) return fail(NGRTD_EINVAL, "null sampler");
+    if (nsteps < 0 || nsteps > 2000000000LL) return fail(NGRTD_EINVAL, "sampler: bad nsteps");
+    if (nsteps == 0) return NGRTD_OK;
+    if (thin < 1) return fail(NGRTD_EINVAL, "sampler: thin must be >= 1");
+    RunArgs ra{};
+    ra.step0 = S->step;
+    ra.nsteps = (int)nsteps;
+    ra.mode = 0;
+    ra.tune = tune ? 1 : 0;
+    ra.hist_start = S->hist_start;
+    ra.trace = record ? trace_d : nullptr;
+    ra.thin = thin;
+    ra.draw0 = S->ndraws;
+    ra.record = record ? 1 : 0;
+    int rc = sampler_launch(S, ra, (cudaStream_t)stream);
+    if (rc) return rc;
+    S->step += nsteps;
+    if (record) S->ndraws += (nsteps + thin - 1) / thin;
+    return NGRTD_OK;
+}
+
+extern "C" int ngrtd_sampler_stop_tuning(ngrtd_sampler* S) {
+    if (!S) return fail(NGRTD_EINVAL, "null sampler");
+    long long it = S->step - S->hist_start;              // len(self._history)
+    long long n_drop = (long long)(S->tune_drop_fraction * (double)it);
+    S->hist_start += n_drop;
+    return NGRTD_OK;
+}
+
+extern "C" int ngrtd_sampler_info(const ngrtd_sampler* S, int64_t* step, int64_t* ndraws, int64_t* hist_start) {
+    if (!S) return fail(NGRTD_EINVAL, "null sampler");
+    if (step) *step = S->step;
+    if (ndraws) *ndraws = S->ndraws;
+    if (hist_start) *hist_start = S->hist_start;
+    return NGRTD_OK;
+}
+
+__global__ void k_int_to_double(const int* a, const long long* b, long long n, double* out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = b ? (double)b[i] : (double)a[i];
+}
+
+extern "C" int ngrtd_sampler_get(ngrtd_sampler* S, int32_t what, double* out_d, void* stream) {
+    if (!S || !out_d) return fail(NGRTD_EINVAL, "sampler_get: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const SamplerView& v = S->sv;
+    size_t B = (size_t)v.B;
+    const double* src = nullptr;
+    size_t n = B;
+    switch (what) {
+        case 0: src = v.q; n = S->n_q; break;
+        case 1: src = v.logp; break;
+        case 2: src = v.lamb; break;
+        case 3: src = v.scal; break;
+        case 4:
+            k_int_to_double<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(nullptr, v.acc_tot, (long long)B, out_d);
+            CUDA_TRY(cudaGetLastError());
+            return NGRTD_OK;
+        case 5: src = v.wf_mean; n = S->n_q; break;
+        case 6: src = v.wf_m2; n = S->n_q; break;
+        default: return fail(NGRTD_EINVAL, "sampler_get: unknown selector");
+    }
+    CUDA_TRY(cudaMemcpyAsync(out_d, src, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return NGRTD_OK;
+}
+
+extern "C" int ngrtd_sampler_set(ngrtd_sampler* S, int32_t what, const double* in_d, void* stream) {
+    if (!S || !in_d) return fail(NGRTD_EINVAL, "sampler_set: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    SamplerView& v = S->sv;
+    double* dst = nullptr;
+    size_t n = (size_t)v.B;
+    switch (what) {
+        case 0: dst = v.q; n = S->n_q; break;
+        case 1: dst = v.logp; break;
+        case 2: dst = v.lamb; break;
+        case 3: dst = v.scal; break;
+        default: return fail(NGRTD_EINVAL, "sampler_set: selector must be 0..3");
+    }
+    CUDA_TRY(cudaMemcpyAsync(dst, in_d, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (what == 0) {                 // new positions: refresh logp
+        RunArgs ra{};
+        ra.mode = 1; ra.nsteps = 1; ra.thin = 1;
+        return sampler_launch(S, ra, st);
+    }
+    return NGRTD_OK;
+}
+
+extern "C" int ngrtd_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    if (!ctr || !key || !out) return fail(NGRTD_EINVAL, "philox: null pointer");
+    unsigned int* d = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d, 16));
+    k_philox_kat<<<1, 1>>>(make_uint4(ctr[0], ctr[1], ctr[2], ctr[3]), make_uint2(key[0], key[1]), d);
+    cudaError_t e = cudaMemcpy(out, d, 16, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(NGRTD_ECUDA, cudaGetErrorString(e));
     return NGRTD_OK;
 }

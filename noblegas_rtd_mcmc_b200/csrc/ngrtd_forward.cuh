@@ -346,16 +346,28 @@ __device__ __forceinline__ double lik_term_studentt(double obs, double mu, doubl
     return cst + 0.5 * log(lam / (nu * 3.14159265358979323846)) - 0.5 * (nu + 1.0) * log1p(lam * d * d / nu);
 }
 
-// ---------------------------------------------------------------- the forward (+ likelihood) kernel
-template <int C1, int C2, bool DYN, int NT, int UA, int MAXW>
-__global__ void __launch_bounds__(MAXW * 32, 1)
-k_forward(PlanView pv, SlotMap sm, const double* __restrict__ theta, long long B, double* __restrict__ out,
-          double* __restrict__ logp, LikPar lik, int lc_cap) {
+// ---------------------------------------------------------------- per-CTA scaffolding shared by the kernels
+// Shared-memory carve-up, chunk streaming of the lag tables and the unit schedule.  k_forward evaluates one
+// parameter vector per chain; k_mcmc_age (ngrtd_mcmc.cuh) runs whole Metropolis steps around eval().
+template <int C1, int C2, bool DYN, int NT, int UA>
+struct FwdCta {
     using WT = WarpTiles<C1, C2, DYN, NT, UA>;
-    const int nwarps = blockDim.x >> 5, nthreads = blockDim.x;
-    extern __shared__ __align__(128) double smem[];
     SmemView s;
-    {
+    const PlanView& pv;
+    int lc_cap, nchunks, nwarps, nthreads, tid, lane, warp;
+    double* scratch_warp;
+    bool need_J;
+
+    __device__ __forceinline__ FwdCta(const PlanView& pv_) : pv(pv_) {}
+
+    // returns the first shared-memory double not used by the forward tables
+    __device__ __forceinline__ double* setup(double* smem, int lc_cap_) {
+        lc_cap = lc_cap_;
+        nthreads = blockDim.x;
+        nwarps = nthreads >> 5;
+        tid = threadIdx.x;
+        lane = tid & 31;
+        warp = tid >> 5;
         double* p = smem;
         s.tbl = p; p += TBL_DOUBLES;       // first: keeps the 128-byte bank alignment of the two word arrays
         s.scratch = p; p += nwarps * NT * 8 * NCOL;
@@ -364,14 +376,19 @@ k_forward(PlanView pv, SlotMap sm, const double* __restrict__ theta, long long B
         s.itp = p; if (WT::ANY_D) p += lc_cap;
         s.xraw = p; if (DYN) p += lc_cap;
         s.xrawd = p; if (DYN && WT::ANY_D) p += lc_cap;
+        scratch_warp = s.scratch + warp * NT * 8 * NCOL;
+        nchunks = WT::ANY_LOOP ? (pv.Lpad + lc_cap - 1) / lc_cap : 1;
+        need_J = false;
+        for (int t = 0; t < pv.ntracer; t++) need_J |= (pv.tr[t].col_b >= 0);
+        if (WT::ANY_D) {
+            for (int i = tid; i < TBL_DOUBLES; i += nthreads) s.tbl[i] = pv.tbl[i];
+        }
+        if (nchunks == 1) load_chunk(0, pv.Lpad);     // resident tables: loaded once per launch
+        __syncthreads();
+        return p;
     }
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int j = lane & 3, r = lane >> 2;
-    double* scratch_warp = s.scratch + warp * NT * 8 * NCOL;
-    if (WT::ANY_D) {
-        for (int i = tid; i < TBL_DOUBLES; i += nthreads) s.tbl[i] = pv.tbl[i];
-    }
-    auto load_chunk = [&](int kc, int len) {
+
+    __device__ __forceinline__ void load_chunk(int kc, int len) {
         if (!WT::ANY_LOOP) return;
         const double2* gf = reinterpret_cast<const double2*>(pv.Xf + (size_t)kc * NCOL);
         double2* sf = reinterpret_cast<double2*>(s.Xf);
@@ -387,22 +404,13 @@ k_forward(PlanView pv, SlotMap sm, const double* __restrict__ theta, long long B
             if (WT::ANY_D)
                 for (int i = tid; i < len; i += nthreads) s.xrawd[i] = pv.xrawd[kc + i];
         }
-    };
-    const long long nunits = (B + NT * 8 - 1) / (NT * 8);
-    const int nchunks = WT::ANY_LOOP ? (pv.Lpad + lc_cap - 1) / lc_cap : 1;
-    bool need_J = false;
-    for (int t = 0; t < pv.ntracer; t++) need_J |= (pv.tr[t].col_b >= 0);
+    }
 
-    auto run_unit = [&](long long u, bool active, bool lockstep) {
+    // forward model of NT tiles: lane (r, j) receives tracers j, j+4 of chain r in val[t][0..1].
+    // In lock-step mode every warp of the CTA must call this the same number of times (inactive warps only
+    // take part in the chunk loads and barriers).
+    __device__ __forceinline__ void eval(const ChainPar (&par)[NT], bool active, bool lockstep, double (&val)[NT][2]) {
         WT w;
-        ChainPar par[NT];
-        long long chain[NT];
-#pragma unroll
-        for (int t = 0; t < NT; t++) {
-            chain[t] = (u * NT + t) * 8 + r;
-            long long cl = chain[t] < B ? chain[t] : B - 1;
-            par[t] = load_chain_par(theta, sm, active ? cl : 0, pv, need_J);
-        }
         w.begin(par, pv);
         if (!lockstep) {
             w.chunk(s, pv, 0, pv.Lpad / 4, lane);
@@ -416,9 +424,74 @@ k_forward(PlanView pv, SlotMap sm, const double* __restrict__ theta, long long B
                 if (active) w.chunk(s, pv, kc, len / 4, lane);
             }
         }
-        if (!active) return;
+        if (active) w.end(par, pv, scratch_warp, lane, val);
+    }
+
+    // Unit schedule.  Resident tables: static and balanced -- units are dealt round-robin to the 4*gridDim.x SM
+    // sub-partitions (warp & 3 selects the sub-partition) and, within one, round-robin to its warps.  All units
+    // cost the same, so every sub-partition carries floor or ceil of nunits/(4*grid) units and its FP64 pipe stays
+    // shared by >= 3 warps until the end (a dynamic counter let the last partial round pile onto random
+    // sub-partitions: profiles/r1_notes.md).  Long lag axis: CTA-wide rounds in lock step.
+    template <class F>
+    __device__ __forceinline__ void for_each_unit(long long nunits, F f) {
+        if (nchunks == 1) {
+            const int spc = nwarps >= 4 ? 4 : nwarps;
+            const int wq = nwarps / spc;
+            const long long slot = (long long)blockIdx.x * spc + (warp % spc);
+            const long long nslots = (long long)gridDim.x * spc;
+            for (long long i = warp / spc;; i += wq) {
+                long long u = slot + i * nslots;
+                if (u >= nunits) break;
+                f(u, true, false);
+            }
+        } else {
+            const long long ncta_units = (nunits + nwarps - 1) / nwarps;
+            for (long long cu = blockIdx.x; cu < ncta_units; cu += gridDim.x) {
+                long long u = cu * nwarps + warp;
+                f(u, u < nunits, true);
+            }
+        }
+    }
+};
+
+// sum of the likelihood terms of the tracers a lane owns (j, j+4), reduced over the 4 lanes of a chain
+__device__ __forceinline__ double lik_reduce(const LikPar& lik, int ntracer, int j, const double (&v)[2], double nu) {
+    double cst = 0.0, acc = 0.0;
+    if (lik.kind == 1) cst = lik_studentt_const(nu);
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        int tr = j + 4 * q;
+        if (tr < ntracer)
+            acc += (lik.kind == 1) ? lik_term_studentt(lik.obs[tr], v[q], lik.sd[tr], nu, cst)
+                                   : lik_term_normal(lik.obs[tr], v[q], lik.sd[tr]);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    return acc;
+}
+
+// ---------------------------------------------------------------- the forward (+ likelihood) kernel
+template <int C1, int C2, bool DYN, int NT, int UA, int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 1)
+k_forward(PlanView pv, SlotMap sm, const double* __restrict__ theta, long long B, double* __restrict__ out,
+          double* __restrict__ logp, LikPar lik, int lc_cap) {
+    extern __shared__ __align__(128) double smem[];
+    FwdCta<C1, C2, DYN, NT, UA> cta(pv);
+    cta.setup(smem, lc_cap);
+    const int j = cta.lane & 3, r = cta.lane >> 2;
+    const long long nunits = (B + NT * 8 - 1) / (NT * 8);
+    cta.for_each_unit(nunits, [&](long long u, bool active, bool lockstep) {
+        ChainPar par[NT];
+        long long chain[NT];
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+            chain[t] = (u * NT + t) * 8 + r;
+            long long cl = chain[t] < B ? chain[t] : B - 1;
+            par[t] = load_chain_par(theta, sm, active ? cl : 0, pv, cta.need_J);
+        }
         double val[NT][2];
-        w.end(par, pv, scratch_warp, lane, val);
+        cta.eval(par, active, lockstep, val);
+        if (!active) return;
 #pragma unroll
         for (int t = 0; t < NT; t++) {
             bool ok = chain[t] < B;
@@ -427,52 +500,12 @@ k_forward(PlanView pv, SlotMap sm, const double* __restrict__ theta, long long B
                 if (j + 4 < pv.ntracer) out[chain[t] * pv.ntracer + j + 4] = val[t][1];
             }
             if (logp != nullptr) {
-                double nu = 0.0, cst = 0.0, acc = 0.0;
-                if (lik.kind == 1) {
-                    nu = lik.nu[ok ? chain[t] : B - 1];
-                    cst = lik_studentt_const(nu);
-                }
-#pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    int tr = j + 4 * q;
-                    if (tr < pv.ntracer) {
-                        acc += (lik.kind == 1) ? lik_term_studentt(lik.obs[tr], val[t][q], lik.sd[tr], nu, cst)
-                                               : lik_term_normal(lik.obs[tr], val[t][q], lik.sd[tr]);
-                    }
-                }
-                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                double nu = (lik.kind == 1) ? lik.nu[ok ? chain[t] : B - 1] : 0.0;
+                double acc = lik_reduce(lik, pv.ntracer, j, val[t], nu);
                 if (j == 0 && ok) logp[chain[t]] = acc;
             }
         }
-    };
-
-    if (nchunks == 1) {
-        // Resident tables: load once, then a static, balanced schedule.  Units are dealt round-robin to the
-        // 4*gridDim.x SM sub-partitions (warp & 3 selects the sub-partition), and within a sub-partition
-        // round-robin to its warps.  All units cost the same, so every sub-partition carries floor or ceil of
-        // nunits/(4*grid) units and its FP64 pipe stays shared by >= 3 warps until the end (a dynamic counter let
-        // the last partial round pile onto random sub-partitions: profiles/r1_notes.md).
-        load_chunk(0, pv.Lpad);
-        __syncthreads();
-        const int spc = nwarps >= 4 ? 4 : nwarps;
-        const int wq = nwarps / spc;
-        const long long slot = (long long)blockIdx.x * spc + (warp % spc);
-        const long long nslots = (long long)gridDim.x * spc;
-        for (long long i = warp / spc;; i += wq) {
-            long long u = slot + i * nslots;
-            if (u >= nunits) break;
-            run_unit(u, true, false);
-        }
-    } else {
-        // long lag axis: the CTA streams X chunk by chunk, all warps in lock step
-        __syncthreads();
-        const long long ncta_units = (nunits + nwarps - 1) / nwarps;
-        for (long long cu = blockIdx.x; cu < ncta_units; cu += gridDim.x) {
-            long long u = cu * nwarps + warp;
-            run_unit(u, u < nunits, true);
-        }
-    }
+    });
 }
 
 }  // namespace ngrtd

@@ -1,0 +1,414 @@
+// ngrtd_mcmc.cuh -- device-resident batched Metropolis sampler (K5) and per-chain running statistics (K6).
+//
+// Restates the sampler the reference configures through the third-party pymc3 3.11.2 (absent from /root/reference;
+// call sites age_ens_runs_mcmc/run_age_mcmc_utils.py:286-344,388-396,412-417 and ng_interp/noble_gas_mcmc.py:224-266,
+// 408-415; semantics in SURVEY.md App. B):
+//   * free variables live in pymc3's transformed space (interval / log-odds / log transforms, log-Jacobian included)
+//   * DEMetropolisZ: q = q0 + lamb*(z1 - z2) + U(-1,1)^nd * scaling with z1 != z2 drawn from the chain's OWN history
+//     (every step, rejected or not, appends the current state), lamb = 2.38/sqrt(2 nd) tuned by acceptance rate every
+//     tune_interval steps, 90 % of the history dropped when tuning stops; metrop_select accepts iff
+//     isfinite(delta) and log U < delta.
+//   * random numbers: Philox4x32-10, key = seed, counter = (global chain id, step, purpose); a chain's trajectory is a
+//     pure function of (seed, global chain id), so results do not depend on how chains are sharded over GPUs.
+// Whole steps (propose -> transform/prior -> forward -> likelihood -> accept -> history/trace/statistics) run inside
+// one persistent kernel; a launch advances every chain by `nsteps` steps with no host round trip.
+#pragma once
+#include "ngrtd_ce.cuh"
+#include "ngrtd_forward.cuh"
+
+namespace ngrtd {
+
+constexpr int ND_MAX = 10;      // sampler dimensions
+constexpr int NVAL = 12;        // value registers: 0..10 = ForwardMod.p_dict slots, 11 = nu_ (raw, in [0,1])
+constexpr int VAL_NU = 11;
+constexpr int CH_REC = ND_MAX + ND_MAX + NVAL + 8;   // per-chain shared-memory record (doubles), age kernel
+enum PriorKind : int { PR_UNIFORM = 0, PR_BETA = 1, PR_NORMAL = 2, PR_HALFNORMAL = 3 };
+
+struct PriorDev {
+    int kind;
+    int target;          // value register written by this dimension
+    double p0, p1;       // uniform: a, b | beta: alpha, beta | normal: mu, sigma | halfnormal: sigma, -
+    double lo, hi;       // beta: affine map of the [0,1] variable onto [lo, hi]
+    double c;            // normalising constant of the log density
+};
+
+struct SamplerView {
+    int nd;
+    PriorDev pr[ND_MAX];
+    int model;               // 0: age model (convolution plan), 1: noble-gas closed-equilibrium model
+    int lik_kind;            // 0 normal, 1 student-t
+    int nu_sampled;          // 1: nu = nu_lo + (nu_hi - nu_lo) * val[VAL_NU]
+    double nu_lo, nu_hi, nu_fixed;
+    int ntr;
+    double obs[MAX_TRACER], sd[MAX_TRACER];
+    int f2_from_f1;          // f2 = 1 - f1 (run_age_mcmc_utils.py:304)
+    unsigned int sampled_mask;   // bit t set: value register t is driven by a sampler dimension
+    int proposal_dist;       // 0 uniform(-1,1), 1 normal(0,1)
+    int de_mcz;              // 1: DE-MC-Z proposals, 0: plain random walk
+    int tune_target;         // 0 lambda, 1 scaling
+    int tune_interval;
+    unsigned long long seed;
+    long long chain_offset;  // global id of local chain 0 (shard offset)
+    long long B;
+    double* q;               // [B, nd] transformed state
+    double* logp;            // [B]
+    double* lamb;            // [B]
+    double* scal;            // [B]
+    int* acc_win;            // [B] accepted since the last tuning point
+    long long* acc_tot;      // [B] accepted since creation
+    double* hist;            // [cap, B, nd] ring of past states
+    int hist_cap;
+    double* wf_mean;         // [B, nd] running mean of the natural values (Welford)
+    double* wf_m2;           // [B, nd] running sum of squared deviations
+    GasList gases;           // noble-gas model: modelled gases
+    double val_defaults[NVAL];   // value registers not driven by a sampler dimension (p_dict defaults)
+};
+
+struct RunArgs {
+    long long step0;         // global index of the first step of this launch
+    int nsteps;
+    int mode;                // 0: Metropolis steps, 1: evaluate logp of the current state (initialisation)
+    int tune;                // 1: tuning phase
+    long long hist_start;    // logical index of the oldest valid history entry
+    double* trace;           // [ndraw, B, nd] natural values (or nullptr)
+    int thin;
+    long long draw0;         // draws recorded before this launch (trace row / Welford count offset)
+    int record;              // 1: record trace rows and statistics
+};
+
+// ---------------------------------------------------------------- Philox4x32-10 (Salmon et al., SC'11)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+    const unsigned int M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        unsigned int hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        unsigned int hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += W0;
+        k.y += W1;
+    }
+    return c;
+}
+__device__ __forceinline__ uint4 chain_rng(unsigned long long seed, long long chain, long long step, unsigned int purpose) {
+    uint4 c = make_uint4((unsigned int)chain, (unsigned int)((unsigned long long)chain >> 32), (unsigned int)step,
+                         purpose | ((unsigned int)((unsigned long long)step >> 32) << 16));
+    uint2 k = make_uint2((unsigned int)seed, (unsigned int)(seed >> 32));
+    return philox4x32_10(c, k);
+}
+__device__ __forceinline__ double u01(unsigned int a, unsigned int b) {   // uniform on (0,1), 53 bits, never 0 or 1
+    unsigned long long x = ((unsigned long long)a << 32) | b;
+    return ((double)(x >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+constexpr unsigned int RNG_SELECT = 0x100u;    // purpose of the (iz1, iz2, accept-uniform) draw
+
+// ---------------------------------------------------------------- priors and transforms (pymc3 3.11.2)
+__device__ __forceinline__ double softplus(double y) { return y > 0.0 ? y + log1p(exp(-y)) : log1p(exp(y)); }
+
+// transformed coordinate x -> natural value v; returns log prior density + log |Jacobian|
+__device__ __forceinline__ double transform_dim(const PriorDev& pr, double x, double& v) {
+    switch (pr.kind) {
+        case PR_UNIFORM: {      // interval transform: v = a + (b-a) sigmoid(x); logp + jac = log sig(x) + log sig(-x)
+            double sp = softplus(-x);
+            v = pr.p0 + (pr.p1 - pr.p0) * exp(-sp);
+            return -2.0 * sp - x;
+        }
+        case PR_BETA: {         // log-odds transform; natural value mapped affinely onto [lo, hi]
+            double sp = softplus(-x);
+            v = pr.lo + (pr.hi - pr.lo) * exp(-sp);
+            return pr.p0 * (-sp) + pr.p1 * (-(x + sp)) - pr.c;
+        }
+        case PR_NORMAL: {
+            double z = (x - pr.p0) / pr.p1;
+            v = x;
+            return pr.c - 0.5 * z * z;
+        }
+        default: {              // half-normal, log transform
+            v = exp(x);
+            return pr.c - v * v / (2.0 * pr.p0 * pr.p0) + x;
+        }
+    }
+}
+
+// pymc3 step_methods/metropolis.py tune(): rescale by acceptance rate
+__device__ __forceinline__ double tune_factor(double acc_rate) {
+    if (acc_rate < 0.001) return 0.1;
+    if (acc_rate < 0.05) return 0.5;
+    if (acc_rate < 0.2) return 0.9;
+    if (acc_rate > 0.95) return 10.0;
+    if (acc_rate > 0.75) return 2.0;
+    if (acc_rate > 0.5) return 1.1;
+    return 1.0;
+}
+
+__device__ __forceinline__ double proposal_noise(int dist, uint4 e) {
+    double u = u01(e.x, e.y);
+    if (dist == 0) return 2.0 * u - 1.0;
+    double u2 = u01(e.z, e.w);
+    return sqrt(-2.0 * log(u)) * cospi(2.0 * u2);
+}
+
+// history ring: logical entry e lives in slot e % cap
+__device__ __forceinline__ size_t hist_off(const SamplerView& sv, long long e, long long chain) {
+    return ((size_t)(e % sv.hist_cap) * (size_t)sv.B + (size_t)chain) * (size_t)sv.nd;
+}
+
+// Welford update + trace row for one dimension
+__device__ __forceinline__ void record_dim(const SamplerView& sv, const RunArgs& ra, long long chain, int d, double v,
+                                           long long draw) {
+    if (ra.trace) ra.trace[((size_t)(draw - ra.draw0) * (size_t)sv.B + (size_t)chain) * sv.nd + d] = v;
+    size_t o = (size_t)chain * sv.nd + d;
+    double n = (double)(draw + 1);
+    double mean = sv.wf_mean[o];
+    double dl = v - mean;
+    mean += dl / n;
+    sv.wf_mean[o] = mean;
+    sv.wf_m2[o] += dl * (v - mean);
+}
+
+// ---------------------------------------------------------------- age model: one warp = NT tiles of 8 chains
+template <int C1, int C2, bool DYN, int NT, int UA, int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 1)
+k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
+    extern __shared__ __align__(128) double smem[];
+    FwdCta<C1, C2, DYN, NT, UA> cta(pv);
+    double* rec_base = cta.setup(smem, lc_cap);
+    const int lane = cta.lane, j = lane & 3, r = lane >> 2;
+    double* rec_warp = rec_base + (size_t)cta.warp * NT * 8 * CH_REC;
+    const long long B = sv.B;
+    const long long nunits = (B + NT * 8 - 1) / (NT * 8);
+    LikPar lik;
+    lik.kind = sv.lik_kind;
+#pragma unroll
+    for (int t = 0; t < MAX_TRACER; t++) { lik.obs[t] = sv.obs[t]; lik.sd[t] = sv.sd[t]; }
+    lik.nu = nullptr;
+
+    cta.for_each_unit(nunits, [&](long long u, bool active, bool lockstep) {
+        long long chain[NT];
+        double* rec[NT];
+        bool ok[NT];
+        // ---- load the chain state into shared memory: qs | qp | vals | scalars(logp, lamb, scal, lpsum, uacc, acc_win, acc_tot)
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+            chain[t] = (u * NT + t) * 8 + r;
+            ok[t] = active && chain[t] < B;
+            long long cl = (active && chain[t] < B) ? chain[t] : 0;
+            rec[t] = rec_warp + (size_t)(t * 8 + r) * CH_REC;
+            for (int d = j; d < sv.nd; d += 4) rec[t][d] = sv.q[cl * sv.nd + d];
+            for (int v = j; v < NVAL; v += 4) rec[t][2 * ND_MAX + v] = sv.val_defaults[v];
+            if (j == 0) {
+                double* sc = rec[t] + 2 * ND_MAX + NVAL;
+                sc[0] = sv.logp[cl];
+                sc[1] = sv.lamb[cl];
+                sc[2] = sv.scal[cl];
+                sc[5] = (double)sv.acc_win[cl];
+                sc[6] = (double)sv.acc_tot[cl];
+            }
+        }
+        __syncwarp();
+        const int nsteps = ra.mode == 1 ? 1 : ra.nsteps;
+        for (int s = 0; s < nsteps; s++) {
+            const long long i = ra.step0 + s;
+            ChainPar par[NT];
+            double nu[NT];
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+                double* qs = rec[t];
+                double* qp = rec[t] + ND_MAX;
+                double* vals = rec[t] + 2 * ND_MAX;
+                double* sc = vals + NVAL;
+                const long long gchain = sv.chain_offset + chain[t];
+                // -- tuning point (pymc3 DEMetropolisZ.astep: rescale before proposing)
+                if (ra.mode == 0 && ra.tune && i > 0 && (i % sv.tune_interval) == 0 && j == 0) {
+                    double f = tune_factor(sc[5] / (double)sv.tune_interval);
+                    if (sv.tune_target == 0) sc[1] *= f; else sc[2] *= f;
+                    sc[5] = 0.0;
+                }
+                __syncwarp();
+                // -- proposal
+                long long nvalid = i - ra.hist_start;
+                if (nvalid > sv.hist_cap) nvalid = sv.hist_cap;
+                const bool use_de = ra.mode == 0 && sv.de_mcz && nvalid > 1;
+                uint4 sel = chain_rng(sv.seed, gchain, i, RNG_SELECT);
+                long long e1 = 0, e2 = 0;
+                if (use_de) {
+                    unsigned int iz1 = __umulhi(sel.x, (unsigned int)nvalid);
+                    unsigned int iz2 = __umulhi(sel.y, (unsigned int)(nvalid - 1));
+                    if (iz2 >= iz1) iz2++;
+                    e1 = i - nvalid + iz1;
+                    e2 = i - nvalid + iz2;
+                }
+                const double lamb = sc[1], scal = sc[2];
+                double lps = 0.0;
+                for (int d = j; d < sv.nd; d += 4) {
+                    double qn = qs[d];
+                    if (ra.mode == 0) {
+                        double eps = proposal_noise(sv.proposal_dist, chain_rng(sv.seed, gchain, i, (unsigned int)d));
+                        if (use_de && ok[t]) qn += lamb * (sv.hist[hist_off(sv, e1, chain[t]) + d] - sv.hist[hist_off(sv, e2, chain[t]) + d]);
+                        qn += eps * scal;
+                    }
+                    qp[d] = qn;
+                    double v;
+                    lps += transform_dim(sv.pr[d], qn, v);
+                    vals[sv.pr[d].target] = v;
+                }
+                lps += __shfl_xor_sync(0xffffffffu, lps, 1);
+                lps += __shfl_xor_sync(0xffffffffu, lps, 2);
+                if (j == 0) { sc[3] = lps; sc[4] = u01(sel.z, sel.w); }
+                __syncwarp();
+                // -- natural parameters of the forward model
+                ChainPar& p = par[t];
+                p.tau1 = vals[0];
+                p.tau2 = vals[1];
+                p.f1 = vals[2];
+                p.f2 = sv.f2_from_f1 ? 1.0 - vals[2] : vals[3];
+                p.eta1 = pv.eta1_is_one ? 1.0 : vals[4];
+                p.eta2 = pv.eta2_is_one ? 1.0 : vals[5];
+                p.D1 = vals[6];
+                p.D2 = vals[7];
+                p.Jlin = cta.need_J ? exp10(vals[8]) : 0.0;
+                p.lam_cfc = (sv.sampled_mask & (1u << 9)) ? LN2 / vals[9] : 0.0;
+                p.lamsf6 = vals[10];
+                nu[t] = sv.nu_sampled ? sv.nu_lo + (sv.nu_hi - sv.nu_lo) * vals[VAL_NU] : sv.nu_fixed;
+            }
+            double val[NT][2];
+            cta.eval(par, active, lockstep, val);
+            if (!active) continue;
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+                double* qs = rec[t];
+                double* qp = rec[t] + ND_MAX;
+                double* sc = rec[t] + 2 * ND_MAX + NVAL;
+                double ll = lik_reduce(lik, pv.ntracer, j, val[t], nu[t]);
+                double lpn = sc[3] + ll;
+                double delta = lpn - sc[0];
+                bool acc = ra.mode == 1 || (isfinite(delta) && log(sc[4]) < delta);    // metrop_select
+                __syncwarp();
+                if (acc) {
+                    for (int d = j; d < sv.nd; d += 4) qs[d] = qp[d];
+                    if (j == 0) { sc[0] = lpn; if (ra.mode == 0) { sc[5] += 1.0; sc[6] += 1.0; } }
+                }
+                __syncwarp();
+                if (ra.mode == 0 && ok[t]) {
+                    size_t ho = hist_off(sv, i, chain[t]);                              // history.append(q_new)
+                    for (int d = j; d < sv.nd; d += 4) sv.hist[ho + d] = qs[d];
+                    if (ra.record && ((i - ra.step0) % ra.thin) == 0) {
+                        long long draw = ra.draw0 + (i - ra.step0) / ra.thin;
+                        for (int d = j; d < sv.nd; d += 4) {
+                            double v;
+                            transform_dim(sv.pr[d], qs[d], v);
+                            record_dim(sv, ra, chain[t], d, v, draw);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- store the chain state
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+            if (!ok[t]) continue;
+            for (int d = j; d < sv.nd; d += 4) sv.q[chain[t] * sv.nd + d] = rec[t][d];
+            if (j == 0) {
+                double* sc = rec[t] + 2 * ND_MAX + NVAL;
+                sv.logp[chain[t]] = sc[0];
+                sv.lamb[chain[t]] = sc[1];
+                sv.scal[chain[t]] = sc[2];
+                sv.acc_win[chain[t]] = (int)sc[5];
+                sv.acc_tot[chain[t]] = (long long)sc[6];
+            }
+        }
+        __syncwarp();
+    });
+}
+
+// ---------------------------------------------------------------- noble-gas CE model: one chain per thread
+// value registers (ng_interp/noble_gas_mcmc.py:224-250): 0 log10 Ae, 1 log10 F, 2 E, 3 m, 4 b, 11 nu_;  T = (E - b)/m
+__global__ void k_mcmc_ng(SamplerView sv, RunArgs ra) {
+    const long long chain = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (chain >= sv.B) return;
+    const long long gchain = sv.chain_offset + chain;
+    double qs[ND_MAX], qp[ND_MAX], vals[NVAL];
+    for (int d = 0; d < sv.nd; d++) qs[d] = sv.q[chain * sv.nd + d];
+    for (int v = 0; v < NVAL; v++) vals[v] = sv.val_defaults[v];
+    double logp = sv.logp[chain], lamb = sv.lamb[chain], scal = sv.scal[chain];
+    int acc_win = sv.acc_win[chain];
+    long long acc_tot = sv.acc_tot[chain];
+    const int nsteps = ra.mode == 1 ? 1 : ra.nsteps;
+    for (int s = 0; s < nsteps; s++) {
+        const long long i = ra.step0 + s;
+        if (ra.mode == 0 && ra.tune && i > 0 && (i % sv.tune_interval) == 0) {
+            double f = tune_factor((double)acc_win / (double)sv.tune_interval);
+            if (sv.tune_target == 0) lamb *= f; else scal *= f;
+            acc_win = 0;
+        }
+        long long nvalid = i - ra.hist_start;
+        if (nvalid > sv.hist_cap) nvalid = sv.hist_cap;
+        const bool use_de = ra.mode == 0 && sv.de_mcz && nvalid > 1;
+        uint4 sel = chain_rng(sv.seed, gchain, i, RNG_SELECT);
+        size_t o1 = 0, o2 = 0;
+        if (use_de) {
+            unsigned int iz1 = __umulhi(sel.x, (unsigned int)nvalid);
+            unsigned int iz2 = __umulhi(sel.y, (unsigned int)(nvalid - 1));
+            if (iz2 >= iz1) iz2++;
+            o1 = hist_off(sv, i - nvalid + iz1, chain);
+            o2 = hist_off(sv, i - nvalid + iz2, chain);
+        }
+        double lps = 0.0;
+        for (int d = 0; d < sv.nd; d++) {
+            double qn = qs[d];
+            if (ra.mode == 0) {
+                double eps = proposal_noise(sv.proposal_dist, chain_rng(sv.seed, gchain, i, (unsigned int)d));
+                if (use_de) qn += lamb * (sv.hist[o1 + d] - sv.hist[o2 + d]);
+                qn += eps * scal;
+            }
+            qp[d] = qn;
+            double v;
+            lps += transform_dim(sv.pr[d], qn, v);
+            vals[sv.pr[d].target] = v;
+        }
+        // forward model: ce_exc_wrapper (ng_interp/noble_gas_mcmc.py:205-213) with T from the lapse-rate line (:240)
+        double Ae = exp10(vals[0]), F = exp10(vals[1]), E = vals[2];
+        double T = (E - vals[4]) / vals[3];
+        double P = ce_lapse_rate(E);
+        double nu = sv.nu_sampled ? sv.nu_lo + (sv.nu_hi - sv.nu_lo) * vals[VAL_NU] : sv.nu_fixed;
+        double cst = sv.lik_kind == 1 ? lik_studentt_const(nu) : 0.0;
+        double ll = 0.0;
+        for (int g = 0; g < sv.gases.n; g++) {
+            double mu = ce_eval(0, sv.gases.id[g], E, T, Ae, F, P, 0.0);
+            ll += sv.lik_kind == 1 ? lik_term_studentt(sv.obs[g], mu, sv.sd[g], nu, cst) : lik_term_normal(sv.obs[g], mu, sv.sd[g]);
+        }
+        double lpn = lps + ll;
+        double delta = lpn - logp;
+        bool acc = ra.mode == 1 || (isfinite(delta) && log(u01(sel.z, sel.w)) < delta);
+        if (acc) {
+            for (int d = 0; d < sv.nd; d++) qs[d] = qp[d];
+            logp = lpn;
+            if (ra.mode == 0) { acc_win++; acc_tot++; }
+        }
+        if (ra.mode == 0) {
+            size_t ho = hist_off(sv, i, chain);
+            for (int d = 0; d < sv.nd; d++) sv.hist[ho + d] = qs[d];
+            if (ra.record && ((i - ra.step0) % ra.thin) == 0) {
+                long long draw = ra.draw0 + (i - ra.step0) / ra.thin;
+                for (int d = 0; d < sv.nd; d++) {
+                    double v;
+                    transform_dim(sv.pr[d], qs[d], v);
+                    record_dim(sv, ra, chain, d, v, draw);
+                }
+            }
+        }
+    }
+    for (int d = 0; d < sv.nd; d++) sv.q[chain * sv.nd + d] = qs[d];
+    sv.logp[chain] = logp;
+    sv.lamb[chain] = lamb;
+    sv.scal[chain] = scal;
+    sv.acc_win[chain] = acc_win;
+    sv.acc_tot[chain] = acc_tot;
+}
+
+__global__ void k_philox_kat(uint4 c, uint2 k, unsigned int* out) {
+    uint4 r = philox4x32_10(c, k);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+}  // namespace ngrtd

@@ -1,0 +1,126 @@
+"""Posterior diagnostics on host arrays posterior[chain, draw]: rank-normalised split R-hat, bulk ESS, MCSE, HDI
+(Vehtari et al. 2021 -- the quantities ArviZ 0.11.4 `az.summary` reports for the reference at
+age_ens_runs_mcmc/run_age_mcmc.py:234 and ng_interp/noble_gas_mcmc.py:450), plus the moment-based estimators used
+when chains are too many to keep traces (per-chain Welford moments gathered across GPUs)."""
+import numpy as np
+from scipy import stats as _st
+
+
+def _split(a):
+    n = a.shape[1] // 2
+    return np.concatenate([a[:, :n], a[:, a.shape[1] - n:]], axis=0)
+
+
+def _z_scale(a):
+    r = _st.rankdata(a, method="average").reshape(a.shape)
+    return _st.norm.ppf((r - 0.375) / (a.size + 0.25))
+
+
+def _autocov(x):
+    n = x.shape[-1]
+    m = 1 << int(np.ceil(np.log2(2 * n)))
+    xc = x - x.mean(axis=-1, keepdims=True)
+    f = np.fft.rfft(xc, m, axis=-1)
+    ac = np.fft.irfft(f * np.conj(f), m, axis=-1)[..., :n]
+    return ac / n
+
+
+def _rhat_plain(a):
+    m, n = a.shape
+    cm = a.mean(axis=1)
+    W = a.var(axis=1, ddof=1).mean()
+    Bn = cm.var(ddof=1) if m > 1 else 0.0
+    return float(np.sqrt(((n - 1) / n * W + Bn) / W))
+
+
+def rhat(a):
+    """Rank-normalised split R-hat (max of bulk and folded)."""
+    a = np.asarray(a, dtype=np.float64)
+    s = _split(a)
+    bulk = _rhat_plain(_z_scale(s))
+    folded = _rhat_plain(_z_scale(np.abs(s - np.median(s))))
+    return max(bulk, folded)
+
+
+def _ess_raw(a):
+    m, n = a.shape
+    if n < 4:
+        return float("nan")
+    acov = _autocov(a)
+    cm = a.mean(axis=1)
+    mean_var = acov[:, 0].mean() * n / (n - 1.0)
+    var_plus = mean_var * (n - 1.0) / n
+    if m > 1:
+        var_plus += cm.var(ddof=1)
+    rho = np.zeros(n)
+    rho_even = 1.0
+    rho[0] = rho_even
+    rho_odd = 1.0 - (mean_var - acov[:, 1].mean()) / var_plus
+    rho[1] = rho_odd
+    t = 1
+    while t < n - 3 and (rho_even + rho_odd) > 0.0:
+        rho_even = 1.0 - (mean_var - acov[:, t + 1].mean()) / var_plus
+        rho_odd = 1.0 - (mean_var - acov[:, t + 2].mean()) / var_plus
+        if rho_even + rho_odd >= 0:
+            rho[t + 1] = rho_even
+            rho[t + 2] = rho_odd
+        t += 2
+    max_t = t - 2
+    if rho_even > 0:
+        rho[max_t + 1] = rho_even
+    t = 1
+    while t <= max_t - 2:
+        if rho[t + 1] + rho[t + 2] > rho[t - 1] + rho[t]:
+            rho[t + 1] = (rho[t - 1] + rho[t]) / 2.0
+            rho[t + 2] = rho[t + 1]
+        t += 2
+    ess = m * n
+    tau = -1.0 + 2.0 * rho[:max_t + 1].sum() + rho[max_t + 1:max_t + 2].sum()
+    tau = max(tau, 1.0 / np.log10(ess))
+    return float(ess / tau)
+
+
+def ess_bulk(a):
+    return _ess_raw(_z_scale(_split(np.asarray(a, dtype=np.float64))))
+
+
+def ess_mean(a):
+    return _ess_raw(_split(np.asarray(a, dtype=np.float64)))
+
+
+def hdi(x, prob=0.94):
+    x = np.sort(np.asarray(x, dtype=np.float64).ravel())
+    n = len(x)
+    k = int(np.floor(prob * n))
+    w = x[k:] - x[:n - k]
+    i = int(np.argmin(w))
+    return float(x[i]), float(x[i + k])
+
+
+def summary(posterior):
+    """posterior: dict var -> array [chain, draw].  Returns dict var -> row with the az.summary columns + median."""
+    out = {}
+    for k, a in posterior.items():
+        a = np.asarray(a, dtype=np.float64)
+        sd = a.std(ddof=1)
+        em = ess_mean(a)
+        lo, hi = hdi(a)
+        out[k] = {"mean": float(a.mean()), "sd": float(sd), "hdi_3%": lo, "hdi_97%": hi,
+                  "mcse_mean": float(sd / np.sqrt(em)) if em == em and em > 0 else float("nan"),
+                  "ess_bulk": ess_bulk(a), "r_hat": rhat(a), "median": float(np.median(a))}
+    return out
+
+
+# ---------------------------------------------------------------------------------------- moment-based (many chains)
+def moments_summary(n, mean, m2):
+    """Per-chain Welford moments (n draws each; mean, m2 of shape [chains, ndim]) -> pooled mean/sd, the classic
+    R-hat sqrt(((n-1)/n W + B/n)/W) and the many-chain ESS estimate M n var+/B (BDA3 eq. 11.4 with the between-chain
+    variance as the variance of the chain means).  Valid when the number of chains is large."""
+    mean = np.asarray(mean, dtype=np.float64)
+    m2 = np.asarray(m2, dtype=np.float64)
+    M = mean.shape[0]
+    W = (m2 / (n - 1.0)).mean(axis=0)
+    Bn = mean.var(axis=0, ddof=1)                    # B / n
+    var_plus = (n - 1.0) / n * W + Bn
+    return {"mean": mean.mean(axis=0), "sd": np.sqrt(var_plus), "r_hat": np.sqrt(var_plus / W),
+            "ess": M * var_plus / Bn, "mcse_mean": np.sqrt(Bn / M), "chains": M, "draws_per_chain": n}

@@ -1,0 +1,43 @@
+"""Multi-GPU plumbing: chains shard over ranks (one process per GPU, torch.distributed over NCCL/NVLink); the only
+collective is the all-gather of per-chain statistics for R-hat / ESS.  On CPU test runs the same code
+goes through the gloo backend."""
+import numpy as np
+
+
+def shard(total, rank, world):
+    """Contiguous block of global chain ids for `rank`: (offset, count).  Philox counters use global ids, so a chain's
+    trajectory does not depend on the sharding."""
+    base, rem = divmod(int(total), int(world))
+    count = base + (1 if rank < rem else 0)
+    offset = rank * base + min(rank, rem)
+    return offset, count
+
+
+def gather_chain_stats(mean_t, m2_t):
+    """All-gather per-chain Welford moments [chains_local, ndim] from every rank -> ([chains_total, ndim], same).
+    Shards may differ in size by one chain; tensors are padded to the maximum and trimmed after the gather."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return mean_t, m2_t
+    world = dist.get_world_size()
+    n_local = torch.tensor([mean_t.shape[0]], dtype=torch.int64, device=mean_t.device)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local)
+    counts = [int(c.item()) for c in counts]
+    nmax = max(counts)
+    packed = torch.zeros((nmax, 2 * mean_t.shape[1]), dtype=mean_t.dtype, device=mean_t.device)
+    packed[:mean_t.shape[0], :mean_t.shape[1]] = mean_t
+    packed[:mean_t.shape[0], mean_t.shape[1]:] = m2_t
+    bufs = [torch.empty_like(packed) for _ in range(world)]
+    dist.all_gather(bufs, packed)
+    allp = torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+    nd = mean_t.shape[1]
+    return allp[:, :nd].contiguous(), allp[:, nd:].contiguous()
+
+
+def global_summary(n_draws, mean_t, m2_t):
+    """R-hat / ESS / pooled moments over the chains of ALL ranks (identical on every rank)."""
+    from . import diagnostics
+    mean_all, m2_all = gather_chain_stats(mean_t, m2_t)
+    return diagnostics.moments_summary(float(n_draws), mean_all.cpu().numpy(), m2_all.cpu().numpy())

@@ -105,3 +105,79 @@ class ForwardMod(object):
     def perform(self, node, inputs, outputs):
         """Forward model for one parameter vector (inputs[0]), result in outputs[0][0] as in the reference."""
         outputs[0][0] = np.array(self.perform_batch(np.asarray(inputs[0], dtype=np.float64).reshape(1, -1))[0])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Model builder + sampler driver: the role of conv_mcmc (run_age_mcmc_utils.py:189-429 of the reference)
+# ---------------------------------------------------------------------------------------------------------------
+class conv_mcmc(object):
+    """Same constructor as the reference; priors, observation errors, likelihood and sampler settings follow
+    build_mcmc_model_joint_sT / sample_mcmc (:275-429).  Plotting and netcdf output are out of scope."""
+
+    def __init__(self, well, tracer, obs_kwgs, conv_kwgs, prior_kwgs, savedir=None, savenum=None):
+        self.well = well
+        self.tracer = list(tracer)
+        g = prior_kwgs.get
+        self.par_names = list(g('par_names', []))
+        self.obs = obs_kwgs
+        self.conv_kwgs = conv_kwgs
+        self.mod_type1 = conv_kwgs.get('mod_type1', False)
+        self.mod_type2 = conv_kwgs.get('mod_type2', False)
+        self.prior_kwgs = dict(prior_kwgs)
+        self.savenum = savenum
+        self.idata = None
+
+    # ---- :286-344
+    def build_priors(self):
+        from .sampler import prior
+        pk = self.prior_kwgs
+        pri = [prior("uniform", "tau1", pk['tau1_low'], pk['tau1_high']),
+               prior("beta", "nu_", 2.0, 0.1, 0.0, 1.0)]                       # nu = nu_*(30-5)+5   (:291-292)
+        if 'J' in self.par_names:
+            pri.append(prior("normal", "J", pk['J_mu'], pk['J_sd']))
+        if self.mod_type2:
+            pri.append(prior("uniform", "tau2", pk['tau2_low'], pk['tau2_high']))
+            pri.append(prior("uniform", "f1", pk['f1_low'], pk['f1_high']))
+        if self.mod_type1 == 'exp_pist_flow':
+            pri.append(prior("uniform", "eta1", pk['eta1_low'], pk['eta1_high']))
+        if self.mod_type2 == 'exp_pist_flow':
+            pri.append(prior("uniform", "eta2", pk['eta2_low'], pk['eta2_high']))
+        if self.mod_type1 == 'dispersion':
+            pri.append(prior("uniform", "D1", pk['D1_low'], pk['D1_high']))
+        if self.mod_type2 == 'dispersion':
+            pri.append(prior("uniform", "D2", pk['D2_low'], pk['D2_high']))
+        if 'thalf_cfc' in self.par_names:
+            pri.append(prior("beta", "thalf_cfc", 2.0, 2.0, pk['cfc_thalf_lo'], pk['cfc_thalf_hi']))
+        if 'lamsf6' in self.par_names:
+            pri.append(prior("halfnormal", "lamsf6", 0.5 / 3))
+        return pri
+
+    # ---- :353-356
+    def observations(self):
+        mu = np.array([np.asarray(self.obs[w]['obs_df'], dtype=np.float64).mean() for w in self.tracer])
+        nerr = np.array([np.asarray(self.obs[w]['obs_df'], dtype=np.float64).std() for w in self.tracer])
+        perr = mu * np.array([self.obs[w]['obs_perr'] for w in self.tracer])
+        return mu, nerr + perr
+
+    def sample_mcmc(self, chains=3, tune=10000, draws=10000, random_seed=123423, tune_interval=1000, thin=1,
+                    likelihood="studentt", hist_cap=None):
+        """mc.DEMetropolisZ(tune_interval=1000); mc.sample(tune=10000, draws=10000, chains=3, ...) (:412-417).
+        Returns {'posterior': {var: ndarray[chain, draw]}, 'sample_stats': {...}}."""
+        ckw = {t: dict(self.conv_kwgs[t], mod_type1=self.mod_type1, mod_type2=self.mod_type2) for t in self.tracer}
+        joint = JointForwardMod(ckw, self.par_names, self.tracer)
+        from .sampler import Sampler
+        pri = self.build_priors()
+        mu, err = self.observations()
+        smp = Sampler(pri, mu, err, chains, plan=joint.plan, lik=likelihood, nu_range=(5.0, 30.0),
+                      f2_from_f1=bool(self.mod_type2), tune_interval=tune_interval,
+                      hist_cap=hist_cap or (tune + draws), seed=random_seed)
+        trace = smp.sample(tune, draws, thin=thin).cpu().numpy()            # [draw, chain, dim]
+        post = {n: trace[:, :, i].T.copy() for i, n in enumerate(smp.names)}
+        post['nu'] = post['nu_'] * (30.0 - 5.0) + 5.0
+        if self.mod_type2:
+            post['f2'] = 1.0 - post['f1']
+            post['tau'] = post['f1'] * post['tau1'] + post['f2'] * post['tau2']          # :305
+        self.idata = {'posterior': post,
+                      'sample_stats': {'accept_rate': smp.get("accepted").cpu().numpy() / float(tune + draws),
+                                       'lamb': smp.get("lamb").cpu().numpy()}}
+        return self.idata

@@ -208,6 +208,24 @@ def main():
             Pv[i], Pl[i] = o.vapor_pressure(), o.lapse_rate()
     np.savez_compressed(os.path.join(GOLD, "ce_model.npz"), E=E, T=T, Ae=Ae, F=F, P_vapor=Pv, P_lapse=Pl,
                         J_flux=np.array(ngu.J_flux(1, 2700, 1000, 3.7, 10.2, 0.05)), **res)
+    # ---- posterior known-answer fixture for config 1 (the only posterior summaries the reference ships) ----
+    import csv
+    import json
+    ng_dir = os.path.join(ref_shims.REFERENCE_ROOT, "ng_interp")
+    post = {"source": "ng_interp/ng_optPLM{1,6,7}.csv (az.summary + median) and panga_comp/ng_conc_4_panga.csv of the reference",
+            "wells": {}}
+    obs = {}
+    with open(os.path.join(ng_dir, "panga_comp", "ng_conc_4_panga.csv")) as f:
+        for row in csv.DictReader(f):
+            obs[row["wells"]] = {g: float(row[g]) for g in ("He", "Ne", "Ar", "Kr", "Xe")}
+    for w in ("PLM1", "PLM6", "PLM7"):
+        with open(os.path.join(ng_dir, "ng_opt%s.csv" % w)) as f:
+            rows = list(csv.reader(f))
+        hdr = rows[0][1:]
+        post["wells"][w] = {"obs": obs[w], "summary": {r[0]: dict(zip(hdr, map(float, r[1:]))) for r in rows[1:] if r}}
+    with open(os.path.join(GOLD, "ng_posterior.json"), "w") as f:
+        json.dump(post, f, indent=1)
+
     print("golden vectors written to", GOLD)
     for f in sorted(os.listdir(GOLD)):
         print("  %-24s %8d bytes" % (f, os.path.getsize(os.path.join(GOLD, f))))
