@@ -683,7 +683,7 @@ static int launch_mcmc_age(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st)
         sh = (size_t)TBL_DOUBLES + (size_t)warps * NT * 8 * NCOL + (size_t)lc_cap * NCOL;
         if (WT::ANY_D) sh += (size_t)lc_cap * NCOL + lc_cap;
         if (DYN) sh += lc_cap + (WT::ANY_D ? lc_cap : 0);
-        sh += (size_t)warps * NT * 8 * CH_REC;
+        sh += (size_t)warps * NT * 8 * CH_REC + (sizeof(PriorDev) * ND_MAX + 7) / 8;
         sh *= sizeof(double);
         if (sh <= 227 * 1024 || lc_cap <= 64) break;
         lc_cap = (lc_cap / 2 + 3) & ~3;

@@ -23,14 +23,19 @@
 
 namespace ngrtd {
 
+// All kernels of the library use this one dynamic shared-memory array; sub-arrays are addressed as OFFSETS (in
+// doubles) from it, so that every access is provably in the shared address space (pointers kept in a struct were
+// demoted to generic LD.E loads inside the sampler kernel: profiles/r1_ncu_mcmc_summary.txt).
+extern __shared__ __align__(128) double ngrtd_smem[];
+
 struct SmemView {
-    double* Xf;
-    double* Xd;
-    double* itp;
-    double* xraw;
-    double* xrawd;
-    double* tbl;
-    double* scratch;   // [warps][NT][8 chains][8 cols]
+    int Xf;
+    int Xd;
+    int itp;
+    int xraw;
+    int xrawd;
+    int tbl;
+    int scratch;   // [warps][NT][8 chains][8 cols]
 };
 
 struct LikPar {
@@ -168,11 +173,12 @@ struct WarpTiles {
         if (!ANY_LOOP) return;
         const int j = lane & 3, r = lane >> 2;
         int k = kc + j;
-        const double* pf = s.Xf + j * NCOL + r;
-        const double* pd = s.Xd + j * NCOL + r;
-        const double* pi = s.itp + j;
-        const double* px = s.xraw + j;
-        const double* pxd = s.xrawd + j;
+        const double* pf = ngrtd_smem + s.Xf + j * NCOL + r;
+        const double* pd = ngrtd_smem + s.Xd + j * NCOL + r;
+        const double* pi = ngrtd_smem + s.itp + j;
+        const double* px = ngrtd_smem + s.xraw + j;
+        const double* pxd = ngrtd_smem + s.xrawd + j;
+        const double* tbl = ngrtd_smem + s.tbl;
         const double dtp = pv.dtp;
         {   // first group of the chunk: direct evaluation (handles tp_0 = 1e-5 and re-anchors the recurrences)
             double bf = pf[0];
@@ -184,9 +190,9 @@ struct WarpTiles {
             for (int t = 0; t < NT; t++) {
                 double w1 = 0.0, w2 = 0.0;
                 if constexpr (C1 == CLS_G) { w1 = c1[t].first(k, dtp); dmma884(a1[t][0][0], a1[t][0][1], w1, bf); }
-                if constexpr (C1 == CLS_D) { w1 = c1[t].first(k, dtp, it, s.tbl); dmma884(a1[t][0][0], a1[t][0][1], w1, bd); }
+                if constexpr (C1 == CLS_D) { w1 = c1[t].first(k, dtp, it, tbl); dmma884(a1[t][0][0], a1[t][0][1], w1, bd); }
                 if constexpr (C2 == CLS_G) { w2 = c2[t].first(k, dtp); dmma884(a2[t][0][0], a2[t][0][1], w2, bf); }
-                if constexpr (C2 == CLS_D) { w2 = c2[t].first(k, dtp, it, s.tbl); dmma884(a2[t][0][0], a2[t][0][1], w2, bd); }
+                if constexpr (C2 == CLS_D) { w2 = c2[t].first(k, dtp, it, tbl); dmma884(a2[t][0][0], a2[t][0][1], w2, bd); }
                 if constexpr (DYN) {
                     double dvk = exp(-lam[t] * ((double)k + dtp));
                     double du = (k == 0) ? exp(-lam[t] * (1e-5 + dtp)) : dvk;
@@ -212,9 +218,9 @@ struct WarpTiles {
                 for (int t = 0; t < NT; t++) {
                     double w1 = 0.0, w2 = 0.0;
                     if constexpr (C1 == CLS_G) { w1 = c1[t].next(k); dmma884(a1[t][u][0], a1[t][u][1], w1, bf); }
-                    if constexpr (C1 == CLS_D) { w1 = c1[t].next(it, s.tbl); dmma884(a1[t][u][0], a1[t][u][1], w1, bd); }
+                    if constexpr (C1 == CLS_D) { w1 = c1[t].next(it, tbl); dmma884(a1[t][u][0], a1[t][u][1], w1, bd); }
                     if constexpr (C2 == CLS_G) { w2 = c2[t].next(k); dmma884(a2[t][u][0], a2[t][u][1], w2, bf); }
-                    if constexpr (C2 == CLS_D) { w2 = c2[t].next(it, s.tbl); dmma884(a2[t][u][0], a2[t][u][1], w2, bd); }
+                    if constexpr (C2 == CLS_D) { w2 = c2[t].next(it, tbl); dmma884(a2[t][u][0], a2[t][u][1], w2, bd); }
                     if constexpr (DYN) {
                         double du = dv[t];
                         dv[t] *= d4[t];
@@ -235,9 +241,9 @@ struct WarpTiles {
             for (int t = 0; t < NT; t++) {
                 double w1 = 0.0, w2 = 0.0;
                 if constexpr (C1 == CLS_G) { w1 = c1[t].next(k); dmma884(a1[t][0][0], a1[t][0][1], w1, bf); }
-                if constexpr (C1 == CLS_D) { w1 = c1[t].next(it, s.tbl); dmma884(a1[t][0][0], a1[t][0][1], w1, bd); }
+                if constexpr (C1 == CLS_D) { w1 = c1[t].next(it, tbl); dmma884(a1[t][0][0], a1[t][0][1], w1, bd); }
                 if constexpr (C2 == CLS_G) { w2 = c2[t].next(k); dmma884(a2[t][0][0], a2[t][0][1], w2, bf); }
-                if constexpr (C2 == CLS_D) { w2 = c2[t].next(it, s.tbl); dmma884(a2[t][0][0], a2[t][0][1], w2, bd); }
+                if constexpr (C2 == CLS_D) { w2 = c2[t].next(it, tbl); dmma884(a2[t][0][0], a2[t][0][1], w2, bd); }
                 if constexpr (DYN) {
                     double du = dv[t];
                     dv[t] *= d4[t];
@@ -355,33 +361,33 @@ struct FwdCta {
     SmemView s;
     const PlanView& pv;
     int lc_cap, nchunks, nwarps, nthreads, tid, lane, warp;
-    double* scratch_warp;
+    int scratch_off;
     bool need_J;
 
     __device__ __forceinline__ FwdCta(const PlanView& pv_) : pv(pv_) {}
 
-    // returns the first shared-memory double not used by the forward tables
-    __device__ __forceinline__ double* setup(double* smem, int lc_cap_) {
+    // returns the offset (in doubles) of the first shared-memory double not used by the forward tables
+    __device__ __forceinline__ int setup(int lc_cap_) {
         lc_cap = lc_cap_;
         nthreads = blockDim.x;
         nwarps = nthreads >> 5;
         tid = threadIdx.x;
         lane = tid & 31;
         warp = tid >> 5;
-        double* p = smem;
+        int p = 0;
         s.tbl = p; p += TBL_DOUBLES;       // first: keeps the 128-byte bank alignment of the two word arrays
         s.scratch = p; p += nwarps * NT * 8 * NCOL;
-        s.Xf = p; p += (size_t)lc_cap * NCOL;
-        s.Xd = p; if (WT::ANY_D) p += (size_t)lc_cap * NCOL;
+        s.Xf = p; p += lc_cap * NCOL;
+        s.Xd = p; if (WT::ANY_D) p += lc_cap * NCOL;
         s.itp = p; if (WT::ANY_D) p += lc_cap;
         s.xraw = p; if (DYN) p += lc_cap;
         s.xrawd = p; if (DYN && WT::ANY_D) p += lc_cap;
-        scratch_warp = s.scratch + warp * NT * 8 * NCOL;
+        scratch_off = s.scratch + warp * NT * 8 * NCOL;
         nchunks = WT::ANY_LOOP ? (pv.Lpad + lc_cap - 1) / lc_cap : 1;
         need_J = false;
         for (int t = 0; t < pv.ntracer; t++) need_J |= (pv.tr[t].col_b >= 0);
         if (WT::ANY_D) {
-            for (int i = tid; i < TBL_DOUBLES; i += nthreads) s.tbl[i] = pv.tbl[i];
+            for (int i = tid; i < TBL_DOUBLES; i += nthreads) ngrtd_smem[s.tbl + i] = pv.tbl[i];
         }
         if (nchunks == 1) load_chunk(0, pv.Lpad);     // resident tables: loaded once per launch
         __syncthreads();
@@ -391,18 +397,18 @@ struct FwdCta {
     __device__ __forceinline__ void load_chunk(int kc, int len) {
         if (!WT::ANY_LOOP) return;
         const double2* gf = reinterpret_cast<const double2*>(pv.Xf + (size_t)kc * NCOL);
-        double2* sf = reinterpret_cast<double2*>(s.Xf);
+        double2* sf = reinterpret_cast<double2*>(ngrtd_smem + s.Xf);
         for (int i = tid; i < len * NCOL / 2; i += nthreads) sf[i] = gf[i];
         if (WT::ANY_D) {
             const double2* gd = reinterpret_cast<const double2*>(pv.Xd + (size_t)kc * NCOL);
-            double2* sd = reinterpret_cast<double2*>(s.Xd);
+            double2* sd = reinterpret_cast<double2*>(ngrtd_smem + s.Xd);
             for (int i = tid; i < len * NCOL / 2; i += nthreads) sd[i] = gd[i];
-            for (int i = tid; i < len; i += nthreads) s.itp[i] = pv.itp[kc + i];
+            for (int i = tid; i < len; i += nthreads) ngrtd_smem[s.itp + i] = pv.itp[kc + i];
         }
         if (DYN) {
-            for (int i = tid; i < len; i += nthreads) s.xraw[i] = pv.xraw[kc + i];
+            for (int i = tid; i < len; i += nthreads) ngrtd_smem[s.xraw + i] = pv.xraw[kc + i];
             if (WT::ANY_D)
-                for (int i = tid; i < len; i += nthreads) s.xrawd[i] = pv.xrawd[kc + i];
+                for (int i = tid; i < len; i += nthreads) ngrtd_smem[s.xrawd + i] = pv.xrawd[kc + i];
         }
     }
 
@@ -424,7 +430,7 @@ struct FwdCta {
                 if (active) w.chunk(s, pv, kc, len / 4, lane);
             }
         }
-        if (active) w.end(par, pv, scratch_warp, lane, val);
+        if (active) w.end(par, pv, ngrtd_smem + scratch_off, lane, val);
     }
 
     // Unit schedule.  Resident tables: static and balanced -- units are dealt round-robin to the 4*gridDim.x SM
@@ -475,9 +481,8 @@ template <int C1, int C2, bool DYN, int NT, int UA, int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, 1)
 k_forward(PlanView pv, SlotMap sm, const double* __restrict__ theta, long long B, double* __restrict__ out,
           double* __restrict__ logp, LikPar lik, int lc_cap) {
-    extern __shared__ __align__(128) double smem[];
     FwdCta<C1, C2, DYN, NT, UA> cta(pv);
-    cta.setup(smem, lc_cap);
+    cta.setup(lc_cap);
     const int j = cta.lane & 3, r = cta.lane >> 2;
     const long long nunits = (B + NT * 8 - 1) / (NT * 8);
     cta.for_each_unit(nunits, [&](long long u, bool active, bool lockstep) {

@@ -169,11 +169,15 @@ __device__ __forceinline__ void record_dim(const SamplerView& sv, const RunArgs&
 template <int C1, int C2, bool DYN, int NT, int UA, int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, 1)
 k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
-    extern __shared__ __align__(128) double smem[];
     FwdCta<C1, C2, DYN, NT, UA> cta(pv);
-    double* rec_base = cta.setup(smem, lc_cap);
+    const int rec_base = cta.setup(lc_cap);
     const int lane = cta.lane, j = lane & 3, r = lane >> 2;
-    double* rec_warp = rec_base + (size_t)cta.warp * NT * 8 * CH_REC;
+    // prior table in shared memory (dynamic indexing of kernel parameters would be demoted to local memory)
+    const int pr_off = rec_base + blockDim.x / 32 * NT * 8 * CH_REC;
+    PriorDev* spr = reinterpret_cast<PriorDev*>(ngrtd_smem + pr_off);
+    if (threadIdx.x < sv.nd) spr[threadIdx.x] = sv.pr[threadIdx.x];
+    __syncthreads();
+    const int rec_warp = rec_base + cta.warp * NT * 8 * CH_REC;
     const long long B = sv.B;
     const long long nunits = (B + NT * 8 - 1) / (NT * 8);
     LikPar lik;
@@ -184,7 +188,7 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
 
     cta.for_each_unit(nunits, [&](long long u, bool active, bool lockstep) {
         long long chain[NT];
-        double* rec[NT];
+        int rec[NT];
         bool ok[NT];
         // ---- load the chain state into shared memory: qs | qp | vals | scalars(logp, lamb, scal, lpsum, uacc, acc_win, acc_tot)
 #pragma unroll
@@ -192,11 +196,12 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
             chain[t] = (u * NT + t) * 8 + r;
             ok[t] = active && chain[t] < B;
             long long cl = (active && chain[t] < B) ? chain[t] : 0;
-            rec[t] = rec_warp + (size_t)(t * 8 + r) * CH_REC;
-            for (int d = j; d < sv.nd; d += 4) rec[t][d] = sv.q[cl * sv.nd + d];
-            for (int v = j; v < NVAL; v += 4) rec[t][2 * ND_MAX + v] = sv.val_defaults[v];
+            rec[t] = rec_warp + (t * 8 + r) * CH_REC;
+            for (int d = j; d < sv.nd; d += 4) ngrtd_smem[rec[t] + d] = sv.q[cl * sv.nd + d];
+#pragma unroll
+            for (int v = 0; v < NVAL / 4; v++) ngrtd_smem[rec[t] + 2 * ND_MAX + 4 * v + j] = sv.val_defaults[4 * v + j];
             if (j == 0) {
-                double* sc = rec[t] + 2 * ND_MAX + NVAL;
+                double* sc = ngrtd_smem + rec[t] + 2 * ND_MAX + NVAL;
                 sc[0] = sv.logp[cl];
                 sc[1] = sv.lamb[cl];
                 sc[2] = sv.scal[cl];
@@ -212,9 +217,9 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
             double nu[NT];
 #pragma unroll
             for (int t = 0; t < NT; t++) {
-                double* qs = rec[t];
-                double* qp = rec[t] + ND_MAX;
-                double* vals = rec[t] + 2 * ND_MAX;
+                double* qs = ngrtd_smem + rec[t];
+                double* qp = qs + ND_MAX;
+                double* vals = qs + 2 * ND_MAX;
                 double* sc = vals + NVAL;
                 const long long gchain = sv.chain_offset + chain[t];
                 // -- tuning point (pymc3 DEMetropolisZ.astep: rescale before proposing)
@@ -248,8 +253,8 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
                     }
                     qp[d] = qn;
                     double v;
-                    lps += transform_dim(sv.pr[d], qn, v);
-                    vals[sv.pr[d].target] = v;
+                    lps += transform_dim(spr[d], qn, v);
+                    vals[spr[d].target] = v;
                 }
                 lps += __shfl_xor_sync(0xffffffffu, lps, 1);
                 lps += __shfl_xor_sync(0xffffffffu, lps, 2);
@@ -275,9 +280,9 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
             if (!active) continue;
 #pragma unroll
             for (int t = 0; t < NT; t++) {
-                double* qs = rec[t];
-                double* qp = rec[t] + ND_MAX;
-                double* sc = rec[t] + 2 * ND_MAX + NVAL;
+                double* qs = ngrtd_smem + rec[t];
+                double* qp = qs + ND_MAX;
+                double* sc = qs + 2 * ND_MAX + NVAL;
                 double ll = lik_reduce(lik, pv.ntracer, j, val[t], nu[t]);
                 double lpn = sc[3] + ll;
                 double delta = lpn - sc[0];
@@ -295,7 +300,7 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
                         long long draw = ra.draw0 + (i - ra.step0) / ra.thin;
                         for (int d = j; d < sv.nd; d += 4) {
                             double v;
-                            transform_dim(sv.pr[d], qs[d], v);
+                            transform_dim(spr[d], qs[d], v);
                             record_dim(sv, ra, chain[t], d, v, draw);
                         }
                     }
@@ -307,9 +312,9 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
 #pragma unroll
         for (int t = 0; t < NT; t++) {
             if (!ok[t]) continue;
-            for (int d = j; d < sv.nd; d += 4) sv.q[chain[t] * sv.nd + d] = rec[t][d];
+            for (int d = j; d < sv.nd; d += 4) sv.q[chain[t] * sv.nd + d] = ngrtd_smem[rec[t] + d];
             if (j == 0) {
-                double* sc = rec[t] + 2 * ND_MAX + NVAL;
+                double* sc = ngrtd_smem + rec[t] + 2 * ND_MAX + NVAL;
                 sv.logp[chain[t]] = sc[0];
                 sv.lamb[chain[t]] = sc[1];
                 sv.scal[chain[t]] = sc[2];
