@@ -367,8 +367,10 @@ static int fill_lik(LikPar& lik, const ngrtd_plan* P, int kind, const double* ob
     if (kind == NGRTD_LIK_STUDENTT && !nu_d) return fail(NGRTD_EINVAL, "student-t needs nu");
     lik.kind = kind;
     for (int t = 0; t < MAX_TRACER; t++) {
+        double sd = t < P->pv.ntracer ? obs_sd[t] : 1.0;
         lik.obs[t] = t < P->pv.ntracer ? obs_mu[t] : 0.0;
-        lik.sd[t] = t < P->pv.ntracer ? obs_sd[t] : 1.0;
+        lik.isd[t] = 1.0 / sd;
+        lik.lc[t] = kind == NGRTD_LIK_NORMAL ? -0.5 * std::log(2.0 * M_PI * sd * sd) : -std::log(sd);
     }
     lik.nu = nu_d;
     return NGRTD_OK;
@@ -623,7 +625,7 @@ extern "C" int ngrtd_ce_host(int32_t what, int32_t ngas, const int32_t* gases, c
 }
 
 // ------------------------------------------------------------------------------------------- stand-alone loglik
-struct ObsPar { int T; double obs[16]; double sd[16]; };
+struct ObsPar { int T; double obs[16]; double isd[16]; double lc[16]; };
 
 __global__ void k_loglik(int kind, ObsPar op, const double* __restrict__ mu, const double* __restrict__ nu,
                          long long B, double* __restrict__ logp) {
@@ -632,9 +634,9 @@ __global__ void k_loglik(int kind, ObsPar op, const double* __restrict__ mu, con
     double acc = 0.0;
     if (kind == NGRTD_LIK_STUDENTT) {
         double n = nu[i], cst = lik_studentt_const(n);
-        for (int t = 0; t < op.T; t++) acc += lik_term_studentt(op.obs[t], mu[i * op.T + t], op.sd[t], n, cst);
+        for (int t = 0; t < op.T; t++) acc += lik_term_studentt(op.obs[t], mu[i * op.T + t], op.isd[t], op.lc[t], n, cst);
     } else {
-        for (int t = 0; t < op.T; t++) acc += lik_term_normal(op.obs[t], mu[i * op.T + t], op.sd[t]);
+        for (int t = 0; t < op.T; t++) acc += lik_term_normal(op.obs[t], mu[i * op.T + t], op.isd[t], op.lc[t]);
     }
     logp[i] = acc;
 }
@@ -648,7 +650,12 @@ extern "C" int ngrtd_loglik_dev(int32_t lik_kind, int32_t T, const double* mu_d,
     if (B <= 0) return B == 0 ? NGRTD_OK : fail(NGRTD_EINVAL, "B < 0");
     ObsPar op;
     op.T = T;
-    for (int t = 0; t < 16; t++) { op.obs[t] = t < T ? obs_mu[t] : 0.0; op.sd[t] = t < T ? obs_sd[t] : 1.0; }
+    for (int t = 0; t < 16; t++) {
+        double sd = t < T ? obs_sd[t] : 1.0;
+        op.obs[t] = t < T ? obs_mu[t] : 0.0;
+        op.isd[t] = 1.0 / sd;
+        op.lc[t] = lik_kind == NGRTD_LIK_NORMAL ? -0.5 * std::log(2.0 * M_PI * sd * sd) : -std::log(sd);
+    }
     unsigned grid = (unsigned)((B + 127) / 128);
     k_loglik<<<grid, 128, 0, (cudaStream_t)stream>>>(lik_kind, op, mu_d, nu_d, B, logp_d);
     CUDA_TRY(cudaGetLastError());
@@ -814,7 +821,12 @@ extern "C" int ngrtd_sampler_create(ngrtd_sampler** out, const ngrtd_sampler_cfg
     v.nu_sampled = cfg->nu_sampled;
     v.nu_lo = cfg->nu_lo; v.nu_hi = cfg->nu_hi; v.nu_fixed = cfg->nu_fixed;
     v.ntr = cfg->nobs;
-    for (int t = 0; t < MAX_TRACER; t++) { v.obs[t] = t < cfg->nobs ? cfg->obs_mu[t] : 0.0; v.sd[t] = t < cfg->nobs ? cfg->obs_sd[t] : 1.0; }
+    for (int t = 0; t < MAX_TRACER; t++) {
+        double sd = t < cfg->nobs ? cfg->obs_sd[t] : 1.0;
+        v.obs[t] = t < cfg->nobs ? cfg->obs_mu[t] : 0.0;
+        v.isd[t] = 1.0 / sd;
+        v.lc[t] = cfg->lik_kind == NGRTD_LIK_NORMAL ? -0.5 * std::log(2.0 * M_PI * sd * sd) : -std::log(sd);
+    }
     v.f2_from_f1 = cfg->f2_from_f1;
     v.proposal_dist = cfg->proposal_dist;
     v.de_mcz = cfg->de_mcz;

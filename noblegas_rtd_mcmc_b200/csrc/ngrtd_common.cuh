@@ -89,45 +89,32 @@ __device__ __forceinline__ ChainPar load_chain_par(const double* __restrict__ th
     return p;
 }
 
-// exp(e) for e <= ~0 given ep = e * 32/ln2.  FP64-pipe cost: 1 DADD + 4 DFMA + 1 DMUL; rounding and its inverse
-// run on the conversion unit (F2I/I2F); degree-4 Taylor in r (truncation <= 1.3e-12 relative).
-// tbl points at hi'[32] (uint32) followed by lo[32] (uint32), hi'[j] = hi(2^(j/32)) - (j << 15), so that the
-// exponent insertion is ONE integer multiply-add:  hi'[j] + n*2^15 = hi[j] + ((n >> 5) << 20).
-// n is clamped at EXP_NMIN (result 2^-1022 * p, i.e. ~2e-308) instead of flushing to zero: one IMNMX instead of
-// a compare and two selects.  Chains whose largest weight would be below 2^-1022 are declared dead (NaN) in
-// Comp<CLS_D>::init, which reproduces the reference's 0/0 = NaN when every weight underflows.
+// exp(e) for e <= ~0 given ep = e * 32/ln2.  FP64-pipe cost: 1 DADD + 4 DFMA + 1 DMUL (+ 2 conversions).
+//   * rounding: F2I.F64 / I2F.F64 on the conversion unit.  The magic-number alternative (ep + 1.5*2^52, two more
+//     DADDs, no conversions) measured 8 % slower in the full kernel (72.4 vs 78.2 cycles per tile-group,
+//     profiles/r1_notes.md) although the conversions also occupy the FP64 pipe for ~3.5 cycles each.
+//     F2I saturates for hugely negative exponents and maps NaN to 0 (r = NaN then poisons the result).
+//   * degree-4 Taylor in r = ep - rint(ep), |r| <= 1/2 (i.e. |x| <= ln2/64): truncation <= 1.3e-12 relative.
+//   * table: hi'[32] (uint32) followed by lo[32] (uint32), hi'[j] = hi(2^(j/32)) - (j << 15), so the exponent
+//     insertion is ONE integer multiply-add: hi'[j] + n*2^15 = hi[j] + ((n >> 5) << 20); any 32-lane gather from a
+//     128-byte array is bank-conflict free.
+//   * n is clamped at EXP_NMIN (result ~2^-1022) instead of flushing to zero: one IMNMX instead of a compare and two
+//     selects.  Chains whose largest weight would be below 2^-1022 are declared dead (NaN) in Comp<CLS_D>::init, which
+//     reproduces the reference's 0/0 = NaN when every weight underflows.
 __device__ __forceinline__ double exp_scaled(double ep, const double* __restrict__ tbl) {
     const unsigned int* th = reinterpret_cast<const unsigned int*>(tbl);
-#if defined(NGRTD_EXP) && NGRTD_EXP == 1   /* timing experiment: magic-number rounding instead of F2I/I2F */
-    double tm = fmax(ep, -2.0e6) + 6755399441055744.0;
-    int n = __double2loint(tm);
-    double r = ep - (tm - 6755399441055744.0);
-#else
-    int n = __double2int_rn(ep);                 // saturates; NaN -> 0
+    int n = __double2int_rn(ep);
     double r = ep - __int2double_rn(n);
-#endif
-#if defined(NGRTD_EXP) && NGRTD_EXP == 2   /* timing experiment: degree-2 polynomial */
-    double p = fma(r, fma(r, EXP_C2, EXP_C1), 1.0);
-#else
     double p = fma(r, fma(r, fma(r, fma(r, EXP_C4, EXP_C3), EXP_C2), EXP_C1), 1.0);
-#endif
     int nc = max(n, EXP_NMIN);
     int off = (nc << 2) & ((TBL_N - 1) << 2);    // byte offset of the table slot
     const char* tb = reinterpret_cast<const char*>(th);
-#if defined(NGRTD_EXP) && NGRTD_EXP == 3   /* timing experiment: no table gather */
-    int hi = 0x3ff00000 + nc * 32768;
-    return __hiloint2double(hi, off) * p;
-#else
     int hi = (int)*reinterpret_cast<const unsigned int*>(tb + off) + nc * 32768;
     int lo = (int)*reinterpret_cast<const unsigned int*>(tb + off + TBL_N * 4);
     return __hiloint2double(hi, lo) * p;
-#endif
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-#if defined(NGRTD_EXP) && NGRTD_EXP == 4   /* timing experiment: no DMMA */
-    c0 += a; c1 = fma(a, b, c1); return;
-#endif
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));

@@ -41,7 +41,8 @@ struct SmemView {
 struct LikPar {
     int kind;                  // -1 none, 0 normal, 1 student-t
     double obs[MAX_TRACER];
-    double sd[MAX_TRACER];
+    double isd[MAX_TRACER];    // 1 / sd
+    double lc[MAX_TRACER];     // normal: -0.5 log(2 pi sd^2); student-t: -log(sd)   (per-tracer constants, host)
     const double* nu;          // [B] (student-t)
 };
 
@@ -338,18 +339,19 @@ struct WarpTiles {
 };
 
 // ---------------------------------------------------------------- likelihood terms (pymc3 3.11.2 formulae)
-__device__ __forceinline__ double lik_term_normal(double obs, double mu, double sd) {
-    double z = (obs - mu) / sd;
-    return -0.5 * log(2.0 * 3.14159265358979323846 * sd * sd) - 0.5 * z * z;
+// Normal:    -0.5 log(2 pi sd^2) - z^2/2,  z = (obs - mu)/sd           (the log is a per-tracer host constant)
+// Student-T, lam = sd^-2:  lgamma((nu+1)/2) - lgamma(nu/2) + 0.5 log(lam/(nu pi)) - (nu+1)/2 log1p(lam (x-mu)^2/nu)
+//            = [lgamma((nu+1)/2) - lgamma(nu/2) - 0.5 log(nu pi)] - log(sd) - (nu+1)/2 log1p(z^2/nu)
+__device__ __forceinline__ double lik_term_normal(double obs, double mu, double isd, double lc) {
+    double z = (obs - mu) * isd;
+    return lc - 0.5 * z * z;
 }
-// Student-T with lam = sd^-2: lgamma((nu+1)/2) - lgamma(nu/2) + 0.5 log(lam/(nu pi)) - (nu+1)/2 log1p(lam (x-mu)^2/nu)
 __device__ __forceinline__ double lik_studentt_const(double nu) {
-    return lgamma(0.5 * (nu + 1.0)) - lgamma(0.5 * nu);
+    return lgamma(0.5 * (nu + 1.0)) - lgamma(0.5 * nu) - 0.5 * log(nu * 3.14159265358979323846);
 }
-__device__ __forceinline__ double lik_term_studentt(double obs, double mu, double sd, double nu, double cst) {
-    double lam = 1.0 / (sd * sd);
-    double d = obs - mu;
-    return cst + 0.5 * log(lam / (nu * 3.14159265358979323846)) - 0.5 * (nu + 1.0) * log1p(lam * d * d / nu);
+__device__ __forceinline__ double lik_term_studentt(double obs, double mu, double isd, double lc, double nu, double cst) {
+    double z = (obs - mu) * isd;
+    return cst + lc - 0.5 * (nu + 1.0) * log1p(z * z / nu);
 }
 
 // ---------------------------------------------------------------- per-CTA scaffolding shared by the kernels
@@ -460,16 +462,22 @@ struct FwdCta {
     }
 };
 
-// sum of the likelihood terms of the tracers a lane owns (j, j+4), reduced over the 4 lanes of a chain
+// sum of the likelihood terms of the tracers a lane owns (j, j+4), reduced over the 4 lanes of a chain.
+// The nu-dependent Student-T constant is evaluated once per chain: lane 0 takes lgamma((nu+1)/2), lane 1 lgamma(nu/2),
+// lane 2 the log, and the pieces are combined with the same shuffles that reduce the tracer terms.
 __device__ __forceinline__ double lik_reduce(const LikPar& lik, int ntracer, int j, const double (&v)[2], double nu) {
-    double cst = 0.0, acc = 0.0;
-    if (lik.kind == 1) cst = lik_studentt_const(nu);
+    double acc = 0.0;
+    if (lik.kind == 1) {
+        if (j == 0) acc = (double)ntracer * lgamma(0.5 * (nu + 1.0));
+        else if (j == 1) acc = -(double)ntracer * lgamma(0.5 * nu);
+        else if (j == 2) acc = -0.5 * (double)ntracer * log(nu * 3.14159265358979323846);
+    }
 #pragma unroll
     for (int q = 0; q < 2; q++) {
         int tr = j + 4 * q;
         if (tr < ntracer)
-            acc += (lik.kind == 1) ? lik_term_studentt(lik.obs[tr], v[q], lik.sd[tr], nu, cst)
-                                   : lik_term_normal(lik.obs[tr], v[q], lik.sd[tr]);
+            acc += (lik.kind == 1) ? lik_term_studentt(lik.obs[tr], v[q], lik.isd[tr], lik.lc[tr], nu, 0.0)
+                                   : lik_term_normal(lik.obs[tr], v[q], lik.isd[tr], lik.lc[tr]);
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);

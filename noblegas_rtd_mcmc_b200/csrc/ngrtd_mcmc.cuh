@@ -40,7 +40,7 @@ struct SamplerView {
     int nu_sampled;          // 1: nu = nu_lo + (nu_hi - nu_lo) * val[VAL_NU]
     double nu_lo, nu_hi, nu_fixed;
     int ntr;
-    double obs[MAX_TRACER], sd[MAX_TRACER];
+    double obs[MAX_TRACER], isd[MAX_TRACER], lc[MAX_TRACER];   // observations, 1/sd, per-tracer likelihood constants
     int f2_from_f1;          // f2 = 1 - f1 (run_age_mcmc_utils.py:304)
     unsigned int sampled_mask;   // bit t set: value register t is driven by a sampler dimension
     int proposal_dist;       // 0 uniform(-1,1), 1 normal(0,1)
@@ -102,20 +102,23 @@ __device__ __forceinline__ double u01(unsigned int a, unsigned int b) {   // uni
 constexpr unsigned int RNG_SELECT = 0x100u;    // purpose of the (iz1, iz2, accept-uniform) draw
 
 // ---------------------------------------------------------------- priors and transforms (pymc3 3.11.2)
-__device__ __forceinline__ double softplus(double y) { return y > 0.0 ? y + log1p(exp(-y)) : log1p(exp(y)); }
-
-// transformed coordinate x -> natural value v; returns log prior density + log |Jacobian|
+// transformed coordinate x -> natural value v; returns log prior density + log |Jacobian|.
+// sigmoid and its log share one exp and one log1p:  e = exp(-|x|), log sig(x) = min(x,0) - log1p(e), sig(x) = [x>=0 ? 1 : e]/(1+e)
 __device__ __forceinline__ double transform_dim(const PriorDev& pr, double x, double& v) {
     switch (pr.kind) {
-        case PR_UNIFORM: {      // interval transform: v = a + (b-a) sigmoid(x); logp + jac = log sig(x) + log sig(-x)
-            double sp = softplus(-x);
-            v = pr.p0 + (pr.p1 - pr.p0) * exp(-sp);
-            return -2.0 * sp - x;
-        }
+        case PR_UNIFORM:        // interval transform: v = a + (b-a) sigmoid(x); logp + jac = log sig(x) + log sig(-x)
         case PR_BETA: {         // log-odds transform; natural value mapped affinely onto [lo, hi]
-            double sp = softplus(-x);
-            v = pr.lo + (pr.hi - pr.lo) * exp(-sp);
-            return pr.p0 * (-sp) + pr.p1 * (-(x + sp)) - pr.c;
+            double e = exp(-fabs(x));
+            double l1 = log1p(e);
+            double sig = ((x >= 0.0) ? 1.0 : e) / (1.0 + e);
+            double lsp = fmin(x, 0.0) - l1;          // log sigmoid(x)
+            double lsm = lsp - x;                    // log sigmoid(-x)
+            if (pr.kind == PR_UNIFORM) {
+                v = pr.p0 + (pr.p1 - pr.p0) * sig;
+                return lsp + lsm;
+            }
+            v = pr.lo + (pr.hi - pr.lo) * sig;
+            return pr.p0 * lsp + pr.p1 * lsm - pr.c;
         }
         case PR_NORMAL: {
             double z = (x - pr.p0) / pr.p1;
@@ -183,7 +186,7 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
     LikPar lik;
     lik.kind = sv.lik_kind;
 #pragma unroll
-    for (int t = 0; t < MAX_TRACER; t++) { lik.obs[t] = sv.obs[t]; lik.sd[t] = sv.sd[t]; }
+    for (int t = 0; t < MAX_TRACER; t++) { lik.obs[t] = sv.obs[t]; lik.isd[t] = sv.isd[t]; lik.lc[t] = sv.lc[t]; }
     lik.nu = nullptr;
 
     cta.for_each_unit(nunits, [&](long long u, bool active, bool lockstep) {
@@ -380,7 +383,7 @@ __global__ void k_mcmc_ng(SamplerView sv, RunArgs ra) {
         double ll = 0.0;
         for (int g = 0; g < sv.gases.n; g++) {
             double mu = ce_eval(0, sv.gases.id[g], E, T, Ae, F, P, 0.0);
-            ll += sv.lik_kind == 1 ? lik_term_studentt(sv.obs[g], mu, sv.sd[g], nu, cst) : lik_term_normal(sv.obs[g], mu, sv.sd[g]);
+            ll += sv.lik_kind == 1 ? lik_term_studentt(sv.obs[g], mu, sv.isd[g], sv.lc[g], nu, cst) : lik_term_normal(sv.obs[g], mu, sv.isd[g], sv.lc[g]);
         }
         double lpn = lps + ll;
         double delta = lpn - logp;

@@ -24,3 +24,22 @@ for B in (2368 * 16 * 8, 65536):
       ms = e0.elapsed_time(e1) / 10
       tg = B / 8 * 210 / 592          # tile-groups per SMSP
       print("%s %-7s B=%d %.4f ms  %.1f cycles per tile-group per SMSP  %.2f TF(8col)" % (os.environ.get("NGRTD_LIB", "default")[-9:-3], name, B, ms, ms * 1e-3 * 1.92e9 / tg, 2.0*840*8*(2 if m2 else 1)*B/ms/1e9), flush=True)
+
+from noblegas_rtd_mcmc_b200.sampler import Sampler, prior
+B = 65536
+pn = list(synthetic.PAR_NAMES_CFG3)
+plan, _, _ = synth_plan("exp_pist_flow", "dispersion", pn)
+truth = np.array([[180.0, 1500.0, 0.6, 0.4, 1.8, 0.4, synthetic.LOG10_J_MONTHLY]])
+obs = plan.forward_host(truth, pn)[0]; sd = 0.05 * np.abs(obs)
+pri = [prior("uniform", "tau1", 12, 12000), prior("beta", "nu_", 2.0, 0.1), prior("normal", "J", synthetic.LOG10_J_MONTHLY, 0.33),
+       prior("uniform", "tau2", 600, 180000), prior("uniform", "f1", 0.01, 0.99), prior("uniform", "eta1", 1, 5),
+       prior("uniform", "D2", 0.01, 2.0)]
+q0 = [-3.0, 2.0, synthetic.LOG10_J_MONTHLY, -4.5, 0.3, -1.0, -1.2]
+for lik in ("normal", "studentt"):
+    smp = Sampler(pri, obs, sd, B, plan=plan, lik=lik, nu_range=(5.0, 30.0), f2_from_f1=True, tune_interval=100, hist_cap=256, seed=1, q0=q0, scaling=0.01)
+    smp.run(20, tune=True); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); smp.run(200, tune=True); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 200
+    print("sampler %-8s %.4f ms/step  %.3e evals/s (6 counted)  acc %.3f" % (lik, ms, B * 6 / ms * 1e3, float(smp.get("accepted").mean()) / smp.info()["step"]), flush=True)
+    smp.close()
