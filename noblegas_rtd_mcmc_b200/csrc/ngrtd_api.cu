@@ -174,7 +174,7 @@ extern "C" int ngrtd_plan_create(ngrtd_plan** out, int32_t L, int32_t nseries, c
             double v = std::exp2((double)i / TBL_N);
             uint64_t b;
             std::memcpy(&b, &v, 8);
-            w[i] = (uint32_t)(b >> 32) - ((uint32_t)i << 15);
+            w[i] = (uint32_t)(b >> 32) - ((uint32_t)i << (20 - TBL_BITS));
             w[TBL_N + i] = (uint32_t)(b & 0xffffffffu);
         }
     }

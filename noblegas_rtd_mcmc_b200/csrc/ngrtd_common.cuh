@@ -12,21 +12,37 @@ constexpr int NSLOT = 11;               // ForwardMod.p_dict slots
 constexpr int MAX_TRACER = 8;
 constexpr int LC_MAX = 1024;            // lags resident in shared memory per chunk
 
-// table-driven exp(): exp(e) = 2^(n/32) * p(r),  n = rint(e*32/ln2),  |r| <= ln2/64.
-// The 32-entry table is stored as two 32-bit arrays (high / low words): any 32-lane gather from a 128-byte
-// array is bank-conflict free (one 4-byte slot per bank, equal slots broadcast), so a lookup costs exactly two
-// shared-memory wavefronts.  (A 2048-entry double table measured 8 wavefronts per lookup and made the kernel
-// LSU-bound: profiles/r1_notes.md.)
-constexpr int TBL_BITS = 5;
+// table-driven exp(): exp(e) = 2^(n/N) * p(r),  n = rint(e*N/ln2),  r = e*N/ln2 - n in [-1/2, 1/2].
+// The N-entry table of 2^(j/N) is stored as two 32-bit arrays (high / low words).  With N = 32 any 32-lane gather from
+// a 128-byte array is bank-conflict free (one 4-byte slot per bank, equal slots broadcast): exactly two shared-memory
+// wavefronts per lookup.  (A 2048-entry double table measured 8 wavefronts per lookup and made the kernel LSU-bound.)
+// p(r) interpolates exp at Chebyshev nodes (near-minimax); max relative error: N=32/deg 4: 7.8e-14, N=64/deg 3: 4.5e-12,
+// N=128/deg 3: 2.8e-13.  Measured on cfg 3 (profiles/r1_notes.md): N=32/deg 4 72.5 cycles per tile-group, N=64/deg 3
+// 72.1, N=128/deg 3 70.5 (the extra bank conflicts of the 512-byte arrays cost less than the fourth DFMA): default N=128.
+#ifndef NGRTD_TBL_BITS
+#define NGRTD_TBL_BITS 7
+#endif
+constexpr int TBL_BITS = NGRTD_TBL_BITS;
 constexpr int TBL_N = 1 << TBL_BITS;
-constexpr int TBL_DOUBLES = TBL_N;      // shared-memory footprint in doubles (hi[32] + lo[32] as uint32)
+constexpr int TBL_DOUBLES = TBL_N;      // shared-memory footprint in doubles (hi[N] + lo[N] as uint32)
 constexpr double LN2 = 0.693147180559945309417232121458;
 constexpr double EXP_K = TBL_N / LN2;
-constexpr double EXP_C1 = LN2 / TBL_N;
-constexpr double EXP_C2 = EXP_C1 * EXP_C1 / 2.0;
-constexpr double EXP_C3 = EXP_C1 * EXP_C1 * EXP_C1 / 6.0;
-constexpr double EXP_C4 = EXP_C1 * EXP_C1 * EXP_C1 * EXP_C1 / 24.0;
-constexpr int EXP_NMIN = -1022 * TBL_N;             // below 2^-1022: flush to zero (see DESIGN.md "underflow")
+#if NGRTD_TBL_BITS == 5
+constexpr int EXP_DEG = 4;
+constexpr double EXP_C0 = 1.0, EXP_C1 = 0.02166084939172217, EXP_C2 = 0.00023459619819944503,
+                 EXP_C3 = 1.693863390316062e-06, EXP_C4 = 9.172607532633896e-09;
+#elif NGRTD_TBL_BITS == 6
+constexpr int EXP_DEG = 3;
+constexpr double EXP_C0 = 0.9999999999955212, EXP_C1 = 0.010830424696239445, EXP_C2 = 5.864919287197594e-05,
+                 EXP_C3 = 2.1173168199978455e-07, EXP_C4 = 0.0;
+#elif NGRTD_TBL_BITS == 7
+constexpr int EXP_DEG = 3;
+constexpr double EXP_C0 = 0.9999999999997201, EXP_C1 = 0.005415212348124269, EXP_C2 = 1.4662271345222707e-05,
+                 EXP_C3 = 2.64664311467397e-08, EXP_C4 = 0.0;
+#else
+#error "NGRTD_TBL_BITS must be 5, 6 or 7"
+#endif
+constexpr int EXP_NMIN = -1022 * TBL_N;             // below 2^-1022: clamp (see DESIGN.md "underflow")
 
 enum Cls : int { CLS_NONE = 0, CLS_P = 1, CLS_G = 2, CLS_D = 3 };
 
@@ -89,15 +105,13 @@ __device__ __forceinline__ ChainPar load_chain_par(const double* __restrict__ th
     return p;
 }
 
-// exp(e) for e <= ~0 given ep = e * 32/ln2.  FP64-pipe cost: 1 DADD + 4 DFMA + 1 DMUL (+ 2 conversions).
+// exp(e) for e <= ~0 given ep = e * N/ln2.  FP64-pipe cost: 1 DADD + deg DFMA + 1 DMUL (+ 2 conversions).
 //   * rounding: F2I.F64 / I2F.F64 on the conversion unit.  The magic-number alternative (ep + 1.5*2^52, two more
 //     DADDs, no conversions) measured 8 % slower in the full kernel (72.4 vs 78.2 cycles per tile-group,
 //     profiles/r1_notes.md) although the conversions also occupy the FP64 pipe for ~3.5 cycles each.
 //     F2I saturates for hugely negative exponents and maps NaN to 0 (r = NaN then poisons the result).
-//   * degree-4 Taylor in r = ep - rint(ep), |r| <= 1/2 (i.e. |x| <= ln2/64): truncation <= 1.3e-12 relative.
-//   * table: hi'[32] (uint32) followed by lo[32] (uint32), hi'[j] = hi(2^(j/32)) - (j << 15), so the exponent
-//     insertion is ONE integer multiply-add: hi'[j] + n*2^15 = hi[j] + ((n >> 5) << 20); any 32-lane gather from a
-//     128-byte array is bank-conflict free.
+//   * table: hi'[N] (uint32) followed by lo[N] (uint32), hi'[j] = hi(2^(j/N)) - (j << (20 - log2 N)), so the exponent
+//     insertion is ONE integer multiply-add: hi'[j] + n*2^(20 - log2 N) = hi[j] + ((n >> log2 N) << 20).
 //   * n is clamped at EXP_NMIN (result ~2^-1022) instead of flushing to zero: one IMNMX instead of a compare and two
 //     selects.  Chains whose largest weight would be below 2^-1022 are declared dead (NaN) in Comp<CLS_D>::init, which
 //     reproduces the reference's 0/0 = NaN when every weight underflows.
@@ -105,11 +119,12 @@ __device__ __forceinline__ double exp_scaled(double ep, const double* __restrict
     const unsigned int* th = reinterpret_cast<const unsigned int*>(tbl);
     int n = __double2int_rn(ep);
     double r = ep - __int2double_rn(n);
-    double p = fma(r, fma(r, fma(r, fma(r, EXP_C4, EXP_C3), EXP_C2), EXP_C1), 1.0);
+    double p = (EXP_DEG == 4) ? fma(r, fma(r, fma(r, fma(r, EXP_C4, EXP_C3), EXP_C2), EXP_C1), EXP_C0)
+                              : fma(r, fma(r, fma(r, EXP_C3, EXP_C2), EXP_C1), EXP_C0);
     int nc = max(n, EXP_NMIN);
     int off = (nc << 2) & ((TBL_N - 1) << 2);    // byte offset of the table slot
     const char* tb = reinterpret_cast<const char*>(th);
-    int hi = (int)*reinterpret_cast<const unsigned int*>(tb + off) + nc * 32768;
+    int hi = (int)*reinterpret_cast<const unsigned int*>(tb + off) + nc * (1 << (20 - TBL_BITS));
     int lo = (int)*reinterpret_cast<const unsigned int*>(tb + off + TBL_N * 4);
     return __hiloint2double(hi, lo) * p;
 }
