@@ -249,7 +249,7 @@ static int launch_forward_t(ngrtd_plan* P, const SlotMap& sm, const double* thet
     long long nunits = (B + NT * 8 - 1) / (NT * 8);
     int warps = warps_req > 0 ? std::min(warps_req, MAXW) : pick_warps(nunits, P->nsm, MAXW);
     if (warps > 4) warps &= ~3;
-    size_t sh = (size_t)TBL_DOUBLES + (size_t)warps * NT * 8 * NCOL;
+    size_t sh = (size_t)TBL_DOUBLES + 2 + (size_t)warps * NT * 8 * NCOL;
     sh += (size_t)lc_cap * NCOL;
     if (WT::ANY_D) sh += (size_t)lc_cap * NCOL + lc_cap;
     if (DYN) sh += lc_cap + (WT::ANY_D ? lc_cap : 0);
@@ -687,7 +687,7 @@ static int launch_mcmc_age(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st)
     int lc_cap = WT::ANY_LOOP ? std::min(P->Lpad, LC_MAX) : 0;
     size_t sh = 0;
     for (;;) {
-        sh = (size_t)TBL_DOUBLES + (size_t)warps * NT * 8 * NCOL + (size_t)lc_cap * NCOL;
+        sh = (size_t)TBL_DOUBLES + 2 + (size_t)warps * NT * 8 * NCOL + (size_t)lc_cap * NCOL;
         if (WT::ANY_D) sh += (size_t)lc_cap * NCOL + lc_cap;
         if (DYN) sh += lc_cap + (WT::ANY_D ? lc_cap : 0);
         sh += (size_t)warps * NT * 8 * CH_REC + (sizeof(PriorDev) * ND_MAX + 7) / 8;

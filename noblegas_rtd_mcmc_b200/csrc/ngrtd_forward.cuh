@@ -36,6 +36,7 @@ struct SmemView {
     int xrawd;
     int tbl;
     int scratch;   // [warps][NT][8 chains][8 cols]
+    int bar;       // mbarrier of the bulk-copy staging (2 doubles reserved)
 };
 
 struct LikPar {
@@ -354,6 +355,36 @@ __device__ __forceinline__ double lik_term_studentt(double obs, double mu, doubl
     return cst + lc - 0.5 * (nu + 1.0) * log1p(z * z / nu);
 }
 
+// ---------------------------------------------------------------- TMA bulk copies (cp.async.bulk, SASS UBLKCP)
+// One elected thread arms an mbarrier with the byte count and issues 1-D bulk copies global -> shared; every thread
+// then waits on the barrier phase.  Sizes and addresses are multiples of 16 bytes by construction (Lpad % 4 == 0).
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+
 // ---------------------------------------------------------------- per-CTA scaffolding shared by the kernels
 // Shared-memory carve-up, chunk streaming of the lag tables and the unit schedule.  k_forward evaluates one
 // parameter vector per chain; k_mcmc_age (ngrtd_mcmc.cuh) runs whole Metropolis steps around eval().
@@ -364,6 +395,7 @@ struct FwdCta {
     const PlanView& pv;
     int lc_cap, nchunks, nwarps, nthreads, tid, lane, warp;
     int scratch_off;
+    unsigned int phase;
     bool need_J;
 
     __device__ __forceinline__ FwdCta(const PlanView& pv_) : pv(pv_) {}
@@ -378,6 +410,7 @@ struct FwdCta {
         warp = tid >> 5;
         int p = 0;
         s.tbl = p; p += TBL_DOUBLES;       // first: keeps the 128-byte bank alignment of the two word arrays
+        s.bar = p; p += 2;
         s.scratch = p; p += nwarps * NT * 8 * NCOL;
         s.Xf = p; p += lc_cap * NCOL;
         s.Xd = p; if (WT::ANY_D) p += lc_cap * NCOL;
@@ -388,30 +421,40 @@ struct FwdCta {
         nchunks = WT::ANY_LOOP ? (pv.Lpad + lc_cap - 1) / lc_cap : 1;
         need_J = false;
         for (int t = 0; t < pv.ntracer; t++) need_J |= (pv.tr[t].col_b >= 0);
+        phase = 0;
+        if (tid == 0) mbar_init(reinterpret_cast<unsigned long long*>(ngrtd_smem + s.bar), 1);
         if (WT::ANY_D) {
             for (int i = tid; i < TBL_DOUBLES; i += nthreads) ngrtd_smem[s.tbl + i] = pv.tbl[i];
         }
+        __syncthreads();
         if (nchunks == 1) load_chunk(0, pv.Lpad);     // resident tables: loaded once per launch
         __syncthreads();
         return p;
     }
 
+    // stage lags [kc, kc+len) of the plan tables into shared memory with TMA bulk copies (one elected thread issues
+    // them, all threads wait on the mbarrier phase).  Callers guarantee no thread still reads the previous chunk.
     __device__ __forceinline__ void load_chunk(int kc, int len) {
         if (!WT::ANY_LOOP) return;
-        const double2* gf = reinterpret_cast<const double2*>(pv.Xf + (size_t)kc * NCOL);
-        double2* sf = reinterpret_cast<double2*>(ngrtd_smem + s.Xf);
-        for (int i = tid; i < len * NCOL / 2; i += nthreads) sf[i] = gf[i];
-        if (WT::ANY_D) {
-            const double2* gd = reinterpret_cast<const double2*>(pv.Xd + (size_t)kc * NCOL);
-            double2* sd = reinterpret_cast<double2*>(ngrtd_smem + s.Xd);
-            for (int i = tid; i < len * NCOL / 2; i += nthreads) sd[i] = gd[i];
-            for (int i = tid; i < len; i += nthreads) ngrtd_smem[s.itp + i] = pv.itp[kc + i];
+        unsigned long long* bar = reinterpret_cast<unsigned long long*>(ngrtd_smem + s.bar);
+        if (tid == 0) {
+            const unsigned int bx = (unsigned int)len * NCOL * 8u, bl = (unsigned int)len * 8u;
+            unsigned int total = bx;
+            if (WT::ANY_D) total += bx + bl;
+            if (DYN) total += bl + (WT::ANY_D ? bl : 0u);
+            mbar_expect_tx(bar, total);
+            bulk_g2s(ngrtd_smem + s.Xf, pv.Xf + (size_t)kc * NCOL, bx, bar);
+            if (WT::ANY_D) {
+                bulk_g2s(ngrtd_smem + s.Xd, pv.Xd + (size_t)kc * NCOL, bx, bar);
+                bulk_g2s(ngrtd_smem + s.itp, pv.itp + kc, bl, bar);
+            }
+            if (DYN) {
+                bulk_g2s(ngrtd_smem + s.xraw, pv.xraw + kc, bl, bar);
+                if (WT::ANY_D) bulk_g2s(ngrtd_smem + s.xrawd, pv.xrawd + kc, bl, bar);
+            }
         }
-        if (DYN) {
-            for (int i = tid; i < len; i += nthreads) ngrtd_smem[s.xraw + i] = pv.xraw[kc + i];
-            if (WT::ANY_D)
-                for (int i = tid; i < len; i += nthreads) ngrtd_smem[s.xrawd + i] = pv.xrawd[kc + i];
-        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
     }
 
     // forward model of NT tiles: lane (r, j) receives tracers j, j+4 of chain r in val[t][0..1].
