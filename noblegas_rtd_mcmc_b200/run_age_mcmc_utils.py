@@ -181,3 +181,19 @@ class conv_mcmc(object):
                       'sample_stats': {'accept_rate': smp.get("accepted").cpu().numpy() / float(tune + draws),
                                        'lamb': smp.get("lamb").cpu().numpy()}}
         return self.idata
+
+    def posterior_predictive(self, idata=None, tracers=None, chain=None, max_draws=None):
+        """Batched replacement of the reference's posterior-predictive Python loop (run_age_mcmc.py:243-319): one
+        launch evaluates every posterior draw for every tracer.  Returns {tracer: ndarray[draws]}."""
+        idata = idata or self.idata
+        post = idata['posterior']
+        tracers = list(tracers or self.tracer)
+        ckw = {t: dict(self.conv_kwgs[t], mod_type1=self.mod_type1, mod_type2=self.mod_type2) for t in tracers}
+        joint = JointForwardMod(ckw, self.par_names, tracers)
+        sel = slice(None) if chain is None else chain                      # the reference uses chain 0 only (:277)
+        cols = [np.asarray(post[p])[sel].reshape(-1) for p in self.par_names]
+        theta = np.ascontiguousarray(np.stack(cols, axis=1))
+        if max_draws is not None:
+            theta = theta[:max_draws]
+        out = joint.perform_batch(theta)
+        return {t: out[:, i].copy() for i, t in enumerate(tracers)}

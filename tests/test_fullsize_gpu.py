@@ -1,0 +1,133 @@
+"""GPU: parity at BASELINE.json's full sizes through size-independent properties (batch-split invariance, mixture and
+input linearity, J scaling, eta=1 identity) plus oracle spot checks on random subsets, for cfg 3 (65,536 chains, L=840),
+the real yearly series (L=25,256, chunk-streamed path) and a cfg-5 style long lag axis (L=10,000)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_subset(X, descs, m1, m2, theta, pn, idx):
+    import c_oracle
+    return c_oracle.forward(X, descs, m1, m2, theta[idx], pn)
+
+
+def test_cfg3_full_batch_properties():
+    from helpers import rel_err, synth_descs
+    from noblegas_rtd_mcmc_b200 import _lib, synthetic
+    pn = list(synthetic.PAR_NAMES_CFG3)
+    X, descs = synth_descs(pn)
+    plan = _lib.Plan(X, descs, "exp_pist_flow", "dispersion")
+    B = 65536
+    theta = synthetic.theta_cfg3_informative(B, 9)
+    theta[: B // 2] = synthetic.theta_cfg3(B // 2, 9)             # half from the wide prior (NaN-producing region)
+    full = plan.forward_host(theta, pn)
+    # (i) batch-split invariance, bitwise (ragged splits, not multiples of the 16-chain unit)
+    cuts = [0, 7, 4099, 33333, B]
+    parts = np.concatenate([plan.forward_host(theta[a:b], pn) for a, b in zip(cuts[:-1], cuts[1:])], axis=0)
+    assert np.array_equal(full, parts, equal_nan=True)
+    # (ii) mixture linearity: f1*EPM + f2*DM with single-component plans
+    p1 = _lib.Plan(X, descs, "exp_pist_flow", False)
+    p2 = _lib.Plan(X, descs, "dispersion", False)
+    c1 = p1.forward_host(theta[:, [0, 4, 6]], ["tau1", "eta1", "J"])
+    c2 = p2.forward_host(theta[:, [1, 5, 6]], ["tau1", "D1", "J"])
+    mix = theta[:, [2]] * c1 + theta[:, [3]] * c2
+    assert rel_err(full, mix) < 1e-12
+    # (iii) input linearity: doubling every series doubles every series-driven tracer exactly
+    plan2 = _lib.Plan(2.0 * X, descs, "exp_pist_flow", "dispersion")
+    dbl = plan2.forward_host(theta[:8192], pn)
+    assert np.array_equal(dbl[:, :6], 2.0 * full[:8192, :6], equal_nan=True)
+    # (iv) He4_ter is proportional to J = 10**theta_J
+    th2 = theta[:8192].copy()
+    th2[:, 6] += np.log10(4.0)
+    he = plan.forward_host(th2, pn)[:, 6]
+    assert rel_err(he, 4.0 * full[:8192, 6]) < 1e-13
+    # (v) oracle spot check on a random subset (C port of the reference arithmetic)
+    idx = np.random.default_rng(0).choice(B, 768, replace=False)
+    want = _oracle_subset(X, descs, "exp_pist_flow", "dispersion", theta, pn, idx)
+    assert rel_err(full[idx], want) < 1e-10
+    assert np.isnan(full).any() and np.isfinite(full).any()
+
+
+def test_real_series_full_length_properties():
+    """L = 25,256 (reference C_in_dict), 4,096 chains of the shipped `.123` EPM+PFM configuration."""
+    from helpers import MODEL_CFGS, load_c_in, real_plan, rel_err
+    m1, m2, pn = MODEL_CFGS["epm_pfm123"]
+    tracers = ["CFC12", "SF6", "H3", "He4_ter", "He3", "CFC11", "CFC113"]
+    plan, C = real_plan(m1, m2, pn, tracers)
+    rng = np.random.default_rng(4)
+    B = 4096
+    f1 = rng.uniform(0.01, 0.99, B)
+    theta = np.stack([rng.uniform(1, 1000, B), rng.uniform(50, 15000, B), f1, 1 - f1, rng.uniform(1, 5, B),
+                      rng.normal(-10.42, 0.33, B), rng.uniform(5, 35, B), np.abs(rng.normal(0, 0.17, B))], axis=1)
+    full = plan.forward_host(theta, pn)
+    halves = np.concatenate([plan.forward_host(theta[:1111], pn), plan.forward_host(theta[1111:], pn)], axis=0)
+    assert np.array_equal(full, halves, equal_nan=True)
+    # eta1 = 1 makes exp_pist_flow identical to exponential (verified on the reference)
+    th1 = theta.copy()
+    th1[:, 4] = 1.0
+    a = plan.forward_host(th1, pn)
+    plan_e, _ = real_plan("exponential", "piston", [p for p in pn if p != "eta1"], tracers)
+    b = plan_e.forward_host(np.delete(th1, 4, axis=1), [p for p in pn if p != "eta1"])
+    assert np.array_equal(a, b, equal_nan=True)
+    # oracle spot check
+    import c_oracle
+    names = ["CFC11", "CFC12", "CFC113", "SF6", "H3"]
+    X = np.stack([C[n] for n in names], axis=1)
+    from test_oracle_golden import _real_descs
+    _, descs = _real_descs(tracers, pn)
+    idx = rng.choice(B, 96, replace=False)
+    want = c_oracle.forward(X, descs, m1, m2, theta[idx], pn)
+    assert rel_err(full[idx], want) < 1e-10
+
+
+def test_cfg5_long_lag_axis_mixture():
+    """cfg 5: L = 10,000 lags, EPM + dispersion mixture with 4He accumulation (chunk-streamed, 10 chunks)."""
+    import c_oracle
+    from helpers import rel_err
+    from noblegas_rtd_mcmc_b200 import _lib
+    L = 10000
+    rng = np.random.default_rng(8)
+    k = np.arange(L)
+    X = np.stack([5 + 2000 * np.exp(-((k - 60.0) / 8.0) ** 2), 500 / (1 + np.exp((k - 50.0) / 8.0)) + 1e-10,
+                  9 * np.exp(-k / 25.0) + 1e-10], axis=1) * rng.lognormal(0, 0.05, (L, 3))
+    descs = [dict(series=0, lam=np.log(2) / 12.34), dict(series=0, lam=np.log(2) / 12.34, rad_accum="3He"),
+             dict(series=1), dict(series=2, use_lamsf6=True), dict(series=-1, rad_accum="4He")]
+    pn = ["tau1", "tau2", "f1", "f2", "eta1", "D2", "J", "lamsf6"]
+    plan = _lib.Plan(X, descs, "exp_pist_flow", "dispersion")
+    B = 2048
+    f1 = rng.uniform(0.01, 0.99, B)
+    theta = np.stack([rng.uniform(1, 1000, B), rng.uniform(50, 15000, B), f1, 1 - f1, rng.uniform(1, 5, B),
+                      rng.uniform(0.01, 2, B), rng.normal(-10.42, 0.33, B), np.abs(rng.normal(0, 0.17, B))], axis=1)
+    out = plan.forward_host(theta, pn)
+    want = c_oracle.forward(X, descs, "exp_pist_flow", "dispersion", theta, pn)
+    assert rel_err(out, want) < 1e-10
+    assert np.isfinite(out).mean() > 0.9
+
+
+def test_posterior_predictive_batch_matches_loop():
+    """the posterior-predictive sweep of run_age_mcmc.py:243-319 as one batched launch."""
+    import pandas as pd
+    from helpers import load_c_in
+    from noblegas_rtd_mcmc_b200.convolution_integral_utils import tracer_conv_integral
+    from noblegas_rtd_mcmc_b200.run_age_mcmc_utils import conv_mcmc
+    C = load_c_in(3000)
+    L = 3000
+    df = lambda v, n: pd.DataFrame({n: v[::-1]}, index=np.arange(L - 1, -1, -1))
+    ckw = {"mod_type1": "dispersion", "mod_type2": False, "CFC12": dict(C_t=df(C["CFC12"], "CFC12")),
+           "H3": dict(C_t=df(C["H3"], "H3_tu"), t_half=12.34)}
+    okw = {t: dict(obs_df=np.array([v, v * 1.02, v * 0.98]), obs_perr=0.05) for t, v in (("CFC12", 36.4), ("H3", 4.87))}
+    pkw = dict(tau1_low=1.0, tau1_high=1000.0, D1_low=0.01, D1_high=2.0, par_names=["tau1", "D1"])
+    mc = conv_mcmc("PLM1", ["CFC12", "H3"], okw, ckw, pkw, "conv_traces", "0")
+    idata = mc.sample_mcmc(chains=8, tune=1500, draws=500, tune_interval=250)
+    post = idata["posterior"]
+    assert post["tau1"].shape == (8, 500) and np.all((post["tau1"] > 1) & (post["tau1"] < 1000))
+    assert np.all((post["nu"] >= 5) & (post["nu"] <= 30))
+    pp = mc.posterior_predictive(chain=0)
+    assert pp["CFC12"].shape == (500,)
+    m = tracer_conv_integral(ckw["H3"]["C_t"], 0)
+    for s in (0, 17, 499):                                              # the reference's per-draw loop, 3 draws
+        m.update_pars(tau=post["tau1"][0, s], mod_type="dispersion", t_half=12.34, D=post["D1"][0, s], bbar=False, Phi_im=False)
+        assert abs(m.convolve() - pp["H3"][s]) <= 1e-12 * abs(pp["H3"][s])
+    mu, err = mc.observations()
+    assert abs(np.median(pp["CFC12"]) - mu[0]) < 4 * err[0]          # the fit explains the observation
