@@ -197,6 +197,11 @@ typedef struct ngrtd_sampler ngrtd_sampler;
 int ngrtd_sampler_create(ngrtd_sampler** s, const ngrtd_sampler_cfg* cfg, ngrtd_plan* plan, int64_t nchains,
                          const double* q0, int32_t device);
 int ngrtd_sampler_destroy(ngrtd_sampler* s);
+/* BASELINE config 4 (joint fit over wells x recharge-ensemble members): every group of `chains_per_group` consecutive
+ * GLOBAL chain ids gets its own observation row (the reference loops wells serially, run_age_mcmc.py:122, and builds
+ * obs_mu/obs_err per well from ens_dict, run_age_mcmc_utils.py:353-356).  obs_mu, obs_sd: HOST [ngroups, nobs]. */
+int ngrtd_sampler_set_obs_groups(ngrtd_sampler* s, const double* obs_mu, const double* obs_sd, int64_t ngroups,
+                                 int64_t chains_per_group);
 /* advance every chain by nsteps Metropolis steps in ONE kernel launch.  tune: tuning phase; record: update the
  * per-chain Welford statistics and, if trace_d != NULL, write natural-space draws trace_d[ceil(nsteps/thin), B, ndim]. */
 int ngrtd_sampler_run(ngrtd_sampler* s, int64_t nsteps, int32_t tune, int32_t record, int32_t thin, double* trace_d,

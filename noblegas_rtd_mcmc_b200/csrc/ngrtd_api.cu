@@ -670,6 +670,7 @@ struct ngrtd_sampler {
     double tune_drop_fraction = 0.9;
     long long step = 0, ndraws = 0, hist_start = 0;
     size_t n_q = 0;
+    double* d_groups = nullptr;     // [3, G, ntr]: obs, 1/sd, likelihood constant
 };
 
 static double lbeta(double a, double b) { return std::lgamma(a) + std::lgamma(b) - std::lgamma(a + b); }
@@ -755,7 +756,7 @@ extern "C" int ngrtd_sampler_destroy(ngrtd_sampler* S) {
     if (!S) return NGRTD_OK;
     SamplerView& v = S->sv;
     cudaFree(v.q); cudaFree(v.logp); cudaFree(v.lamb); cudaFree(v.scal); cudaFree(v.acc_win); cudaFree(v.acc_tot);
-    cudaFree(v.hist); cudaFree(v.wf_mean); cudaFree(v.wf_m2);
+    cudaFree(v.hist); cudaFree(v.wf_mean); cudaFree(v.wf_m2); cudaFree(S->d_groups);
     delete S;
     return NGRTD_OK;
 }
@@ -836,6 +837,8 @@ extern "C" int ngrtd_sampler_create(ngrtd_sampler** out, const ngrtd_sampler_cfg
     v.chain_offset = cfg->chain_offset;
     v.B = nchains;
     v.hist_cap = cfg->hist_cap;
+    v.g_obs = v.g_isd = v.g_lc = nullptr;
+    v.cpg = 0;
     for (int i = 0; i < NVAL; i++) v.val_defaults[i] = 0.0;
     if (plan) {
         v.val_defaults[NGRTD_P_F1] = 1.0;                                     // p_dict defaults, run_age_mcmc_utils.py:73-79
@@ -888,6 +891,39 @@ extern "C" int ngrtd_sampler_create(ngrtd_sampler** out, const ngrtd_sampler_cfg
     }
     if (rc) { ngrtd_sampler_destroy(S); return rc; }
     *out = S;
+    return NGRTD_OK;
+}
+
+// per-group observations: group g owns global chains [g*cpg, (g+1)*cpg)
+extern "C" int ngrtd_sampler_set_obs_groups(ngrtd_sampler* S, const double* obs_mu, const double* obs_sd, int64_t ngroups,
+                                            int64_t chains_per_group) {
+    if (!S || !obs_mu || !obs_sd) return fail(NGRTD_EINVAL, "obs_groups: null pointer");
+    if (ngroups < 1 || chains_per_group < 1) return fail(NGRTD_EINVAL, "obs_groups: need ngroups, chains_per_group >= 1");
+    SamplerView& v = S->sv;
+    if ((v.chain_offset + v.B + chains_per_group - 1) / chains_per_group > ngroups)
+        return fail(NGRTD_EINVAL, "obs_groups: the shard's chains reach beyond the last group");
+    const size_t n = (size_t)ngroups * v.ntr;
+    std::vector<double> h(3 * n);
+    for (size_t i = 0; i < n; i++) {
+        double sd = obs_sd[i];
+        h[i] = obs_mu[i];
+        h[n + i] = 1.0 / sd;
+        h[2 * n + i] = v.lik_kind == NGRTD_LIK_NORMAL ? -0.5 * std::log(2.0 * M_PI * sd * sd) : -std::log(sd);
+    }
+    CUDA_TRY(cudaSetDevice(S->device));
+    cudaFree(S->d_groups);
+    S->d_groups = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&S->d_groups, 3 * n * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(S->d_groups, h.data(), 3 * n * sizeof(double), cudaMemcpyHostToDevice));
+    v.g_obs = S->d_groups;
+    v.g_isd = S->d_groups + n;
+    v.g_lc = S->d_groups + 2 * n;
+    v.cpg = chains_per_group;
+    RunArgs ra{};                    // the likelihood changed: refresh logp of the current state
+    ra.mode = 1; ra.nsteps = 1; ra.thin = 1;
+    int rc = sampler_launch(S, ra, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
     return NGRTD_OK;
 }
 

@@ -60,6 +60,11 @@ struct SamplerView {
     int hist_cap;
     double* wf_mean;         // [B, nd] running mean of the natural values (Welford)
     double* wf_m2;           // [B, nd] running sum of squared deviations
+    // per-group observations (config 4: wells x ensemble members): tables [G, ntr]; group = global chain id / cpg
+    const double* g_obs;
+    const double* g_isd;
+    const double* g_lc;
+    long long cpg;           // chains per group (0: one observation vector for all chains, obs/isd/lc above)
     GasList gases;           // noble-gas model: modelled gases
     double val_defaults[NVAL];   // value registers not driven by a sampler dimension (p_dict defaults)
 };
@@ -286,7 +291,24 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
                 double* qs = ngrtd_smem + rec[t];
                 double* qp = qs + ND_MAX;
                 double* sc = qs + 2 * ND_MAX + NVAL;
-                double ll = lik_reduce(lik, pv.ntracer, j, val[t], nu[t]);
+                double ll;
+                if (sv.cpg > 0) {                    // this chain's own observation row
+                    const long long grp = (sv.chain_offset + (ok[t] ? chain[t] : 0)) / sv.cpg;
+                    LikPar lg;
+                    lg.kind = lik.kind;
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        int tr = j + 4 * q;
+                        if (tr < pv.ntracer) {
+                            lg.obs[tr] = sv.g_obs[grp * pv.ntracer + tr];
+                            lg.isd[tr] = sv.g_isd[grp * pv.ntracer + tr];
+                            lg.lc[tr] = sv.g_lc[grp * pv.ntracer + tr];
+                        }
+                    }
+                    ll = lik_reduce(lg, pv.ntracer, j, val[t], nu[t]);
+                } else {
+                    ll = lik_reduce(lik, pv.ntracer, j, val[t], nu[t]);
+                }
                 double lpn = sc[3] + ll;
                 double delta = lpn - sc[0];
                 bool acc = ra.mode == 1 || (isfinite(delta) && log(sc[4]) < delta);    // metrop_select
@@ -381,9 +403,13 @@ __global__ void k_mcmc_ng(SamplerView sv, RunArgs ra) {
         double nu = sv.nu_sampled ? sv.nu_lo + (sv.nu_hi - sv.nu_lo) * vals[VAL_NU] : sv.nu_fixed;
         double cst = sv.lik_kind == 1 ? lik_studentt_const(nu) : 0.0;
         double ll = 0.0;
+        const long long grp = sv.cpg > 0 ? gchain / sv.cpg : 0;
         for (int g = 0; g < sv.gases.n; g++) {
             double mu = ce_eval(0, sv.gases.id[g], E, T, Ae, F, P, 0.0);
-            ll += sv.lik_kind == 1 ? lik_term_studentt(sv.obs[g], mu, sv.isd[g], sv.lc[g], nu, cst) : lik_term_normal(sv.obs[g], mu, sv.isd[g], sv.lc[g]);
+            double ob = sv.cpg > 0 ? sv.g_obs[grp * sv.gases.n + g] : sv.obs[g];
+            double is = sv.cpg > 0 ? sv.g_isd[grp * sv.gases.n + g] : sv.isd[g];
+            double lc = sv.cpg > 0 ? sv.g_lc[grp * sv.gases.n + g] : sv.lc[g];
+            ll += sv.lik_kind == 1 ? lik_term_studentt(ob, mu, is, lc, nu, cst) : lik_term_normal(ob, mu, is, lc);
         }
         double lpn = lps + ll;
         double delta = lpn - logp;

@@ -103,6 +103,15 @@ class Sampler(object):
                                               _lib.dptr(trace), _lib.stream_ptr(stream)))
         return trace
 
+    def set_obs_groups(self, obs_mu, obs_sd, chains_per_group):
+        """Config 4: obs_mu/obs_sd [ngroups, nobs]; global chains [g*cpg, (g+1)*cpg) are fitted to row g."""
+        mu = _lib.f64(np.atleast_2d(obs_mu))
+        sd = _lib.f64(np.atleast_2d(obs_sd))
+        if mu.shape != sd.shape:
+            raise ValueError("obs_mu and obs_sd must have the same shape [ngroups, nobs]")
+        _lib.check(_lib.lib.ngrtd_sampler_set_obs_groups(self.handle, _lib.hptr(mu), _lib.hptr(sd), mu.shape[0],
+                                                         int(chains_per_group)))
+
     def stop_tuning(self):
         _lib.check(_lib.lib.ngrtd_sampler_stop_tuning(self.handle))
 

@@ -168,3 +168,45 @@ def test_age_posterior_matches_quadrature():
     mcse = a.std() / np.sqrt(D.ess_mean(a))
     assert abs(a.mean() - qm) < 5 * mcse + 0.01 * qs, (a.mean(), qm, mcse)
     assert abs(a.std() - qs) < 0.08 * qs, (a.std(), qs)
+
+
+def test_observation_groups_config4():
+    """Config 4 (wells x ensemble members): one sampler with per-group observation rows == independent samplers per
+    group (bit-identical trajectories, because chains are keyed by global id), for both kernels."""
+    import torch
+    from helpers import synth_plan
+    from noblegas_rtd_mcmc_b200 import synthetic
+    from noblegas_rtd_mcmc_b200.sampler import Sampler, prior
+    fx, mcmc_model = _ng_setup()
+    wells = ["PLM1", "PLM6", "PLM7"]
+    mdls = [mcmc_model(fx["wells"][w]["obs"], mcmc_model.well_elev["PLM1"]) for w in wells]
+    kw = dict(plan=None, gases=mdls[0].gases, lik="studentt", nu_range=(1.0, 30.0), tune_interval=50, hist_cap=400, seed=3)
+    joint = Sampler(mdls[0].build_priors(), mdls[0].obs_mu, mdls[0].obs_sd, 3 * 40, **kw)
+    joint.set_obs_groups(np.stack([m.obs_mu for m in mdls]), np.stack([m.obs_sd for m in mdls]), 40)
+    joint.run(200, tune=True)
+    qj = joint.get("q")
+    for g, m in enumerate(mdls):
+        solo = Sampler(m.build_priors(), m.obs_mu, m.obs_sd, 40, chain_offset=40 * g, **kw)
+        solo.run(200, tune=True)
+        assert torch.equal(qj[40 * g:40 * (g + 1)], solo.get("q")), wells[g]
+    # age model, 2 groups x 24 chains through the fused kernel (groups straddle the 16-chain units)
+    pn = list(synthetic.PAR_NAMES_CFG3)
+    plan, _, _ = synth_plan("exp_pist_flow", "dispersion", pn)
+    truths = np.array([[180.0, 1500.0, 0.6, 0.4, 1.8, 0.4, synthetic.LOG10_J_MONTHLY],
+                       [90.0, 2500.0, 0.3, 0.7, 1.2, 0.9, synthetic.LOG10_J_MONTHLY]])
+    obs = plan.forward_host(truths, pn)
+    sd = 0.05 * np.abs(obs)
+    pri = [prior("uniform", "tau1", 12, 12000), prior("beta", "nu_", 2.0, 0.1), prior("normal", "J", synthetic.LOG10_J_MONTHLY, 0.33),
+           prior("uniform", "tau2", 600, 180000), prior("uniform", "f1", 0.01, 0.99), prior("uniform", "eta1", 1, 5),
+           prior("uniform", "D2", 0.01, 2.0)]
+    q0 = [-3.0, 2.0, synthetic.LOG10_J_MONTHLY, -4.5, 0.3, -1.0, -1.2]
+    akw = dict(plan=plan, lik="studentt", nu_range=(5.0, 30.0), f2_from_f1=True, tune_interval=25, hist_cap=200, seed=8, q0=q0, scaling=0.01)
+    joint = Sampler(pri, obs[0], sd[0], 48, **akw)
+    joint.set_obs_groups(obs, sd, 24)
+    joint.run(60, tune=True)
+    for g in range(2):
+        solo = Sampler(pri, obs[g], sd[g], 24, chain_offset=24 * g, **akw)
+        solo.run(60, tune=True)
+        assert torch.equal(joint.get("q")[24 * g:24 * (g + 1)], solo.get("q")), g
+    with pytest.raises(Exception):
+        joint.set_obs_groups(obs, sd, 8)          # 48 chains would need 6 groups
