@@ -255,6 +255,34 @@ def main():
         e2e_s = float(t[0])
     e2e_value = world * B * T_COUNTED * args.steps / e2e_s
 
+    # ---- informational: the same workload as fused Metropolis steps (propose -> forward -> Student-T -> accept) inside
+    #      the persistent sampler kernel, 100 steps per launch, chains started inside the informative region ----
+    from noblegas_rtd_mcmc_b200.sampler import Sampler, prior
+    truth = np.array([[180.0, 1500.0, 0.6, 0.4, 1.8, 0.4, synthetic.LOG10_J_MONTHLY]])
+    sobs = plan.forward_host(truth, pn)[0]
+    pri = [prior("uniform", "tau1", 12, 12000), prior("beta", "nu_", 2.0, 0.1), prior("normal", "J", synthetic.LOG10_J_MONTHLY, 0.33),
+           prior("uniform", "tau2", 600, 180000), prior("uniform", "f1", 0.01, 0.99), prior("uniform", "eta1", 1, 5),
+           prior("uniform", "D2", 0.01, 2.0)]
+    smp = Sampler(pri, sobs, 0.05 * np.abs(sobs), B, plan=plan, lik="studentt", nu_range=(5.0, 30.0), f2_from_f1=True,
+                  tune_interval=100, hist_cap=256, seed=1, chain_offset=rank * B, scaling=0.01, device=local,
+                  q0=[-3.0, 2.0, synthetic.LOG10_J_MONTHLY, -4.5, 0.3, -1.0, -1.2])
+    smp.run(100, tune=True)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(stream)
+    smp.run(100, tune=True, stream=stream)
+    s1.record(stream)
+    barrier()
+    smp_ms = s0.elapsed_time(s1) / 100.0
+    if world > 1:
+        t = torch.tensor([smp_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        smp_ms = float(t[0])
+    sampler_info = {"value": world * B * T_COUNTED / (smp_ms * 1e-3), "unit": UNIT, "ms_per_step": smp_ms,
+                    "steps_per_launch": 100, "kernel": "k_mcmc_age<G,D>", "proposal": "DE-MC-Z", "likelihood": "studentt",
+                    "accept_rate": float(smp.get("accepted").mean()) / 200.0}
+    smp.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cstep, n, cores = cpu_port_rate(seconds_target=12.0)
@@ -280,7 +308,7 @@ def main():
                              "peak_source": "measured FP64 DFMA peak on this pool (tools/microbench/fp64_peak.cu); "
                                             "MEASURED_PEAKS.json has no FP64 entry",
                              "kernel": "k_forward<G,D>", "kernel_ms": kern_ms, "flops_per_chain": F_STEP},
-                "cpu_baseline": cpu, "checksum_logp": checksum}
+                "cpu_baseline": cpu, "sampler": sampler_info, "checksum_logp": checksum}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -482,45 +482,54 @@ struct FwdCta {
     // sub-partitions (warp & 3 selects the sub-partition) and, within one, round-robin to its warps.  All units
     // cost the same, so every sub-partition carries floor or ceil of nunits/(4*grid) units and its FP64 pipe stays
     // shared by >= 3 warps until the end (a dynamic counter let the last partial round pile onto random
-    // sub-partitions: profiles/r1_notes.md).  Long lag axis: CTA-wide rounds in lock step.
-    template <class F>
-    __device__ __forceinline__ void for_each_unit(long long nunits, F f) {
-        if (nchunks == 1) {
+    // sub-partitions: profiles/r1_notes.md).  Long lag axis: CTA-wide rounds in lock step (inactive warps still
+    // iterate so that they take part in the chunk barriers).
+    // Used as:  for (cta.sched_begin(n); cta.sched_valid(); cta.sched_next()) { u = cta.unit; active = cta.active; ... }
+    // (a plain loop, not a callback: a lambda capturing the kernel-parameter structs by reference was not inlined in
+    // the full build and forced a 1.5 KB local-memory copy of the parameters per thread).
+    long long unit, sched_i, sched_n;
+    bool active, lockstep;
+    __device__ __forceinline__ void sched_begin(long long nunits) {
+        sched_n = nunits;
+        lockstep = nchunks != 1;
+        sched_i = lockstep ? (long long)blockIdx.x : (long long)(warp / (nwarps >= 4 ? 4 : nwarps));
+        sched_update();
+    }
+    __device__ __forceinline__ void sched_update() {
+        if (!lockstep) {
             const int spc = nwarps >= 4 ? 4 : nwarps;
-            const int wq = nwarps / spc;
-            const long long slot = (long long)blockIdx.x * spc + (warp % spc);
-            const long long nslots = (long long)gridDim.x * spc;
-            for (long long i = warp / spc;; i += wq) {
-                long long u = slot + i * nslots;
-                if (u >= nunits) break;
-                f(u, true, false);
-            }
+            unit = ((long long)blockIdx.x * spc + (warp % spc)) + sched_i * ((long long)gridDim.x * spc);
+            active = true;
         } else {
-            const long long ncta_units = (nunits + nwarps - 1) / nwarps;
-            for (long long cu = blockIdx.x; cu < ncta_units; cu += gridDim.x) {
-                long long u = cu * nwarps + warp;
-                f(u, u < nunits, true);
-            }
+            unit = sched_i * nwarps + warp;
+            active = unit < sched_n;
         }
+    }
+    __device__ __forceinline__ bool sched_valid() const {
+        return lockstep ? sched_i < (sched_n + nwarps - 1) / nwarps : unit < sched_n;
+    }
+    __device__ __forceinline__ void sched_next() {
+        sched_i += lockstep ? (long long)gridDim.x : (long long)(nwarps / (nwarps >= 4 ? 4 : nwarps));
+        sched_update();
     }
 };
 
 // sum of the likelihood terms of the tracers a lane owns (j, j+4), reduced over the 4 lanes of a chain.
+// ob/is/lc: observation, 1/sd and per-tracer constant of the lane's two tracers (registers, no indexed structs).
 // The nu-dependent Student-T constant is evaluated once per chain: lane 0 takes lgamma((nu+1)/2), lane 1 lgamma(nu/2),
 // lane 2 the log, and the pieces are combined with the same shuffles that reduce the tracer terms.
-__device__ __forceinline__ double lik_reduce(const LikPar& lik, int ntracer, int j, const double (&v)[2], double nu) {
+__device__ __forceinline__ double lik_reduce(int kind, int ntracer, int j, const double (&v)[2], const double (&ob)[2],
+                                             const double (&is)[2], const double (&lc)[2], double nu) {
     double acc = 0.0;
-    if (lik.kind == 1) {
+    if (kind == 1) {
         if (j == 0) acc = (double)ntracer * lgamma(0.5 * (nu + 1.0));
         else if (j == 1) acc = -(double)ntracer * lgamma(0.5 * nu);
         else if (j == 2) acc = -0.5 * (double)ntracer * log(nu * 3.14159265358979323846);
     }
 #pragma unroll
     for (int q = 0; q < 2; q++) {
-        int tr = j + 4 * q;
-        if (tr < ntracer)
-            acc += (lik.kind == 1) ? lik_term_studentt(lik.obs[tr], v[q], lik.isd[tr], lik.lc[tr], nu, 0.0)
-                                   : lik_term_normal(lik.obs[tr], v[q], lik.isd[tr], lik.lc[tr]);
+        if (j + 4 * q < ntracer)
+            acc += (kind == 1) ? lik_term_studentt(ob[q], v[q], is[q], lc[q], nu, 0.0) : lik_term_normal(ob[q], v[q], is[q], lc[q]);
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
@@ -536,7 +545,15 @@ k_forward(PlanView pv, SlotMap sm, const double* __restrict__ theta, long long B
     cta.setup(lc_cap);
     const int j = cta.lane & 3, r = cta.lane >> 2;
     const long long nunits = (B + NT * 8 - 1) / (NT * 8);
-    cta.for_each_unit(nunits, [&](long long u, bool active, bool lockstep) {
+    double ob[2], is[2], lc[2];                 // the lane's two tracers (j, j+4)
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        int tr = min(j + 4 * q, MAX_TRACER - 1);
+        ob[q] = lik.obs[tr]; is[q] = lik.isd[tr]; lc[q] = lik.lc[tr];
+    }
+    for (cta.sched_begin(nunits); cta.sched_valid(); cta.sched_next()) {
+        const long long u = cta.unit;
+        const bool active = cta.active, lockstep = cta.lockstep;
         ChainPar par[NT];
         long long chain[NT];
 #pragma unroll
@@ -547,7 +564,7 @@ k_forward(PlanView pv, SlotMap sm, const double* __restrict__ theta, long long B
         }
         double val[NT][2];
         cta.eval(par, active, lockstep, val);
-        if (!active) return;
+        if (!active) continue;
 #pragma unroll
         for (int t = 0; t < NT; t++) {
             bool ok = chain[t] < B;
@@ -557,11 +574,11 @@ k_forward(PlanView pv, SlotMap sm, const double* __restrict__ theta, long long B
             }
             if (logp != nullptr) {
                 double nu = (lik.kind == 1) ? lik.nu[ok ? chain[t] : B - 1] : 0.0;
-                double acc = lik_reduce(lik, pv.ntracer, j, val[t], nu);
+                double acc = lik_reduce(lik.kind, pv.ntracer, j, val[t], ob, is, lc, nu);
                 if (j == 0 && ok) logp[chain[t]] = acc;
             }
         }
-    });
+    }
 }
 
 }  // namespace ngrtd

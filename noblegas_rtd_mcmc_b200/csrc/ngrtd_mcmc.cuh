@@ -188,13 +188,16 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
     const int rec_warp = rec_base + cta.warp * NT * 8 * CH_REC;
     const long long B = sv.B;
     const long long nunits = (B + NT * 8 - 1) / (NT * 8);
-    LikPar lik;
-    lik.kind = sv.lik_kind;
+    double ob0[2], is0[2], lc0[2];              // shared observation vector: the lane's two tracers (j, j+4)
 #pragma unroll
-    for (int t = 0; t < MAX_TRACER; t++) { lik.obs[t] = sv.obs[t]; lik.isd[t] = sv.isd[t]; lik.lc[t] = sv.lc[t]; }
-    lik.nu = nullptr;
+    for (int q = 0; q < 2; q++) {
+        int tr = min(j + 4 * q, MAX_TRACER - 1);
+        ob0[q] = sv.obs[tr]; is0[q] = sv.isd[tr]; lc0[q] = sv.lc[tr];
+    }
 
-    cta.for_each_unit(nunits, [&](long long u, bool active, bool lockstep) {
+    for (cta.sched_begin(nunits); cta.sched_valid(); cta.sched_next()) {
+        const long long u = cta.unit;
+        const bool active = cta.active, lockstep = cta.lockstep;
         long long chain[NT];
         int rec[NT];
         bool ok[NT];
@@ -291,24 +294,16 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
                 double* qs = ngrtd_smem + rec[t];
                 double* qp = qs + ND_MAX;
                 double* sc = qs + 2 * ND_MAX + NVAL;
-                double ll;
-                if (sv.cpg > 0) {                    // this chain's own observation row
+                double ob[2] = {ob0[0], ob0[1]}, is[2] = {is0[0], is0[1]}, lc[2] = {lc0[0], lc0[1]};
+                if (sv.cpg > 0) {                    // config 4: this chain's own observation row
                     const long long grp = (sv.chain_offset + (ok[t] ? chain[t] : 0)) / sv.cpg;
-                    LikPar lg;
-                    lg.kind = lik.kind;
 #pragma unroll
                     for (int q = 0; q < 2; q++) {
-                        int tr = j + 4 * q;
-                        if (tr < pv.ntracer) {
-                            lg.obs[tr] = sv.g_obs[grp * pv.ntracer + tr];
-                            lg.isd[tr] = sv.g_isd[grp * pv.ntracer + tr];
-                            lg.lc[tr] = sv.g_lc[grp * pv.ntracer + tr];
-                        }
+                        long long o = grp * pv.ntracer + min(j + 4 * q, pv.ntracer - 1);
+                        ob[q] = sv.g_obs[o]; is[q] = sv.g_isd[o]; lc[q] = sv.g_lc[o];
                     }
-                    ll = lik_reduce(lg, pv.ntracer, j, val[t], nu[t]);
-                } else {
-                    ll = lik_reduce(lik, pv.ntracer, j, val[t], nu[t]);
                 }
+                double ll = lik_reduce(sv.lik_kind, pv.ntracer, j, val[t], ob, is, lc, nu[t]);
                 double lpn = sc[3] + ll;
                 double delta = lpn - sc[0];
                 bool acc = ra.mode == 1 || (isfinite(delta) && log(sc[4]) < delta);    // metrop_select
@@ -348,7 +343,7 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
             }
         }
         __syncwarp();
-    });
+    }
 }
 
 // ---------------------------------------------------------------- noble-gas CE model: one chain per thread

@@ -108,3 +108,37 @@ def J_flux(Del, rho_r, rho_w, U, Th, phi):
     PU = 1.19e-13
     PTh = 2.88e-14
     return Del * rho_r / rho_w * (U * PU + Th * PTh) * ((1 - phi) / phi)
+
+
+class ng_parse():
+    """Helium component separation of the reference (utils/noble_gas_utils.py:354-422, `He_comps`), batched: array-valued
+    Ae/F/E/T (e.g. the 50,000 posterior draws the reference loops over at age_modeling_mcmc.prep.py:356-385) give
+    array-valued components in `obs_dict_`.  One CE launch replaces three `noble_gas_fun` evaluations."""
+
+    def __init__(self, obs_dict, Ae, F, E, T):
+        self.obs_dict = obs_dict          # keys He4, He3 (single well)
+        self.Ae = Ae
+        self.F = F
+        self.E = E
+        self.T = T
+        self.obs_dict_ = obs_dict.copy()
+
+    def He_comps(self, Rterr):
+        He4_obs = self.obs_dict['He4']
+        He3_obs = self.obs_dict['He3']
+        ng_ = noble_gas_fun(gases=['He'], E=self.E, T=self.T, Ae=self.Ae, F=self.F, P='lapse_rate')
+        He4_eq = ng_.equil_conc()['He']                    # atmospheric equilibrium                      (:400)
+        He4_ex = ng_.ce_exc(add_eq_conc=False)['He']       # excess-air component                         (:401)
+        He4_atm = ng_.ce_exc(add_eq_conc=True)['He']       # equilibrium + excess air                     (:402)
+        He4_ter = He4_obs - He4_atm                        # terrigenic 4He                               (:403)
+        He4_del = 100 * (He4_ter / He4_atm)                # (:406)
+        self.obs_dict_['He4_eq'] = He4_eq
+        self.obs_dict_['He4_atm'] = He4_atm
+        self.obs_dict_['He4_ter'] = He4_ter
+        self.obs_dict_['He4_del'] = He4_del
+        Ratm = 1.384e-6                                    # 3He/4He in the atmosphere                    (:413)
+        S = 0.0
+        CF = 4.021e14 / (1 - S)
+        He3_trit = He3_obs - (He4_obs - He4_ter) * Ratm + He4_eq * Ratm * (1 - 0.983) - He4_ter * Rterr   # (:420)
+        self.obs_dict_['He3_tu'] = He3_trit * CF
+        self.He4_ex = He4_ex

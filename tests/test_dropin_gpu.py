@@ -159,3 +159,25 @@ def test_fused_loglik_matches_oracle():
     assert np.array_equal(model, model2)
     assert np.allclose(lp_n, O.logp_normal(obs, model, sd), rtol=1e-12, equal_nan=True)
     assert np.allclose(lp_t, O.logp_studentt(obs, model, sd, nu), rtol=1e-12, equal_nan=True)
+
+
+def test_ng_parse_he_comps_batched():
+    """He_comps over a batch of CE parameter draws against the oracle arithmetic."""
+    import np_oracle as O
+    from helpers import GOLD
+    from noblegas_rtd_mcmc_b200.noble_gas_utils import ng_parse
+    z = np.load(os.path.join(GOLD, "ce_model.npz"))
+    sel = z["T"] > 0.0
+    E, T, Ae, F = z["E"][sel], z["T"][sel], z["Ae"][sel], z["F"][sel]
+    obs = {"He4": 7.283e-08, "He3": 1.1e-13}
+    p = ng_parse(obs, Ae, F, E, T)
+    p.He_comps(Rterr=2.0e-8)
+    eq = O.equil_conc(["He"], T, O.lapse_rate(E))[:, 0]
+    atm = O.ce_exc(["He"], E, T, Ae, F, True)[:, 0]
+    ter = obs["He4"] - atm
+    tu = (obs["He3"] - (obs["He4"] - ter) * 1.384e-6 + eq * 1.384e-6 * (1 - 0.983) - ter * 2.0e-8) * 4.021e14
+    assert np.allclose(p.obs_dict_["He4_eq"], eq, rtol=1e-12) and np.allclose(p.obs_dict_["He4_ter"], ter, rtol=1e-9, atol=1e-22)
+    assert np.allclose(p.obs_dict_["He3_tu"], tu, rtol=1e-9, atol=1e-9)
+    s = ng_parse(obs, 0.01, 0.5, 3000.0, 3.5)
+    s.He_comps(2.0e-8)
+    assert isinstance(s.obs_dict_["He4_ter"], float)
