@@ -282,6 +282,36 @@ def main():
                     "steps_per_launch": 100, "kernel": "k_mcmc_age<G,D>", "proposal": "DE-MC-Z", "likelihood": "studentt",
                     "accept_rate": float(smp.get("accepted").mean()) / 200.0}
     smp.close()
+    # ---- informational: ESS/s (BASELINE.json's secondary metric) on config 1, the noble-gas closed-equilibrium fit of
+    #      well PLM1 with the reference's sampler settings (DEMetropolisZ, tune 10,000 / tune_interval 5,000), whose
+    #      posterior is validated against the reference's own summaries (tests/test_sampler_gpu.py).  32,768 chains per
+    #      GPU x 5,000 recorded draws, 2,048-slot history ring; per-chain Welford moments all-gathered over NCCL; many-chain ESS estimate. ----
+    import json as _json
+    from noblegas_rtd_mcmc_b200 import distributed as ngdist
+    from noblegas_rtd_mcmc_b200.noble_gas_mcmc import mcmc_model
+    fx = _json.load(open(os.path.join(ROOT, "tests", "golden", "ng_posterior.json")))["wells"]["PLM1"]
+    mdl = mcmc_model(fx["obs"], mcmc_model.well_elev["PLM1"])
+    NGC = 32768
+    ngs = Sampler(mdl.build_priors(), mdl.obs_mu, mdl.obs_sd, NGC, plan=None, gases=mdl.gases, lik="studentt",
+                  nu_range=(1.0, 30.0), tune_interval=5000, hist_cap=2048, seed=123423, chain_offset=rank * NGC, device=local)
+    barrier()
+    t_ess = time.perf_counter()
+    ngs.run(10000, tune=True, stream=stream)
+    ngs.stop_tuning()
+    ngs.run(5000, tune=False, record=True, stream=stream)
+    torch.cuda.synchronize()
+    summ = ngdist.global_summary(5000, ngs.get("mean"), ngs.get("m2"))
+    ess_s = time.perf_counter() - t_ess
+    if world > 1:
+        t = torch.tensor([ess_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ess_s = float(t[0])
+    ess_info = {"workload": "cfg1: noble-gas CE fit, well PLM1, DE-MC-Z, Student-T", "min_ess": float(np.min(summ["ess"])),
+                "max_r_hat": float(np.max(summ["r_hat"])), "seconds": ess_s, "ess_per_sec": float(np.min(summ["ess"])) / ess_s,
+                "chains": int(summ["chains"]), "steps_per_chain": 15000, "params": ngs.names,
+                "estimator": "M n var+/B over all chains (per-chain Welford moments all-gathered)",
+                "reference": "ess_bulk 1,304-4,049 per 200,000 draws (ng_interp/ng_optPLM1.csv), wall time not recoverable"}
+    ngs.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -308,7 +338,7 @@ def main():
                              "peak_source": "measured FP64 DFMA peak on this pool (tools/microbench/fp64_peak.cu); "
                                             "MEASURED_PEAKS.json has no FP64 entry",
                              "kernel": "k_forward<G,D>", "kernel_ms": kern_ms, "flops_per_chain": F_STEP},
-                "cpu_baseline": cpu, "sampler": sampler_info, "checksum_logp": checksum}
+                "cpu_baseline": cpu, "sampler": sampler_info, "ess": ess_info, "checksum_logp": checksum}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
