@@ -396,7 +396,7 @@ struct FwdCta {
     int lc_cap, nchunks, nwarps, nthreads, tid, lane, warp;
     int scratch_off;
     unsigned int phase;
-    bool need_J;
+    bool need_J, pending;   // pending: resident tables issued (TMA in flight), not yet waited for
 
     __device__ __forceinline__ FwdCta(const PlanView& pv_) : pv(pv_) {}
 
@@ -427,15 +427,17 @@ struct FwdCta {
             for (int i = tid; i < TBL_DOUBLES; i += nthreads) ngrtd_smem[s.tbl + i] = pv.tbl[i];
         }
         __syncthreads();
-        if (nchunks == 1) load_chunk(0, pv.Lpad);     // resident tables: loaded once per launch
-        __syncthreads();
+        pending = false;
+        if (nchunks == 1 && WT::ANY_LOOP) {           // resident tables: one TMA load per launch, waited for lazily so
+            issue_chunk(0, pv.Lpad);                  // that it overlaps the first unit's parameter loads and prologue
+            pending = true;
+        }
         return p;
     }
 
     // stage lags [kc, kc+len) of the plan tables into shared memory with TMA bulk copies (one elected thread issues
     // them, all threads wait on the mbarrier phase).  Callers guarantee no thread still reads the previous chunk.
-    __device__ __forceinline__ void load_chunk(int kc, int len) {
-        if (!WT::ANY_LOOP) return;
+    __device__ __forceinline__ void issue_chunk(int kc, int len) {
         unsigned long long* bar = reinterpret_cast<unsigned long long*>(ngrtd_smem + s.bar);
         if (tid == 0) {
             const unsigned int bx = (unsigned int)len * NCOL * 8u, bl = (unsigned int)len * 8u;
@@ -453,8 +455,15 @@ struct FwdCta {
                 if (WT::ANY_D) bulk_g2s(ngrtd_smem + s.xrawd, pv.xrawd + kc, bl, bar);
             }
         }
-        mbar_wait(bar, phase);
+    }
+    __device__ __forceinline__ void wait_chunk() {
+        mbar_wait(reinterpret_cast<unsigned long long*>(ngrtd_smem + s.bar), phase);
         phase ^= 1u;
+    }
+    __device__ __forceinline__ void load_chunk(int kc, int len) {
+        if (!WT::ANY_LOOP) return;
+        issue_chunk(kc, len);
+        wait_chunk();
     }
 
     // forward model of NT tiles: lane (r, j) receives tracers j, j+4 of chain r in val[t][0..1].
@@ -464,6 +473,7 @@ struct FwdCta {
         WT w;
         w.begin(par, pv);
         if (!lockstep) {
+            if (pending) { wait_chunk(); pending = false; }
             w.chunk(s, pv, 0, pv.Lpad / 4, lane);
         } else {
             for (int c = 0; c < nchunks; c++) {
@@ -579,6 +589,7 @@ k_forward(PlanView pv, SlotMap sm, const double* __restrict__ theta, long long B
             }
         }
     }
+    if (cta.pending) cta.wait_chunk();      // warps without work must not exit under an in-flight bulk copy
 }
 
 }  // namespace ngrtd

@@ -344,6 +344,7 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
         }
         __syncwarp();
     }
+    if (cta.pending) cta.wait_chunk();      // warps without work must not exit under an in-flight bulk copy
 }
 
 // ---------------------------------------------------------------- noble-gas CE model: one chain per thread

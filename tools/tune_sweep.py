@@ -6,14 +6,14 @@ import numpy as np, torch
 from noblegas_rtd_mcmc_b200 import synthetic
 from helpers import synth_plan
 
-B = 65536
+B = 65536 * 4
 cfgs = {"epm_dm": ("exp_pist_flow", "dispersion", list(synthetic.PAR_NAMES_CFG3)),
         "epm": ("exp_pist_flow", False, ["tau1", "eta1", "J"]),
         "dm": ("dispersion", False, ["tau1", "D1", "J"])}
 th7 = synthetic.theta_cfg3(B, 0)
 cols = dict(zip(synthetic.PAR_NAMES_CFG3, th7.T))
 cols["D1"] = cols["D2"]
-variants = [(0, 0, 0), (16, 2, 1), (16, 2, 2), (16, 1, 1), (16, 1, 2), (16, 3, 1), (12, 3, 1), (12, 2, 1), (8, 2, 1), (8, 2, 2), (8, 4, 1), (8, 1, 2)]
+variants = [(0, 0, 0), (16, 1, 1), (24, 1, 1), (20, 1, 1), (24, 2, 1)]
 which = sys.argv[1:] or list(cfgs)
 for name in which:
     m1, m2, pn = cfgs[name]
@@ -40,21 +40,3 @@ for name in which:
         if ref is None: ref = cs
         print("%-7s W=%2d NT=%d UA=%d  %.4f ms  %.2f TFLOP/s(8col)  checksum_rel=%.1e" % (name, w, nt, ua, ms, flops / ms / 1e9, abs(cs - ref) / abs(ref)), flush=True)
 
-# fixed overhead: time vs B at the default variant (W=16, NT=2 -> 37,888 chains per full round)
-for k in ("NGRTD_FWD_WARPS", "NGRTD_FWD_NT", "NGRTD_FWD_UA"):
-    os.environ[k] = "0"
-m1, m2, pn = cfgs["epm_dm"]
-plan, _, _ = synth_plan(m1, m2, pn)
-for Bs in (16, 2368 * 4, 2368 * 8, 2368 * 16, 2368 * 32, 2368 * 64, 65536, 2368 * 128):
-    th = torch.from_numpy(synthetic.theta_cfg3(Bs, 0)).cuda()
-    lp = torch.empty(Bs, dtype=torch.float64, device="cuda")
-    for _ in range(3):
-        plan.forward_loglik_dev(th, pn, np.ones(7), np.ones(7) * 0.05, "normal", logp_t=lp)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(20):
-        plan.forward_loglik_dev(th, pn, np.ones(7), np.ones(7) * 0.05, "normal", logp_t=lp)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 20
-    print("epm_dm B=%7d  %.4f ms  (%.2f TFLOP/s 8col)" % (Bs, ms, 2.0 * 840 * 8 * 2 * Bs / ms / 1e9), flush=True)
