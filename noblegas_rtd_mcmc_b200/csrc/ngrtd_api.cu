@@ -167,6 +167,50 @@ extern "C" int ngrtd_plan_create(ngrtd_plan** out, int32_t L, int32_t nseries, c
             xrawd[k] = xraw[k] * p15[k];
         }
     }
+    // ---- constant-tail detection (see PlanView::Kc) ----
+    {
+        PlanView& pv = P->pv;
+        pv.Kc = Lpad;
+        pv.dyn_bg = 0.0;
+        for (int c = 0; c < NCOL; c++) pv.ct[c] = ColTail{-1, 0.0, 0.0, 0.0, 0.0};
+        const bool want = getenv("NGRTD_NO_TAIL") == nullptr && c1 != CLS_D && c2 != CLS_D && (c1 == CLS_G || c2 == CLS_G);
+        if (want && L >= 64) {
+            int kvar = 0;                                       // first lag from which every used series is constant
+            auto scan = [&](int sidx) {
+                const double last = series[(size_t)(L - 1) * nseries + sidx];
+                int k = L - 1;
+                while (k > 0 && series[(size_t)(k - 1) * nseries + sidx] == last) k--;
+                kvar = std::max(kvar, k);
+            };
+            bool ok = true;
+            double i0 = 0.0, sl = 1.0;
+            for (size_t c = 1; c < cols.size(); c++) {
+                if (cols[c].mode == 2) {                        // lag index must be an exact arithmetic progression in the tail
+                    if (lag_index) {
+                        sl = lag_index[L - 1] - lag_index[L - 2];
+                        i0 = lag_index[L - 1] - sl * (double)(L - 1);
+                        int k = L - 1;
+                        while (k > 0 && lag_index[k - 1] == i0 + sl * (double)(k - 1)) k--;
+                        kvar = std::max(kvar, k);
+                    }
+                } else {
+                    scan(cols[c].series);
+                }
+            }
+            if (P->dyn && dyn_series >= 0) scan(dyn_series);
+            int Kc = std::max(4, (kvar + 3) & ~3);
+            if (ok && Kc + 32 <= L) {                           // a tail worth cutting
+                pv.Kc = Kc;
+                pv.ct[0] = ColTail{0, 1.0, 0.0, 0.0, 0.0};
+                for (size_t c = 1; c < cols.size(); c++) {
+                    const ColKey& ck = cols[c];
+                    if (ck.mode == 2) pv.ct[c] = ColTail{3, 0.0, ck.lambda, i0, sl};
+                    else pv.ct[c] = ColTail{ck.mode == 1 ? 2 : 1, series[(size_t)(L - 1) * nseries + ck.series], ck.lambda, 0.0, 0.0};
+                }
+                if (P->dyn && dyn_series >= 0) pv.dyn_bg = series[(size_t)(L - 1) * nseries + dyn_series];
+            }
+        }
+    }
     std::vector<double> tbl(TBL_DOUBLES);
     {
         uint32_t* w = reinterpret_cast<uint32_t*>(tbl.data());
@@ -247,7 +291,8 @@ template <int C1, int C2, bool DYN, int NT, int UA, int MAXW>
 static int launch_forward_t(ngrtd_plan* P, const SlotMap& sm, const double* theta, long long B, double* out,
                             double* logp, const LikPar& lik, cudaStream_t st, int warps_req) {
     using WT = WarpTiles<C1, C2, DYN, NT, UA>;
-    int lc_cap = WT::ANY_LOOP ? std::min(P->Lpad, LC_MAX) : 0;
+    const int Lloop = (WT::ANY_G && !WT::ANY_D && P->pv.Kc < P->pv.L) ? P->pv.Kc : P->Lpad;
+    int lc_cap = WT::ANY_LOOP ? std::min(Lloop, LC_MAX) : 0;
     long long nunits = (B + NT * 8 - 1) / (NT * 8);
     int warps = warps_req > 0 ? std::min(warps_req, MAXW) : pick_warps(nunits, P->nsm, MAXW);
     if (warps > 4) warps &= ~3;
@@ -699,7 +744,8 @@ static int launch_mcmc_age(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st)
     int warps = pick_warps(nunits, P->nsm, MAXW);
     if (warps > 4) warps &= ~3;
     // shared memory: forward tables + one CH_REC record per resident chain; shrink the lag chunk until it fits
-    int lc_cap = WT::ANY_LOOP ? std::min(P->Lpad, LC_MAX) : 0;
+    const int Lloop = (WT::ANY_G && !WT::ANY_D && P->pv.Kc < P->pv.L) ? P->pv.Kc : P->Lpad;
+    int lc_cap = WT::ANY_LOOP ? std::min(Lloop, LC_MAX) : 0;
     size_t sh = 0;
     for (;;) {
         sh = (size_t)TBL_DOUBLES + 2 + (size_t)warps * NT * 8 * NCOL + (size_t)lc_cap * NCOL;

@@ -53,6 +53,13 @@ struct TracerDev {
     int sf6;     // 1: *= 1 + lamsf6
 };
 
+struct ColTail {
+    int type;        // 0 ones, 1 decay, 2 ingrowth, 3 lag-index * decay, -1 unused column
+    double bg;       // constant series value beyond Kc
+    double lam;      // decay constant folded into the column
+    double i0, s;    // type 3: lag_index[k] = i0 + s*k for k >= Kc
+};
+
 // Device view of a plan (passed by value to kernels).
 struct PlanView {
     int L;          // true number of lags
@@ -63,11 +70,18 @@ struct PlanView {
     const double* itp;    // [Lpad] 1/tp (pad: 0)
     const double* xraw;   // [Lpad] raw series of the per-chain-lambda tracer
     const double* xrawd;  // [Lpad] xraw * tp^-1.5
-    const double* tbl;    // [32] doubles = hi[32], lo[32] words of 2^(j/32)
+    const double* tbl;    // [TBL_N] doubles = hi[TBL_N], lo[TBL_N] words of 2^(j/TBL_N)
     int ntracer;
     TracerDev tr[MAX_TRACER];
     int eta1_is_one, eta2_is_one;   // 'exponential' == exp_pist_flow with eta = 1 (bit-identical in the reference)
     double default_log10J;          // run_age_mcmc_utils.py:90-91
+    // Constant-tail closed form (exponential-class components only).  The reference back-extends every input series by
+    // ~25,000 constant rows (age_modeling_mcmc.prep.py:165-223): beyond lag Kc every folded column is bg*exp(-lam tp),
+    // bg*(1-exp(-lam tp)) or (i0 + s k)*exp(-lam tp), whose products with geometric weights sum in closed form.  The lag
+    // loop then covers only [0, Kc) and the tail [Kc, L) is added analytically in the epilogue (exact to rounding).
+    int Kc;                         // first lag of the analytic tail (multiple of 4); Kc >= Lpad: no tail
+    ColTail ct[NCOL];
+    double dyn_bg;                  // constant value of the per-chain-lambda series beyond Kc
 };
 
 struct SlotMap {

@@ -140,6 +140,35 @@ struct Comp<CLS_D> {
     }
 };
 
+// ---------------------------------------------------------------- analytic tail of geometric weights
+// G0(x, n) = sum_{i<n} e^{-i x},  G1(x, n) = sum_{i<n} i e^{-i x}   (x = eta/tau + lambda >= 0)
+__device__ __forceinline__ double geo_sum0(double x, double n) {
+    if (x == 0.0) return n;
+    return expm1(-n * x) / expm1(-x);
+}
+__device__ __forceinline__ double geo_sum1(double x, double n) {
+    double nx = n * x;
+    if (nx < 1e-4) {            // nearly uniform weights: Taylor in x (the closed form cancels like 2/(n x))
+        double m = n - 1.0;
+        double S1 = 0.5 * n * m, S2 = m * n * (2.0 * n - 1.0) / 6.0, S3 = S1 * S1;
+        return S1 - x * S2 + 0.5 * x * x * S3;
+    }
+    double om = -expm1(-x);     // 1 - q
+    double q = exp(-x), qn = exp(-nx);
+    return (q * geo_sum0(x, n) - n * qn) / om;
+}
+// sum_{k=a}^{L-1} w_k x_k for one folded column; w_k = Wa * exp(-er (k - a)), a = first tail lag with non-zero weight
+__device__ __forceinline__ double col_tail(const ColTail& ct, double er, double Wa, double a, double n, double dtp) {
+    if (ct.type < 0) return 0.0;
+    double g0 = geo_sum0(er, n);
+    if (ct.type == 0) return Wa * g0;
+    double Da = exp(-ct.lam * (a + dtp));
+    double g0l = (ct.lam == 0.0) ? g0 : geo_sum0(er + ct.lam, n);
+    if (ct.type == 1) return Wa * ct.bg * Da * g0l;
+    if (ct.type == 2) return Wa * ct.bg * (g0 - Da * g0l);
+    return Wa * Da * ((ct.i0 + ct.s * a) * g0l + ct.s * geo_sum1(er + ct.lam, n));
+}
+
 // ---------------------------------------------------------------- one warp = NT tiles of 8 chains
 template <int C1, int C2, bool DYN, int NT, int UA>
 struct WarpTiles {
@@ -269,6 +298,29 @@ struct WarpTiles {
                 a1[t][0][0] += a1[t][u][0]; a1[t][0][1] += a1[t][u][1];
                 a2[t][0][0] += a2[t][u][0]; a2[t][0][1] += a2[t][u][1];
             }
+            if (ANY_G && !ANY_D && pv.Kc < pv.L) {      // analytic tail [Kc, L) of the exponential-class components
+                const double dtp = pv.dtp;
+                if constexpr (C1 == CLS_G) {
+                    double a = (double)max(c1[t].k0, pv.Kc), n = (double)pv.L - a;
+                    if (n > 0.0) {
+                        double Wa = exp(-c1[t].er * ((a + dtp) - c1[t].tpk0));
+                        a1[t][0][0] += col_tail(pv.ct[2 * j], c1[t].er, Wa, a, n, dtp);
+                        a1[t][0][1] += col_tail(pv.ct[2 * j + 1], c1[t].er, Wa, a, n, dtp);
+                        if (DYN && j == 0)
+                            ad1[t] += Wa * pv.dyn_bg * exp(-p[t].lam_cfc * (a + dtp)) * geo_sum0(c1[t].er + p[t].lam_cfc, n);
+                    }
+                }
+                if constexpr (C2 == CLS_G) {
+                    double a = (double)max(c2[t].k0, pv.Kc), n = (double)pv.L - a;
+                    if (n > 0.0) {
+                        double Wa = exp(-c2[t].er * ((a + dtp) - c2[t].tpk0));
+                        a2[t][0][0] += col_tail(pv.ct[2 * j], c2[t].er, Wa, a, n, dtp);
+                        a2[t][0][1] += col_tail(pv.ct[2 * j + 1], c2[t].er, Wa, a, n, dtp);
+                        if (DYN && j == 0)
+                            ad2[t] += Wa * pv.dyn_bg * exp(-p[t].lam_cfc * (a + dtp)) * geo_sum0(c2[t].er + p[t].lam_cfc, n);
+                    }
+                }
+            }
             double m[2], md = 0.0;
             double x1[2], x2[2] = {0.0, 0.0}, xd1 = 0.0, xd2 = 0.0;
             // component 1
@@ -394,6 +446,7 @@ struct FwdCta {
     SmemView s;
     const PlanView& pv;
     int lc_cap, nchunks, nwarps, nthreads, tid, lane, warp;
+    int Lloop;       // lags covered by the lag loop: Lpad, or Kc when the analytic tail applies
     int scratch_off;
     unsigned int phase;
     bool need_J, pending;   // pending: resident tables issued (TMA in flight), not yet waited for
@@ -418,7 +471,8 @@ struct FwdCta {
         s.xraw = p; if (DYN) p += lc_cap;
         s.xrawd = p; if (DYN && WT::ANY_D) p += lc_cap;
         scratch_off = s.scratch + warp * NT * 8 * NCOL;
-        nchunks = WT::ANY_LOOP ? (pv.Lpad + lc_cap - 1) / lc_cap : 1;
+        Lloop = (WT::ANY_G && !WT::ANY_D && pv.Kc < pv.L) ? pv.Kc : pv.Lpad;
+        nchunks = WT::ANY_LOOP ? (Lloop + lc_cap - 1) / lc_cap : 1;
         need_J = false;
         for (int t = 0; t < pv.ntracer; t++) need_J |= (pv.tr[t].col_b >= 0);
         phase = 0;
@@ -429,7 +483,7 @@ struct FwdCta {
         __syncthreads();
         pending = false;
         if (nchunks == 1 && WT::ANY_LOOP) {           // resident tables: one TMA load per launch, waited for lazily so
-            issue_chunk(0, pv.Lpad);                  // that it overlaps the first unit's parameter loads and prologue
+            issue_chunk(0, Lloop);                    // that it overlaps the first unit's parameter loads and prologue
             pending = true;
         }
         return p;
@@ -474,11 +528,11 @@ struct FwdCta {
         w.begin(par, pv);
         if (!lockstep) {
             if (pending) { wait_chunk(); pending = false; }
-            w.chunk(s, pv, 0, pv.Lpad / 4, lane);
+            w.chunk(s, pv, 0, Lloop / 4, lane);
         } else {
             for (int c = 0; c < nchunks; c++) {
                 int kc = c * lc_cap;
-                int len = min(lc_cap, pv.Lpad - kc);
+                int len = min(lc_cap, Lloop - kc);
                 __syncthreads();
                 load_chunk(kc, len);
                 __syncthreads();

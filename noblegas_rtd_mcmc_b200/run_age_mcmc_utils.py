@@ -171,7 +171,14 @@ class conv_mcmc(object):
         smp = Sampler(pri, mu, err, chains, plan=joint.plan, lik=likelihood, nu_range=(5.0, 30.0),
                       f2_from_f1=bool(self.mod_type2), tune_interval=tune_interval,
                       hist_cap=hist_cap or (tune + draws), seed=random_seed)
-        trace = smp.sample(tune, draws, thin=thin).cpu().numpy()            # [draw, chain, dim]
+        import time as _time
+        import torch as _torch
+        _torch.cuda.synchronize()
+        t0 = _time.perf_counter()
+        trace_t = smp.sample(tune, draws, thin=thin)
+        _torch.cuda.synchronize()
+        self.sampling_time = _time.perf_counter() - t0                       # what pymc3 stores as `sampling_time`
+        trace = trace_t.cpu().numpy()                                        # [draw, chain, dim]
         post = {n: trace[:, :, i].T.copy() for i, n in enumerate(smp.names)}
         post['nu'] = post['nu_'] * (30.0 - 5.0) + 5.0
         if self.mod_type2:
@@ -179,7 +186,7 @@ class conv_mcmc(object):
             post['tau'] = post['f1'] * post['tau1'] + post['f2'] * post['tau2']          # :305
         self.idata = {'posterior': post,
                       'sample_stats': {'accept_rate': smp.get("accepted").cpu().numpy() / float(tune + draws),
-                                       'lamb': smp.get("lamb").cpu().numpy()}}
+                                       'lamb': smp.get("lamb").cpu().numpy(), 'sampling_time': self.sampling_time}}
         return self.idata
 
     def posterior_predictive(self, idata=None, tracers=None, chain=None, max_draws=None):
