@@ -106,3 +106,51 @@ def test_ce_edges():
         assert np.allclose(got[g], want[:, i], rtol=1e-12, atol=0, equal_nan=True), g
     one_atm = noble_gas_fun(["Ar"], 1234.0, 12.0, 0.002, 0.3, "1atm").equil_conc()["Ar"]
     assert abs(one_atm - O.equil_conc(["Ar"], 12.0, 0.000101325)[0]) < 1e-12 * one_atm
+
+
+def test_constant_tail_closed_form_corners():
+    """Series with a long constant tail (the reference's back-extension): analytic tail vs the oracle's full lag loop,
+    including masks beyond the cut (k0 > Kc), masks beyond the window, nearly uniform weights (Taylor branch of the
+    arithmetico-geometric sum), a non-unit lag-index slope and per-chain CFC decay."""
+    import np_oracle as O
+    from helpers import rel_err
+    from noblegas_rtd_mcmc_b200 import _lib
+    rng = np.random.default_rng(12)
+    L, nv = 6000, 77
+    X = np.empty((L, 3))
+    X[:nv] = rng.uniform(1.0, 50.0, (nv, 3))
+    X[nv:] = np.array([3.3273, 1e-10, 7.5])
+    idx = 2.0 * np.arange(L) + 10.0                                   # regular lag index, slope 2, offset 10
+    descs = [dict(series=0, lam=np.log(2) / 12.34), dict(series=0, lam=np.log(2) / 12.34, rad_accum="3He"), dict(series=1),
+             dict(series=2, use_thalf_cfc=True), dict(series=-1, rad_accum="4He"), dict(series=1, use_lamsf6=True)]
+    pn = ["tau1", "tau2", "f1", "f2", "eta1", "eta2", "J", "thalf_cfc", "lamsf6"]
+    plan = _lib.Plan(X, descs, "exp_pist_flow", "exp_pist_flow", lag_index=idx)
+    B = 600
+    f1 = rng.uniform(0.05, 0.95, B)
+    tau1 = np.exp(rng.uniform(0, np.log(2000), B))
+    tau2 = np.exp(rng.uniform(np.log(50), np.log(15000), B))
+    tau2[:8] = [1e6, 5e7, 1e9, 7000.0, 7499.9, 7500.1, 9000.0, 1e5]   # nearly uniform weights / masks around and beyond L
+    eta2 = rng.uniform(1, 5, B)
+    eta2[:8] = [1.0, 1.0, 1.0, 5.0, 5.0, 5.0, 5.0, 1.0001]
+    theta = np.stack([tau1, tau2, f1, 1 - f1, rng.uniform(1, 5, B), eta2, rng.normal(-10.4, 0.3, B), rng.uniform(5, 35, B),
+                      np.abs(rng.normal(0, 0.17, B))], axis=1)
+    out = plan.forward_host(theta, pn)
+    tp = O.lag_grid(L)
+    want = np.empty_like(out)
+    names = ["H3", "He3", "X", "CFC12", "He4_ter", "SF6"]
+    for i, d in enumerate(descs):
+        s = X[:, d["series"]] if d["series"] >= 0 else np.zeros(L)
+        want[:, i] = O.forward_mod(theta, pn, names[i], s, "exp_pist_flow", "exp_pist_flow",
+                                   t_half=(12.34 if d.get("lam") else False), rad_accum=d.get("rad_accum", False),
+                                   index_newest_first=idx)
+    assert rel_err(out, want) < 1e-10
+    assert np.isnan(out[:, 0]).sum() >= 2 and np.isfinite(out[0]).all()
+    # an irregular lag index disables the analytic tail for the 4He column but must still be exact
+    idx2 = idx.copy()
+    idx2[L - 3] += 0.5
+    plan2 = _lib.Plan(X, descs, "exponential", False, lag_index=idx2)
+    th2 = theta[:64][:, [0, 6, 7, 8]]
+    got = plan2.forward_host(th2, ["tau1", "J", "thalf_cfc", "lamsf6"])
+    w2 = O.forward_mod(th2, ["tau1", "J", "thalf_cfc", "lamsf6"], "He4_ter", np.zeros(L), "exponential", False, rad_accum="4He",
+                       index_newest_first=idx2)
+    assert rel_err(got[:, 4], w2) < 1e-10
