@@ -131,7 +131,9 @@ class tracer_conv_integral():
         if plan is None:
             desc = dict(series=0, rad_accum=ra, lam=0.0 if lam_batched else float(lam), use_thalf_cfc=lam_batched)
             plan = _lib.Plan(vals.reshape(-1, 1), [desc], self.mod_type, False, lag_index=idx, dtp=dtp)
-            self._plans = {key: plan}
+            if len(self._plans) >= 8:          # callers toggle mod_type/tau between convolve() calls (run_age_mcmc.py:299-303)
+                self._plans.pop(next(iter(self._plans)))
+            self._plans[key] = plan
         names, cols = ["tau1"], [self._col(self.tau, B)]
         if self.mod_type == "exp_pist_flow":
             names.append("eta1"); cols.append(self._col(self.eta, B))

@@ -38,7 +38,6 @@ struct ngrtd_plan {
     bool dyn = false;
     PlanView pv{};
     double *dXf = nullptr, *dXd = nullptr, *ditp = nullptr, *dxraw = nullptr, *dxrawd = nullptr, *dtbl = nullptr;
-    unsigned int* dcounter = nullptr;
     // workspace of the *_host entry points
     double *w_theta = nullptr, *w_out = nullptr, *w_logp = nullptr, *w_nu = nullptr;
     size_t w_theta_n = 0, w_out_n = 0, w_logp_n = 0, w_nu_n = 0;
@@ -232,7 +231,6 @@ extern "C" int ngrtd_plan_create(ngrtd_plan** out, int32_t L, int32_t nseries, c
     if ((e = up(&P->dXf, Xf)) != cudaSuccess || (e = up(&P->dXd, Xd)) != cudaSuccess ||
         (e = up(&P->ditp, itp)) != cudaSuccess || (e = up(&P->dxraw, xraw)) != cudaSuccess ||
         (e = up(&P->dxrawd, xrawd)) != cudaSuccess || (e = up(&P->dtbl, tbl)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&P->dcounter, 64)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&P->hstream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&P->hstream2, cudaStreamNonBlocking)) != cudaSuccess) {
         ngrtd_plan_destroy(P);
@@ -259,7 +257,7 @@ extern "C" int ngrtd_plan_create(ngrtd_plan** out, int32_t L, int32_t nseries, c
 extern "C" int ngrtd_plan_destroy(ngrtd_plan* P) {
     if (!P) return NGRTD_OK;
     cudaFree(P->dXf); cudaFree(P->dXd); cudaFree(P->ditp); cudaFree(P->dxraw); cudaFree(P->dxrawd);
-    cudaFree(P->dtbl); cudaFree(P->dcounter);
+    cudaFree(P->dtbl);
     cudaFree(P->w_theta); cudaFree(P->w_out); cudaFree(P->w_logp); cudaFree(P->w_nu);
     if (P->hstream) cudaStreamDestroy(P->hstream);
     if (P->hstream2) cudaStreamDestroy(P->hstream2);
