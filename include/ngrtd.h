@@ -139,6 +139,17 @@ int ngrtd_ce_host(int32_t what, int32_t ngas, const int32_t* gases, const double
 int ngrtd_ce_wrapper_dev(int32_t ngas, const int32_t* gases, const double* theta_d, int64_t B, double* out_d,
                          void* stream);
 
+/* ---- CFC-11/12/113 and SF6 solubility + closed-system excess-air corrections: cfc_ce_corr / sf6_ce_corr of
+ *      utils/cfc_utils.py:25-152,160-306 (batch callers: age_modeling_mcmc.prep.py:242-303).
+ *  species: HOST int32[nspecies] with values 11, 12, 113 (CFCs) or 6 (SF6)
+ *  what: 0 = equil_air_conc_*(C_meas), 1 = equil_aq_conc_*(z_i), 2 = ce_exc_conc_*(z_i), 3 = solubility_*()
+ *  E, T, Ae (ccSTP/g, as passed to the constructors), F: [B];  X: [B, nspecies] C_meas or z_i;  S = salinity      */
+int ngrtd_cfc_dev(int32_t what, int32_t nspecies, const int32_t* species, const double* E_d, const double* T_d,
+                  const double* Ae_d, const double* F_d, const double* X_d, double S, int64_t B, double* out_d,
+                  void* stream);
+int ngrtd_cfc_host(int32_t what, int32_t nspecies, const int32_t* species, const double* E_h, const double* T_h,
+                   const double* Ae_h, const double* F_h, const double* X_h, double S, int64_t B, double* out_h);
+
 /* ---- stand-alone log-likelihood over model outputs mu[B, T] (pymc3 Normal / StudentT logp). */
 int ngrtd_loglik_dev(int32_t lik_kind, int32_t T, const double* mu_d, const double* obs_mu, const double* obs_sd,
                      const double* nu_d, int64_t B, double* logp_d, void* stream);

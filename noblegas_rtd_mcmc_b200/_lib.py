@@ -73,6 +73,8 @@ _PROTOS = {
     "ngrtd_ce_host": ([_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _vp], ctypes.c_int),
     "ngrtd_ce_wrapper_dev": ([_i32, _vp, _vp, _i64, _vp, _vp], ctypes.c_int),
     "ngrtd_loglik_dev": ([_i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp], ctypes.c_int),
+    "ngrtd_cfc_dev": ([_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _vp, _vp], ctypes.c_int),
+    "ngrtd_cfc_host": ([_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _vp], ctypes.c_int),
     "ngrtd_sampler_create": ([ctypes.POINTER(_vp), ctypes.POINTER(SamplerCfg), _vp, _i64, _vp, _i32], ctypes.c_int),
     "ngrtd_sampler_destroy": ([_vp], ctypes.c_int),
     "ngrtd_sampler_set_obs_groups": ([_vp, _vp, _vp, _i64, _i64], ctypes.c_int),

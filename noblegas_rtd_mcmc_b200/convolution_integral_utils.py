@@ -83,7 +83,7 @@ class tracer_conv_integral():
     def _col(x, B, default=0.0):
         if x is None or x is False:
             x = default
-        return np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), (B,)))
+        return np.array(np.broadcast_to(np.asarray(x, dtype=np.float64), (B,)), dtype=np.float64)   # writable copy
 
     # ---- :155-281
     def gen_g_tp(self):

@@ -681,6 +681,61 @@ extern "C" int ngrtd_ce_host(int32_t what, int32_t ngas, const int32_t* gases, c
     return rc;
 }
 
+// ------------------------------------------------------------------------------------------- CFC / SF6 corrections
+extern "C" int ngrtd_cfc_dev(int32_t what, int32_t nspecies, const int32_t* species, const double* E_d, const double* T_d,
+                             const double* Ae_d, const double* F_d, const double* X_d, double S, int64_t B, double* out_d,
+                             void* stream) {
+    if (nspecies < 1 || nspecies > 4 || !species) return fail(NGRTD_EINVAL, "cfc: nspecies must be in 1..4");
+    SpeciesList sl;
+    sl.n = nspecies;
+    for (int i = 0; i < nspecies; i++) {
+        if (species[i] != 11 && species[i] != 12 && species[i] != 113 && species[i] != 6)
+            return fail(NGRTD_EINVAL, "cfc: species must be 11, 12, 113 (CFCs) or 6 (SF6)");
+        sl.id[i] = species[i];
+    }
+    if (what < 0 || what > 3) return fail(NGRTD_EINVAL, "cfc: unknown output selector");
+    if (!T_d || !out_d) return fail(NGRTD_EINVAL, "cfc: T / out is null");
+    if (what != 3 && (!E_d || !X_d)) return fail(NGRTD_EINVAL, "cfc: E and the concentration / mixing-ratio input are required");
+    if ((what == 0 || what == 2) && (!Ae_d || !F_d)) return fail(NGRTD_EINVAL, "cfc: excess-air corrections need Ae and F");
+    if (B <= 0) return B == 0 ? NGRTD_OK : fail(NGRTD_EINVAL, "B < 0");
+    unsigned grid = (unsigned)((B + 127) / 128);
+    k_cfc<<<grid, 128, 0, (cudaStream_t)stream>>>(what, sl, E_d, T_d, Ae_d, F_d, X_d, S, B, out_d);
+    CUDA_TRY(cudaGetLastError());
+    return NGRTD_OK;
+}
+
+extern "C" int ngrtd_cfc_host(int32_t what, int32_t nspecies, const int32_t* species, const double* E_h, const double* T_h,
+                              const double* Ae_h, const double* F_h, const double* X_h, double S, int64_t B, double* out_h) {
+    if (B <= 0) return B == 0 ? NGRTD_OK : fail(NGRTD_EINVAL, "B < 0");
+    if (!T_h || !out_h) return fail(NGRTD_EINVAL, "cfc: T / out is null");
+    if (nspecies < 1 || nspecies > 4) return fail(NGRTD_EINVAL, "cfc: nspecies must be in 1..4");
+    const size_t n = (size_t)B, ns = (size_t)nspecies;
+    double* buf = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&buf, (4 + 2 * ns) * n * sizeof(double)));
+    const double* src[4] = {E_h, T_h, Ae_h, F_h};
+    double* dev[4];
+    for (int i = 0; i < 4; i++) {
+        dev[i] = src[i] ? buf + i * n : nullptr;
+        if (src[i]) {
+            cudaError_t e = cudaMemcpy(dev[i], src[i], n * sizeof(double), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { cudaFree(buf); return fail(NGRTD_ECUDA, cudaGetErrorString(e)); }
+        }
+    }
+    double* dX = X_h ? buf + 4 * n : nullptr;
+    if (X_h) {
+        cudaError_t e = cudaMemcpy(dX, X_h, ns * n * sizeof(double), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(buf); return fail(NGRTD_ECUDA, cudaGetErrorString(e)); }
+    }
+    double* dout = buf + (4 + ns) * n;
+    int rc = ngrtd_cfc_dev(what, nspecies, species, dev[0], dev[1], dev[2], dev[3], dX, S, B, dout, nullptr);
+    if (rc == NGRTD_OK) {
+        cudaError_t e = cudaMemcpy(out_h, dout, ns * n * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(NGRTD_ECUDA, cudaGetErrorString(e));
+    }
+    cudaFree(buf);
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------------- stand-alone loglik
 struct ObsPar { int T; double obs[16]; double isd[16]; double lc[16]; };
 

@@ -95,4 +95,63 @@ __global__ void k_ce_wrapper(GasList gl, const double* __restrict__ theta, long 
     for (int g = 0; g < gl.n; g++) out[i * gl.n + g] = ce_eval(0, gl.id[g], e, t, ae, f, p, 0.0);
 }
 
+// ---------------------------------------------------------------- CFC / SF6 solubility and excess-air corrections
+// Restates utils/cfc_utils.py (cfc_ce_corr :25-152, sf6_ce_corr :160-306): the batch callers are the 50,000-draw
+// observation-ensemble loops of age_modeling_mcmc.prep.py:242-303.  species: 11, 12, 113 (CFCs), 6 (SF6).
+__device__ __forceinline__ double cfc_solubility(int sp, double T, double S) {      // :62-83, :196-209  [mol atm^-1 kg^-1]
+    double a1, a2, a3, b1, b2, b3;
+    switch (sp) {
+        case 11: a1 = -136.2685; a2 = 206.1150; a3 = 57.2805; b1 = -.148598; b2 = 0.095114; b3 = -0.0163396; break;
+        case 12: a1 = -124.4395; a2 = 185.4299; a3 = 51.6383; b1 = -0.149779; b2 = 0.094668; b3 = -0.0160043; break;
+        case 113: a1 = -136.129; a2 = 206.475; a3 = 55.8957; b1 = -0.02754; b2 = 0.006033; b3 = 0.0; break;
+        default: a1 = -98.7264000; a2 = 142.803; a3 = 38.8746; b1 = 0.0268696; b2 = -0.0334407; b3 = 0.0070843; break;
+    }
+    double T_k = T + 273.15;
+    double th = T_k / 100;
+    return exp(a1 + a2 * (100 / T_k) + a3 * log(T_k / 100) + S * (b1 + b2 * th + b3 * (th * th)));
+}
+__device__ __forceinline__ double cfc_vapor_pressure_atm(double T) {                 // :35-52
+    return ce_vapor_pressure(T) / 0.000101325;
+}
+__device__ __forceinline__ double cfc_lapse_rate_atm(double E) { return pow(1.0 - .0065 * E / 288.15, 5.2561); }   // :54-60
+
+struct SpeciesList { int n; int id[4]; };
+
+// what: 0 equil_air_conc (measured aqueous -> atmospheric mixing ratio, :85-105 / :228-247),
+//       1 equil_aq_conc  (mixing ratio -> aqueous, :107-124 / :262-278), 2 ce_exc_conc (:126-143 / :280-296), 3 solubility
+// Ae is the constructor argument in ccSTP/g (the classes multiply by 1000 themselves, :29 / :164).
+__global__ void k_cfc(int what, SpeciesList sl, const double* __restrict__ E, const double* __restrict__ T,
+                      const double* __restrict__ Ae_, const double* __restrict__ F_, const double* __restrict__ X, double S,
+                      long long B, double* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const double t = T[i], e = E ? E[i] : 0.0;
+    const double Ae = Ae_ ? Ae_[i] * 1000. : 0.0, F = F_ ? F_[i] : 0.0;
+    const double P = cfc_lapse_rate_atm(e), Pv = cfc_vapor_pressure_atm(t);
+    const double P_da = P - Pv;
+    for (int k = 0; k < sl.n; k++) {
+        const int sp = sl.id[k];
+        const bool sf6 = sp == 6;
+        const double Ki = cfc_solubility(sp, t, S);
+        const double x = X ? X[i * sl.n + k] : 0.0;
+        double v;
+        if (what == 3) {
+            v = Ki;
+        } else if (what == 0) {
+            const double molar_volume = 22414.1;
+            v = (x + ((x * F * (Ae / molar_volume)) / (Ki * P_da))) / (Ki * P_da + (Ae / molar_volume));
+            if (sf6) v = v * 0.001;
+        } else if (what == 1) {
+            v = Ki * x * P_da;
+            if (sf6) v = v / 0.001;
+        } else {
+            double C_eq = Ki * x * (P - Pv);
+            double A = Ae / 22414 / 1e-12;
+            v = ((1 - F) * A * (x * 1e-12)) / (1 + F * A * ((x * 1e-12 / C_eq)));
+            if (sf6) v = 1000 * v;
+        }
+        out[i * sl.n + k] = v;
+    }
+}
+
 }  // namespace ngrtd

@@ -208,6 +208,22 @@ def main():
             Pv[i], Pl[i] = o.vapor_pressure(), o.lapse_rate()
     np.savez_compressed(os.path.join(GOLD, "ce_model.npz"), E=E, T=T, Ae=Ae, F=F, P_vapor=Pv, P_lapse=Pl,
                         J_flux=np.array(ngu.J_flux(1, 2700, 1000, 3.7, 10.2, 0.05)), **res)
+    # ---- CFC / SF6 corrections (utils/cfc_utils.py), SURVEY 8f-2 ----
+    import cfc_utils as ref_cfc
+    n = 120
+    E = rng.uniform(2700.0, 3300.0, n); T = rng.uniform(0.1, 12.0, n); Ae = 10 ** rng.uniform(-4, -1, n); F = 10 ** rng.uniform(-1, 0.5, n)
+    Cm = rng.uniform(0.2, 5.0, (n, 3)); zi = rng.uniform(50.0, 550.0, (n, 3)); Cs = rng.uniform(0.1, 3.0, n); zs = rng.uniform(1.0, 11.0, n)
+    r = {k: np.empty((n, 3)) for k in ("cfc_air", "cfc_aq", "cfc_exc", "cfc_K")}
+    q = {k: np.empty(n) for k in ("sf6_air", "sf6_aq", "sf6_exc", "sf6_K")}
+    for i in range(n):
+        c = ref_cfc.cfc_ce_corr(cfc_num=[11, 12, 113], E=E[i], T=T[i], Ae=Ae[i], F=F[i])
+        r["cfc_K"][i] = c.solubility_cfc(); r["cfc_air"][i] = c.equil_air_conc_cfc(Cm[i]); r["cfc_aq"][i] = c.equil_aq_conc_cfc(zi[i])
+        r["cfc_exc"][i] = c.ce_exc_conc_cfc(zi[i])
+        s6 = ref_cfc.sf6_ce_corr(E=E[i], T=T[i], Ae=Ae[i], F=F[i])
+        q["sf6_K"][i] = s6.solubility_sf6(); q["sf6_air"][i] = s6.equil_air_conc_sf6(Cs[i]); q["sf6_aq"][i] = s6.equil_aq_conc_sf6(zs[i])
+        q["sf6_exc"][i] = s6.ce_exc_conc_sf6(zs[i])
+    np.savez_compressed(os.path.join(GOLD, "cfc_model.npz"), E=E, T=T, Ae=Ae, F=F, Cm=Cm, zi=zi, Cs=Cs, zs=zs, **r, **q)
+
     # ---- posterior known-answer fixture for config 1 (the only posterior summaries the reference ships) ----
     import csv
     import json

@@ -181,3 +181,27 @@ def test_ng_parse_he_comps_batched():
     s = ng_parse(obs, 0.01, 0.5, 3000.0, 3.5)
     s.He_comps(2.0e-8)
     assert isinstance(s.obs_dict_["He4_ter"], float)
+
+
+def test_cfc_sf6_dropin_golden():
+    """cfc_ce_corr / sf6_ce_corr drop-ins (batched and scalar) against the untouched reference."""
+    from helpers import GOLD, rel_err
+    from noblegas_rtd_mcmc_b200.cfc_utils import cfc_ce_corr, sf6_ce_corr
+    z = np.load(os.path.join(GOLD, "cfc_model.npz"))
+    E, T, Ae, F = z["E"], z["T"], z["Ae"], z["F"]
+    c = cfc_ce_corr(cfc_num=[11, 12, 113], E=E, T=T, Ae=Ae, F=F)
+    assert rel_err(c.solubility_cfc(), z["cfc_K"]) < 1e-12
+    assert rel_err(c.equil_air_conc_cfc(z["Cm"]), z["cfc_air"]) < 1e-12
+    assert rel_err(c.equil_aq_conc_cfc(z["zi"]), z["cfc_aq"]) < 1e-12
+    assert rel_err(c.ce_exc_conc_cfc(z["zi"]), z["cfc_exc"]) < 1e-12
+    s6 = sf6_ce_corr(E=E, T=T, Ae=Ae, F=F)
+    assert rel_err(s6.solubility_sf6(), z["sf6_K"]) < 1e-12
+    assert rel_err(s6.equil_air_conc_sf6(z["Cs"]), z["sf6_air"]) < 1e-12
+    assert rel_err(s6.equil_aq_conc_sf6(z["zs"]), z["sf6_aq"]) < 1e-12
+    assert rel_err(s6.ce_exc_conc_sf6(z["zs"]), z["sf6_exc"]) < 1e-12
+    one = cfc_ce_corr(cfc_num=[11, 12, 113], E=float(E[3]), T=float(T[3]), Ae=float(Ae[3]), F=float(F[3]))
+    assert one.equil_air_conc_cfc(z["Cm"][3]).shape == (3,) and rel_err(one.equil_air_conc_cfc(z["Cm"][3]), z["cfc_air"][3]) < 1e-12
+    v = sf6_ce_corr(E=float(E[3]), T=float(T[3]), Ae=float(Ae[3]), F=float(F[3])).equil_air_conc_sf6(float(z["Cs"][3]))
+    assert isinstance(v, float) and abs(v - z["sf6_air"][3]) < 1e-12 * abs(v)
+    with pytest.raises(ValueError):
+        cfc_ce_corr(cfc_num=[13], E=1.0, T=1.0, Ae=0.1, F=0.1)

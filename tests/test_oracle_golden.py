@@ -220,3 +220,14 @@ def test_c_oracle_ce_and_loglik():
     obs = np.array([1.1, 0.7, 1.3, 0.9]); sd = np.array([0.1, 0.2, 0.05, 0.3]); nu = rng.uniform(1.0, 30.0, 50)
     assert np.allclose(c_oracle.loglik("normal", mu, obs, sd), O.logp_normal(obs, mu, sd), rtol=1e-13)
     assert np.allclose(c_oracle.loglik("studentt", mu, obs, sd, nu), O.logp_studentt(obs, mu, sd, nu), rtol=1e-12)
+
+
+def test_cfc_sf6_corrections_golden():
+    """utils/cfc_utils.py: numpy restatement vs the untouched reference."""
+    z = np.load(os.path.join(GOLD, "cfc_model.npz"))
+    E, T, Ae, F = z["E"], z["T"], z["Ae"], z["F"]
+    for what, key, X in (("K", "cfc_K", None), ("air", "cfc_air", z["Cm"]), ("aq", "cfc_aq", z["zi"]), ("exc", "cfc_exc", z["zi"])):
+        assert rel_err(O.cfc_corr(what, [11, 12, 113], E, T, Ae, F, X), z[key]) < 1e-13, key
+    for what, key, X in (("K", "sf6_K", None), ("air", "sf6_air", z["Cs"]), ("aq", "sf6_aq", z["zs"]), ("exc", "sf6_exc", z["zs"])):
+        Xa = None if X is None else X.reshape(-1, 1)
+        assert rel_err(O.cfc_corr(what, [6], E, T, Ae, F, Xa)[:, 0], z[key]) < 1e-13, key
