@@ -119,6 +119,11 @@ int ngrtd_forward_loglik_host(ngrtd_plan* plan, const double* theta_h, int64_t B
  *      one model, parameters tau/eta/D [B] (eta, D may be NULL when unused).                        */
 int ngrtd_rtd_weights_dev(int32_t mod_type, int32_t L, double dtp, const double* tau_d, const double* eta_d,
                           const double* D_d, int64_t B, double* g_d, void* stream);
+/* ---- 'frac_inf_diff' RTD: frac_rtd_numba_disp (conv utils :36-63, numba in the reference) + gen_g_tp post-processing
+ *      (:238-270).  tau, D, bbar, Phi_im: [B] (B <= 65,535); g: [B, L] normalised weights; fm_mu: [B] mean travel time
+ *      (the reference's `FM_mu` attribute) or NULL.  Feed g to ngrtd_convolve_g_dev for the concentration.              */
+int ngrtd_rtd_weights_fdm_dev(int32_t L, double dtp, const double* tau_d, const double* D_d, const double* bbar_d,
+                              const double* phi_d, int64_t B, double* g_d, double* fm_mu_d, void* stream);
 /* ---- tracer_conv_integral.convolve(g_tau=...) tail (:305-340): decay/ingrowth + input assembly + dot
  *      for externally supplied weights g[B, L]; series [L] newest-first, lag_index [L] or NULL.      */
 int ngrtd_convolve_g_dev(int32_t L, double dtp, const double* g_d, int64_t B, const double* series_d,

@@ -3,8 +3,10 @@ B200 through libngrtd.so.  Same names, kwargs and mutating-attribute behaviour a
 (utils/convolution_integral_utils.py:105-340); additive behaviour: array-valued tau/eta/D/J/lamba of shape [B]
 give batched results of shape [B].
 
-Not provided ("next"): the fracture/matrix-diffusion models 'frac_inf_diff[.mint]'
-(:199-266) and the dead 'SF6' accumulation branch (:330-331, J_sf6 is never set by any caller).
+'frac_inf_diff' (fracture / matrix diffusion with a dispersion advective RTD, :36-63,238-266) is evaluated by a
+dedicated quadrature kernel and convolved through the external-weights path.  Not provided: 'frac_inf_diff.mint'
+(an older pure-Python duplicate that prints on every call, :199-235), the external advective RTD `f_tadv_ext`
+(:66-97) and the dead 'SF6' accumulation branch (:330-331, J_sf6 is never set by any caller).
 """
 import numpy as np
 
@@ -60,9 +62,13 @@ class tracer_conv_integral():
 
     # ------------------------------------------------------------------ helpers
     def _check_model(self):
+        if self.mod_type == "frac_inf_diff":
+            if getattr(self, "f_tadv_ext", None) is not None:
+                raise NotImplementedError("frac_inf_diff with an external advective RTD (f_tadv_ext) is not provided")
+            return
         if self.mod_type not in _MODS:
-            if self.mod_type in ("frac_inf_diff", "frac_inf_diff.mint"):
-                raise NotImplementedError("mod_type %r is outside the B200 hot path (SURVEY.md 8f)" % self.mod_type)
+            if self.mod_type == "frac_inf_diff.mint":
+                raise NotImplementedError("mod_type 'frac_inf_diff.mint' is a superseded duplicate; use 'frac_inf_diff'")
             raise ValueError("unknown mod_type %r (known: %s)" % (self.mod_type, ", ".join(_MODS)))
 
     def _grid(self):
@@ -96,6 +102,17 @@ class tracer_conv_integral():
         tp[0] += 1e-5
         tp += dtp
         self.tau_list = tp.copy()
+        if self.mod_type == "frac_inf_diff":
+            B, scalar = self._batch(self.tau, self.D, self.bbar, self.Phi_im)
+            dev = torch.device("cuda")
+            t = [torch.from_numpy(self._col(v, B)).to(dev) for v in (self.tau, self.D, self.bbar, self.Phi_im)]
+            g = torch.empty((B, L), dtype=torch.float64, device=dev)
+            mu = torch.empty(B, dtype=torch.float64, device=dev)
+            _lib.check(_lib.lib.ngrtd_rtd_weights_fdm_dev(L, dtp, _lib.dptr(t[0]), _lib.dptr(t[1]), _lib.dptr(t[2]), _lib.dptr(t[3]),
+                                                          B, _lib.dptr(g), _lib.dptr(mu), _lib.stream_ptr()))
+            out, m = g.cpu().numpy(), mu.cpu().numpy()
+            self.FM_mu = float(m[0]) if scalar else m          # mean travel time (:264-265)
+            return out[0] if scalar else out
         B, scalar = self._batch(self.tau, self.eta, self.D)
         dev = torch.device("cuda")
         tau = torch.from_numpy(self._col(self.tau, B)).to(dev)
@@ -118,6 +135,8 @@ class tracer_conv_integral():
         g_tau = kwargs.get('g_tau', None)
         vals, idx, dtp = self._grid()
         L = len(vals)
+        if g_tau is None and self.mod_type == "frac_inf_diff":
+            g_tau = self.gen_g_tp()                             # weights by quadrature, then the external-weights path
         if g_tau is not None:
             return self._convolve_external(np.asarray(g_tau, dtype=np.float64), vals, idx, dtp)
         lam = getattr(self, "lamba", 0.0)

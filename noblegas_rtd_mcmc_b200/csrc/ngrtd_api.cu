@@ -572,6 +572,103 @@ extern "C" int ngrtd_rtd_weights_dev(int32_t mod_type, int32_t L, double dtp, co
     return NGRTD_OK;
 }
 
+// ---- fracture / matrix-diffusion RTD ('frac_inf_diff'): frac_rtd_numba_disp (conv utils :36-63, the only
+// numba-compiled code of the reference) + the post-processing of gen_g_tp (:238-270).  One CTA per (chain, lag)
+// evaluates the 1000-point log-spaced inner quadrature: advective dispersion RTD x matrix-diffusion retention kernel,
+// the retention kernel normalised by its own trapezoid integral (:59).  ~200 FP64 instructions per quadrature point.
+constexpr int FDM_NQ = 1000;
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(128) k_fdm_lag(int L, double dtp, const double* __restrict__ tau_, const double* __restrict__ D_,
+                                                 const double* __restrict__ bbar_, const double* __restrict__ phi_,
+                                                 double* __restrict__ f) {
+    __shared__ double tadv_s[FDM_NQ], tret_s[FDM_NQ], fret_s[FDM_NQ], fadv_s[FDM_NQ];
+    __shared__ double red[4];
+    const int i = blockIdx.x;
+    const long long b = blockIdx.y;
+    if (i == 0) {                                    // f_t_tran[0] = 0 (:256)
+        if (threadIdx.x == 0) f[b * (long long)L] = 0.0;
+        return;
+    }
+    const double tau = tau_[b], D = D_[b], bbar = bbar_[b], phi = phi_[b];
+    const double D_o = (2.3e-9) * 60 * 60 * 24 * 365;                        // :244
+    const double kappa = phi * sqrt((D_o * (phi * phi)) * 1);                // :247
+    const double T = (double)i + dtp;
+    const double hi = log10(T - 1.e-6);
+    const double step = (hi - (-6.0)) / (double)(FDM_NQ - 1);                // np.logspace -> linspace step
+    for (int m = threadIdx.x; m < FDM_NQ; m += blockDim.x) {
+        double y = (m < FDM_NQ - 1) ? __dadd_rn(__dmul_rn((double)m, step), -6.0) : hi;
+        double tadv = exp10(y);
+        double x = tadv / tau;
+        double om = 1. - x;
+        double fadv = ((1. / tau) / (sqrt(4. * 3.14159265358979323846 * D * x))) * (1. / x) * exp(-1. * ((om * om) / (4. * D * x)));   // :34
+        double tret = T - tadv;
+        double Beta = tadv / bbar;
+        double fret = (kappa * Beta) / (2 * sqrt(3.14159265358979323846) * pow(tret, 1.5)) *
+                      exp((-1 * (kappa * kappa) * (Beta * Beta)) / (4 * tret));                                                        // :58
+        tadv_s[m] = tadv; tret_s[m] = tret; fret_s[m] = fret; fadv_s[m] = fadv;
+    }
+    __syncthreads();
+    double part = 0.0;
+    for (int m = threadIdx.x; m < FDM_NQ - 1; m += blockDim.x) part += (tret_s[m] - tret_s[m + 1]) * (fret_s[m + 1] + fret_s[m]);
+    const double N = 0.5 * block_sum(part, red);                             // _trapz(f_ret[::-1], t_ret[::-1])  (:59)
+    part = 0.0;
+    for (int m = threadIdx.x; m < FDM_NQ - 1; m += blockDim.x) {
+        double a0 = (fret_s[m] / N) * fadv_s[m], a1 = (fret_s[m + 1] / N) * fadv_s[m + 1];
+        part += (tadv_s[m + 1] - tadv_s[m]) * (a1 + a0);
+    }
+    const double I = 0.5 * block_sum(part, red);                             // _trapz(f_i, tadv)  (:62)
+    if (threadIdx.x == 0) f[b * (long long)L + i] = I;
+}
+
+// normalise by trapz over tp_ (tp_[0] = 0), mean travel time, then g / g.sum()  (:256-270)
+__global__ void __launch_bounds__(256) k_fdm_post(int L, double dtp, double* __restrict__ g, double* __restrict__ fm_mu) {
+    __shared__ double red[8];
+    const long long b = blockIdx.x;
+    double* row = g + b * (long long)L;
+    auto tpv = [&](int k) { return k == 0 ? 0.0 : (double)k + dtp; };
+    double p0 = 0.0, p1 = 0.0, ps = 0.0;
+    for (int k = threadIdx.x; k < L - 1; k += blockDim.x) {
+        double dx = tpv(k + 1) - tpv(k);
+        p0 += dx * (row[k + 1] + row[k]);
+    }
+    const double nrm = 0.5 * block_sum(p0, red);
+    p0 = 0.0;
+    for (int k = threadIdx.x; k < L - 1; k += blockDim.x) {
+        double dx = tpv(k + 1) - tpv(k);
+        double f0 = row[k] / nrm, f1 = row[k + 1] / nrm;
+        p0 += dx * (f1 + f0);
+        p1 += dx * (f1 * tpv(k + 1) + f0 * tpv(k));
+    }
+    for (int k = threadIdx.x; k < L; k += blockDim.x) ps += row[k] / nrm;
+    const double t0 = block_sum(p0, red), t1 = block_sum(p1, red), S = block_sum(ps, red);
+    if (threadIdx.x == 0 && fm_mu) fm_mu[b] = t1 / t0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < L; k += blockDim.x) row[k] = (row[k] / nrm) / S;
+}
+
+extern "C" int ngrtd_rtd_weights_fdm_dev(int32_t L, double dtp, const double* tau_d, const double* D_d, const double* bbar_d,
+                                         const double* phi_d, int64_t B, double* g_d, double* fm_mu_d, void* stream) {
+    if (L < 2 || !tau_d || !D_d || !bbar_d || !phi_d || !g_d) return fail(NGRTD_EINVAL, "rtd_weights_fdm: bad arguments");
+    if (B <= 0) return B == 0 ? NGRTD_OK : fail(NGRTD_EINVAL, "B < 0");
+    if (B > 65535) return fail(NGRTD_EINVAL, "rtd_weights_fdm: at most 65,535 parameter sets per call");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_fdm_lag<<<dim3((unsigned)L, (unsigned)B), 128, 0, st>>>(L, dtp, tau_d, D_d, bbar_d, phi_d, g_d);
+    CUDA_TRY(cudaGetLastError());
+    k_fdm_post<<<(unsigned)B, 256, 0, st>>>(L, dtp, g_d, fm_mu_d);
+    CUDA_TRY(cudaGetLastError());
+    return NGRTD_OK;
+}
+
 // convolve(g_tau=g) tail: decay/ingrowth (:313-316), input assembly (:320-333), dot (:336-337); one CTA per row
 __global__ void k_convolve_g(int L, double dtp, const double* __restrict__ g, const double* __restrict__ series,
                              const double* __restrict__ lag_index, const double* __restrict__ lambda, int rad_accum,

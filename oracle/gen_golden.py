@@ -208,6 +208,21 @@ def main():
             Pv[i], Pl[i] = o.vapor_pressure(), o.lapse_rate()
     np.savez_compressed(os.path.join(GOLD, "ce_model.npz"), E=E, T=T, Ae=Ae, F=F, P_vapor=Pv, P_lapse=Pl,
                         J_flux=np.array(ngu.J_flux(1, 2700, 1000, 3.7, 10.2, 0.05)), **res)
+    # ---- fracture / matrix-diffusion RTD (numba-compiled in the reference), SURVEY 8f-4 ----
+    out = {}
+    c500 = C_in["CFC12"].iloc[-500:]
+    for key, kw in (("a", dict(tau=30.0, D=0.3, bbar=1e-3, Phi_im=0.02)), ("b", dict(tau=120.0, D=0.05, bbar=5e-4, Phi_im=0.05)),
+                    ("c", dict(tau=8.0, D=1.5, bbar=2e-3, Phi_im=0.01))):
+        m = conv.tracer_conv_integral(c500.copy(), c500.index[-1])
+        m.update_pars(mod_type="frac_inf_diff", t_half=25.0, **kw)
+        with np.errstate(all="ignore"):
+            out[key + "/g"] = m.gen_g_tp()
+            out[key + "/FM_mu"] = np.array(m.FM_mu)
+            out[key + "/C"] = np.array(m.convolve())
+        out[key + "/par"] = np.array([kw["tau"], kw["D"], kw["bbar"], kw["Phi_im"]])
+    out["c12_500"] = c500.to_numpy().ravel()[::-1].copy()
+    np.savez_compressed(os.path.join(GOLD, "fdm_weights.npz"), **out)
+
     # ---- CFC / SF6 corrections (utils/cfc_utils.py), SURVEY 8f-2 ----
     import cfc_utils as ref_cfc
     n = 120

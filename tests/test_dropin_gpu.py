@@ -205,3 +205,23 @@ def test_cfc_sf6_dropin_golden():
     assert isinstance(v, float) and abs(v - z["sf6_air"][3]) < 1e-12 * abs(v)
     with pytest.raises(ValueError):
         cfc_ce_corr(cfc_num=[13], E=1.0, T=1.0, Ae=0.1, F=0.1)
+
+
+def test_frac_inf_diff_dropin_golden():
+    """tracer_conv_integral(mod_type='frac_inf_diff') on the GPU vs the reference's numba implementation."""
+    from helpers import GOLD, rel_err
+    from noblegas_rtd_mcmc_b200.convolution_integral_utils import tracer_conv_integral
+    z = np.load(os.path.join(GOLD, "fdm_weights.npz"))
+    c12 = _df(z["c12_500"], "CFC12")
+    for k in "abc":
+        tau, D, bbar, phi = z[k + "/par"]
+        m = tracer_conv_integral(c12.copy(), c12.index[-1])
+        m.update_pars(mod_type="frac_inf_diff", t_half=25.0, tau=tau, D=D, bbar=bbar, Phi_im=phi)
+        g = m.gen_g_tp()
+        assert rel_err(g, z[k + "/g"]) < 1e-10, k
+        assert abs(m.FM_mu - float(z[k + "/FM_mu"])) < 1e-10 * m.FM_mu
+        assert abs(m.convolve() - float(z[k + "/C"])) < 1e-10 * abs(float(z[k + "/C"]))
+    m.tau = np.array([30.0, 120.0])                       # batched parameters
+    m.D, m.bbar, m.Phi_im = np.array([0.3, 0.05]), np.array([1e-3, 5e-4]), np.array([0.02, 0.05])
+    out = m.convolve()
+    assert out.shape == (2,) and abs(out[0] - float(z["a/C"])) < 1e-10 * out[0] and abs(out[1] - float(z["b/C"])) < 1e-10 * out[1]

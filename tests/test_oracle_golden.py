@@ -231,3 +231,18 @@ def test_cfc_sf6_corrections_golden():
     for what, key, X in (("K", "sf6_K", None), ("air", "sf6_air", z["Cs"]), ("aq", "sf6_aq", z["zs"]), ("exc", "sf6_exc", z["zs"])):
         Xa = None if X is None else X.reshape(-1, 1)
         assert rel_err(O.cfc_corr(what, [6], E, T, Ae, F, Xa)[:, 0], z[key]) < 1e-13, key
+
+
+def test_frac_inf_diff_weights_golden():
+    """the numba-compiled fracture / matrix-diffusion RTD of the reference vs the numpy restatement,
+    including the SURVEY known answer (CFC-12 newest 500 rows, tau=30, D=0.3, bbar=1e-3, Phi_im=0.02)."""
+    z = np.load(os.path.join(GOLD, "fdm_weights.npz"))
+    tp = O.lag_grid(500)
+    for k in "abc":
+        tau, D, bbar, phi = z[k + "/par"]
+        g, mu = O.frac_inf_diff_weights(tp, tau, D, bbar, phi)
+        assert rel_err(g, z[k + "/g"]) < 1e-12, k
+        assert abs(mu - float(z[k + "/FM_mu"])) < 1e-12 * mu
+        C = O.convolve(z["c12_500"], tp, g.reshape(1, -1), O.thalf_2_lambda(25.0))[0]
+        assert abs(C - float(z[k + "/C"])) < 1e-12 * abs(C)
+    assert abs(float(z["a/FM_mu"]) - 86.31699496976702) < 1e-11
