@@ -224,9 +224,13 @@ int ngrtd_sampler_run(ngrtd_sampler* s, int64_t nsteps, int32_t tune, int32_t re
                       void* stream);
 int ngrtd_sampler_stop_tuning(ngrtd_sampler* s);   /* DEMetropolisZ.stop_tuning: drop the oldest fraction of the history */
 /* what: 0 q [B,ndim] (transformed), 1 logp [B], 2 lamb [B], 3 scaling [B], 4 accepted count [B], 5 mean [B,ndim],
- *       6 M2 [B,ndim] (Welford, natural values) -- copied to out_d (device) on `stream` */
+ *       6 M2 [B,ndim] (Welford, natural values), 7 history ring [hist_cap,B,ndim], 8 accepted since the last tuning point [B]
+ *       -- copied to out_d (device) on `stream`.  Together with ngrtd_sampler_info these are the complete sampler state
+ *       (checkpoint; the reference only saves finished traces, run_age_mcmc_utils.py:425).                                 */
 int ngrtd_sampler_get(ngrtd_sampler* s, int32_t what, double* out_d, void* stream);
-int ngrtd_sampler_set(ngrtd_sampler* s, int32_t what, const double* in_d, void* stream);   /* what 0..3: checkpoint restore */
+/* restore: same selectors; setting q (0) re-evaluates logp unless logp (1) is set afterwards */
+int ngrtd_sampler_set(ngrtd_sampler* s, int32_t what, const double* in_d, void* stream);
+int ngrtd_sampler_set_counters(ngrtd_sampler* s, int64_t step, int64_t ndraws, int64_t hist_start);
 int ngrtd_sampler_info(const ngrtd_sampler* s, int64_t* step, int64_t* ndraws, int64_t* hist_start);
 int ngrtd_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);   /* known-answer hook */
 

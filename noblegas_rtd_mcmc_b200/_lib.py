@@ -83,6 +83,7 @@ _PROTOS = {
     "ngrtd_sampler_stop_tuning": ([_vp], ctypes.c_int),
     "ngrtd_sampler_get": ([_vp, _i32, _vp, _vp], ctypes.c_int),
     "ngrtd_sampler_set": ([_vp, _i32, _vp, _vp], ctypes.c_int),
+    "ngrtd_sampler_set_counters": ([_vp, _i64, _i64, _i64], ctypes.c_int),
     "ngrtd_sampler_info": ([_vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64), ctypes.POINTER(_i64)], ctypes.c_int),
     "ngrtd_philox4x32_10": ([_vp, _vp, _vp], ctypes.c_int),
 }

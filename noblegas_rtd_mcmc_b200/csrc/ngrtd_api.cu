@@ -1176,6 +1176,20 @@ extern "C" int ngrtd_sampler_info(const ngrtd_sampler* S, int64_t* step, int64_t
     return NGRTD_OK;
 }
 
+extern "C" int ngrtd_sampler_set_counters(ngrtd_sampler* S, int64_t step, int64_t ndraws, int64_t hist_start) {
+    if (!S) return fail(NGRTD_EINVAL, "null sampler");
+    if (step < 0 || ndraws < 0 || hist_start < 0 || hist_start > step) return fail(NGRTD_EINVAL, "sampler_set_counters: bad counters");
+    S->step = step;
+    S->ndraws = ndraws;
+    S->hist_start = hist_start;
+    return NGRTD_OK;
+}
+
+__global__ void k_double_to_int(const double* a, long long n, int* oi, long long* ol) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) { if (oi) oi[i] = (int)a[i]; else ol[i] = (long long)a[i]; }
+}
+
 __global__ void k_int_to_double(const int* a, const long long* b, long long n, double* out) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) out[i] = b ? (double)b[i] : (double)a[i];
@@ -1194,11 +1208,14 @@ extern "C" int ngrtd_sampler_get(ngrtd_sampler* S, int32_t what, double* out_d, 
         case 2: src = v.lamb; break;
         case 3: src = v.scal; break;
         case 4:
-            k_int_to_double<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(nullptr, v.acc_tot, (long long)B, out_d);
+        case 8:
+            k_int_to_double<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(what == 8 ? v.acc_win : nullptr,
+                                                                         what == 8 ? nullptr : v.acc_tot, (long long)B, out_d);
             CUDA_TRY(cudaGetLastError());
             return NGRTD_OK;
         case 5: src = v.wf_mean; n = S->n_q; break;
         case 6: src = v.wf_m2; n = S->n_q; break;
+        case 7: src = v.hist; n = (size_t)v.hist_cap * S->n_q; break;
         default: return fail(NGRTD_EINVAL, "sampler_get: unknown selector");
     }
     CUDA_TRY(cudaMemcpyAsync(out_d, src, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -1216,7 +1233,16 @@ extern "C" int ngrtd_sampler_set(ngrtd_sampler* S, int32_t what, const double* i
         case 1: dst = v.logp; break;
         case 2: dst = v.lamb; break;
         case 3: dst = v.scal; break;
-        default: return fail(NGRTD_EINVAL, "sampler_set: selector must be 0..3");
+        case 4:
+        case 8:
+            k_double_to_int<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in_d, (long long)n, what == 8 ? v.acc_win : nullptr,
+                                                                         what == 8 ? nullptr : v.acc_tot);
+            CUDA_TRY(cudaGetLastError());
+            return NGRTD_OK;
+        case 5: dst = v.wf_mean; n = S->n_q; break;
+        case 6: dst = v.wf_m2; n = S->n_q; break;
+        case 7: dst = v.hist; n = (size_t)v.hist_cap * S->n_q; break;
+        default: return fail(NGRTD_EINVAL, "sampler_set: unknown selector");
     }
     CUDA_TRY(cudaMemcpyAsync(dst, in_d, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (what == 0) {                 // new positions: refresh logp

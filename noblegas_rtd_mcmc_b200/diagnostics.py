@@ -124,3 +124,33 @@ def moments_summary(n, mean, m2):
     var_plus = (n - 1.0) / n * W + Bn
     return {"mean": mean.mean(axis=0), "sd": np.sqrt(var_plus), "r_hat": np.sqrt(var_plus / W),
             "ess": M * var_plus / Bn, "mcse_mean": np.sqrt(Bn / M), "chains": M, "draws_per_chain": n}
+
+
+def save_trace(path, posterior, sample_stats=None, attrs=None):
+    """Write a trace as `.npz` with the groups / variable names the reference stores through `az.to_netcdf`
+    (run_age_mcmc_utils.py:425, noble_gas_mcmc.py:288): `posterior/<var>` arrays shaped [chain, draw], optional
+    `sample_stats/<name>` and scalar `attrs/<name>` (e.g. sampling_time)."""
+    out = {}
+    for k, v in posterior.items():
+        a = np.asarray(v, dtype=np.float64)
+        if a.ndim != 2:
+            raise ValueError(f"posterior[{k!r}] must be [chain, draw], got shape {a.shape}")
+        out["posterior/" + k] = a
+    for k, v in (sample_stats or {}).items():
+        out["sample_stats/" + k] = np.asarray(v)
+    for k, v in (attrs or {}).items():
+        out["attrs/" + k] = np.asarray(v)
+    np.savez_compressed(path, **out)
+
+
+def load_trace(path):
+    """Inverse of `save_trace`: returns {"posterior": {...}, "sample_stats": {...}, "attrs": {...}}."""
+    tr = {"posterior": {}, "sample_stats": {}, "attrs": {}}
+    with np.load(path) as z:
+        for k in z.files:
+            grp, _, name = k.partition("/")
+            if grp not in tr or not name:
+                raise ValueError(f"{path}: unexpected entry {k!r}")
+            a = z[k]
+            tr[grp][name] = a.item() if grp == "attrs" and a.ndim == 0 else a
+    return tr

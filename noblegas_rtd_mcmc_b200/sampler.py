@@ -71,6 +71,7 @@ class Sampler(object):
             for i, g in enumerate(gases):
                 cfg.gases[i] = _lib.GAS[g[0:2]]
         self.plan = plan
+        self.hist_cap = int(hist_cap)
         self.nchains = int(nchains)
         self.ndim = cfg.ndim
         q0a = None if q0 is None else _lib.f64(q0)
@@ -115,12 +116,14 @@ class Sampler(object):
     def stop_tuning(self):
         _lib.check(_lib.lib.ngrtd_sampler_stop_tuning(self.handle))
 
-    _WHAT = {"q": 0, "logp": 1, "lamb": 2, "scaling": 3, "accepted": 4, "mean": 5, "m2": 6}
+    _WHAT = {"q": 0, "logp": 1, "lamb": 2, "scaling": 3, "accepted": 4, "mean": 5, "m2": 6, "history": 7, "accepted_window": 8}
 
     def get(self, what, stream=None):
         import torch
         w = self._WHAT[what]
         shape = (self.nchains, self.ndim) if w in (0, 5, 6) else (self.nchains,)
+        if w == 7:
+            shape = (self.hist_cap, self.nchains, self.ndim)
         out = torch.empty(shape, dtype=torch.float64, device=self.device)
         _lib.check(_lib.lib.ngrtd_sampler_get(self.handle, w, _lib.dptr(out), _lib.stream_ptr(stream)))
         return out
@@ -133,11 +136,23 @@ class Sampler(object):
         _lib.check(_lib.lib.ngrtd_sampler_info(self.handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return dict(step=a.value, ndraws=b.value, hist_start=c.value)
 
-    def state_dict(self):
-        """Checkpoint: positions, logp, tuning state and counters as host arrays."""
-        d = {k: self.get(k).cpu().numpy() for k in ("q", "logp", "lamb", "scaling", "accepted", "mean", "m2")}
+    def state_dict(self, history=True):
+        """Checkpoint: the complete sampler state as host arrays.  With the history ring the restored
+        sampler continues bit-identically; without it (smaller file) DE-MC-Z restarts from an empty history."""
+        keys = ["q", "logp", "lamb", "scaling", "accepted", "accepted_window", "mean", "m2"] + (["history"] if history else [])
+        d = {k: self.get(k).cpu().numpy() for k in keys}
         d.update(self.info())
         return d
+
+    def load_state_dict(self, d):
+        import torch
+        for k in ("q", "lamb", "scaling", "accepted", "accepted_window", "mean", "m2", "history", "logp"):   # logp after q
+            if k in d:
+                t = torch.from_numpy(np.ascontiguousarray(d[k], dtype=np.float64)).to(self.device)
+                self.set(k, t)
+        hist_start = d["hist_start"] if "history" in d else d["step"]
+        _lib.check(_lib.lib.ngrtd_sampler_set_counters(self.handle, int(d["step"]), int(d["ndraws"]), int(hist_start)))
+        torch.cuda.synchronize()
 
     def sample(self, tune, draws, thin=1, keep_trace=True, chunk=None):
         """mc.sample(tune=, draws=, discard_tuned_samples=True): tuning phase, stop_tuning, recorded draws.

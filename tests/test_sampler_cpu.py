@@ -128,3 +128,17 @@ def test_chain_stats_gather_gloo_world2():
         p.join(timeout=60)
     assert [r[1] for r in res] == [True, True]
     assert res[0][2] == res[1][2] and res[0][3] == 11
+
+
+def test_trace_npz_roundtrip(tmp_path):
+    from noblegas_rtd_mcmc_b200 import diagnostics as dg
+    rng = np.random.default_rng(3)
+    post = {"tau1": rng.normal(size=(4, 50)), "f1": rng.uniform(size=(4, 50))}
+    dg.save_trace(tmp_path / "t.npz", post, sample_stats={"accepted": rng.integers(0, 2, (4, 50))}, attrs={"sampling_time": 1.25})
+    tr = dg.load_trace(tmp_path / "t.npz")
+    assert set(tr["posterior"]) == {"tau1", "f1"} and tr["attrs"]["sampling_time"] == 1.25
+    for k in post:
+        assert np.array_equal(tr["posterior"][k], post[k])
+    assert np.allclose(dg.summary(tr["posterior"])["tau1"]["mean"], post["tau1"].mean())
+    with pytest.raises(ValueError):
+        dg.save_trace(tmp_path / "bad.npz", {"x": np.zeros(5)})

@@ -210,3 +210,43 @@ def test_observation_groups_config4():
         assert torch.equal(joint.get("q")[24 * g:24 * (g + 1)], solo.get("q")), g
     with pytest.raises(Exception):
         joint.set_obs_groups(obs, sd, 8)          # 48 chains would need 6 groups
+
+
+def test_checkpoint_resume_is_bit_identical(tmp_path):
+    """state_dict -> npz -> a NEW sampler -> continue: same trajectory, statistics and trace as an
+    uninterrupted run (both kernels)."""
+    import torch
+    from helpers import synth_plan
+    from noblegas_rtd_mcmc_b200 import synthetic
+    from noblegas_rtd_mcmc_b200.sampler import Sampler, prior
+    fx, mcmc_model = _ng_setup()
+    mdl = mcmc_model(fx["wells"]["PLM1"]["obs"], mcmc_model.well_elev["PLM1"])
+    kw = dict(plan=None, gases=mdl.gases, lik="studentt", nu_range=(1.0, 30.0), tune_interval=64, hist_cap=128, seed=21)
+    pn = list(synthetic.PAR_NAMES_CFG3)
+    plan, _, _ = synth_plan("exp_pist_flow", "dispersion", pn)
+    obs = plan.forward_host(np.array([[180.0, 1500.0, 0.6, 0.4, 1.8, 0.4, synthetic.LOG10_J_MONTHLY]]), pn)[0]
+    pri = [prior("uniform", "tau1", 12, 12000), prior("beta", "nu_", 2.0, 0.1), prior("normal", "J", synthetic.LOG10_J_MONTHLY, 0.33),
+           prior("uniform", "tau2", 600, 180000), prior("uniform", "f1", 0.01, 0.99), prior("uniform", "eta1", 1, 5),
+           prior("uniform", "D2", 0.01, 2.0)]
+    akw = dict(plan=plan, lik="studentt", nu_range=(5.0, 30.0), f2_from_f1=True, tune_interval=20, hist_cap=48, seed=4, scaling=0.01,
+               q0=[-3.0, 2.0, synthetic.LOG10_J_MONTHLY, -4.5, 0.3, -1.0, -1.2])
+    for make, n1, n2 in ((lambda: Sampler(mdl.build_priors(), mdl.obs_mu, mdl.obs_sd, 33, **kw), 150, 170),
+                         (lambda: Sampler(pri, obs, 0.05 * np.abs(obs), 19, **akw), 50, 45)):
+        a = make()
+        a.run(n1, tune=True)
+        a.stop_tuning()
+        a.run(n2, tune=False, record=True)
+        ta = a.run(30, tune=False, record=True, keep_trace=True)
+        b = make()
+        b.run(n1, tune=True)
+        b.stop_tuning()
+        b.run(n2 - 20, tune=False, record=True)
+        np.savez(tmp_path / "ckpt.npz", **b.state_dict())
+        c = make()
+        c.load_state_dict(dict(np.load(tmp_path / "ckpt.npz")))
+        assert c.info() == b.info()
+        c.run(20, tune=False, record=True)
+        tc = c.run(30, tune=False, record=True, keep_trace=True)
+        assert torch.equal(ta, tc)
+        for k in ("q", "logp", "lamb", "mean", "m2", "accepted"):
+            assert torch.equal(a.get(k), c.get(k)), k
