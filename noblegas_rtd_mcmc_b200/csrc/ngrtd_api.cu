@@ -92,13 +92,14 @@ extern "C" int ngrtd_plan_create(ngrtd_plan** out, int32_t L, int32_t nseries, c
     const int Lpad = P->Lpad;
 
     // lag grid exactly as the reference builds it: arange -> tp[0] += 1e-5 -> tp += dtp (conv utils :168-173)
-    std::vector<double> tp(Lpad, 0.0), p15(Lpad, 0.0), itp(Lpad, 0.0);
+    std::vector<double> tp(Lpad, 0.0), p15(Lpad, 0.0), itp(2 * (size_t)Lpad, 0.0);   // itp: {1/tp, tp} pairs
     for (int k = 0; k < L; k++) {
         double t = (double)k;
         if (k == 0) t += 1e-5;
         t += dtp;
         tp[k] = t;
-        itp[k] = 1.0 / t;
+        itp[2 * k] = 1.0 / t;
+        itp[2 * k + 1] = t;
         p15[k] = 1.0 / (t * std::sqrt(t));
     }
     // folded columns
@@ -296,7 +297,7 @@ static int launch_forward_t(ngrtd_plan* P, const SlotMap& sm, const double* thet
     if (warps > 4) warps &= ~3;
     size_t sh = (size_t)TBL_DOUBLES + 2 + (size_t)warps * NT * 8 * NCOL;
     sh += (size_t)lc_cap * NCOL;
-    if (WT::ANY_D) sh += (size_t)lc_cap * NCOL + lc_cap;
+    if (WT::ANY_D) sh += (size_t)lc_cap * NCOL + 2 * (size_t)lc_cap;
     if (DYN) sh += lc_cap + (WT::ANY_D ? lc_cap : 0);
     sh *= sizeof(double);
     auto kern = k_forward<C1, C2, DYN, NT, UA, MAXW>;
@@ -899,7 +900,7 @@ static int launch_mcmc_age(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st)
     size_t sh = 0;
     for (;;) {
         sh = (size_t)TBL_DOUBLES + 2 + (size_t)warps * NT * 8 * NCOL + (size_t)lc_cap * NCOL;
-        if (WT::ANY_D) sh += (size_t)lc_cap * NCOL + lc_cap;
+        if (WT::ANY_D) sh += (size_t)lc_cap * NCOL + 2 * (size_t)lc_cap;
         if (DYN) sh += lc_cap + (WT::ANY_D ? lc_cap : 0);
         sh += (size_t)warps * NT * 8 * CH_REC + (sizeof(PriorDev) * ND_MAX + 7) / 8;
         sh *= sizeof(double);

@@ -20,7 +20,7 @@ constexpr int LC_MAX = 1024;            // lags resident in shared memory per ch
 // N=128/deg 3: 2.8e-13.  Measured on cfg 3 (profiles/r1_notes.md): N=32/deg 4 72.5 cycles per tile-group, N=64/deg 3
 // 72.1, N=128/deg 3 70.5 (the extra bank conflicts of the 512-byte arrays cost less than the fourth DFMA): default N=128.
 #ifndef NGRTD_TBL_BITS
-#define NGRTD_TBL_BITS 7
+#define NGRTD_TBL_BITS 8
 #endif
 constexpr int TBL_BITS = NGRTD_TBL_BITS;
 constexpr int TBL_N = 1 << TBL_BITS;
@@ -39,9 +39,31 @@ constexpr double EXP_C0 = 0.9999999999955212, EXP_C1 = 0.010830424696239445, EXP
 constexpr int EXP_DEG = 3;
 constexpr double EXP_C0 = 0.9999999999997201, EXP_C1 = 0.005415212348124269, EXP_C2 = 1.4662271345222707e-05,
                  EXP_C3 = 2.64664311467397e-08, EXP_C4 = 0.0;
+#elif NGRTD_TBL_BITS == 8
+constexpr int EXP_DEG = 3;
+constexpr double EXP_C0 = 0.9999999999999825, EXP_C1 = 0.0027076061740622769, EXP_C2 = 3.6655661567589337e-06,
+                 EXP_C3 = 3.3083029837113949e-09, EXP_C4 = 0.0;
+#elif NGRTD_TBL_BITS == 9
+constexpr int EXP_DEG = 3;
+constexpr double EXP_C0 = 0.99999999999999891, EXP_C1 = 0.0013538030870311429, EXP_C2 = 9.1639143421807685e-07,
+                 EXP_C3 = 4.1353784454173436e-10, EXP_C4 = 0.0;
 #else
-#error "NGRTD_TBL_BITS must be 5, 6 or 7"
+#error "NGRTD_TBL_BITS must be 5..9"
 #endif
+// exp_scaled_bits: q(g) ~= exp((g - 1) ln2 / N) on g in [1, 2)  (tools/exp_poly_g.py: constants and error bounds)
+#if NGRTD_TBL_BITS == 7
+constexpr double EXQ_C0 = 0.99459942332194162, EXQ_C1 = 0.0053859675366433966, EXQ_C2 = 1.4582602945559778e-05,
+                 EXQ_C3 = 2.6538188920206277e-08;      // max rel err 2.8e-13
+#elif NGRTD_TBL_BITS == 8
+constexpr double EXQ_C0 = 0.99729605607536986, EXQ_C1 = 0.0027002849873872833, EXQ_C2 = 3.6556244405132574e-06,
+                 EXQ_C3 = 3.3127848075725495e-09;      // 1.8e-14
+#elif NGRTD_TBL_BITS == 9
+constexpr double EXQ_C0 = 0.99864711289033903, EXQ_C1 = 0.0013519715460713645, EXQ_C2 = 9.1514977059835842e-07,
+                 EXQ_C3 = 4.1381786370901806e-10;      // 1.2e-15
+#else
+constexpr double EXQ_C0 = 0, EXQ_C1 = 0, EXQ_C2 = 0, EXQ_C3 = 0;
+#endif
+constexpr double FX_MAGIC = 1572864.0;               // 1.5 * 2^20: ulp 2^-32, integer part biased by 2^19
 constexpr int EXP_NMIN = -1022 * TBL_N;             // below 2^-1022: clamp (see DESIGN.md "underflow")
 
 enum Cls : int { CLS_NONE = 0, CLS_P = 1, CLS_G = 2, CLS_D = 3 };
@@ -67,7 +89,7 @@ struct PlanView {
     double dtp;     // integer-valued shift of the lag grid
     const double* Xf;     // [Lpad, 8] folded columns
     const double* Xd;     // [Lpad, 8] Xf * tp^-1.5 (dispersion component)
-    const double* itp;    // [Lpad] 1/tp (pad: 0)
+    const double* itp;    // [Lpad][2] {1/tp, tp} (pad: 0, 0)
     const double* xraw;   // [Lpad] raw series of the per-chain-lambda tracer
     const double* xrawd;  // [Lpad] xraw * tp^-1.5
     const double* tbl;    // [TBL_N] doubles = hi[TBL_N], lo[TBL_N] words of 2^(j/TBL_N)
@@ -141,6 +163,36 @@ __device__ __forceinline__ double exp_scaled(double ep, const double* __restrict
     int hi = (int)*reinterpret_cast<const unsigned int*>(tb + off) + nc * (1 << (20 - TBL_BITS));
     int lo = (int)*reinterpret_cast<const unsigned int*>(tb + off + TBL_N * 4);
     return __hiloint2double(hi, lo) * p;
+}
+
+// Conversion-free variant used by the dispersion lag loop.  t = ep + FX_MAGIC; the addition is folded into the caller's
+// FMA chain (cp + FX_MAGIC is a per-chain constant), so it costs nothing.  With 2^20 <= t < 2^21 the mantissa of t IS ep
+// in fixed point: high word bits 0..19 = floor(ep) + 2^19, low word = the 32-bit fraction F of ep.
+//   * table slot / exponent insertion come from the high word on the integer pipes (the 2^19 bias and the exponent
+//     field of t fold into one immediate);
+//   * g = 1 + F 2^-32 is assembled from the bits of F (two shifts, one OR) and p = q(g) = exp((g-1) ln2/N) is a cubic
+//     in g: no F2I / I2F (each costs ~3.5 cycles of the shared FP64/DMMA pipe on top of the XU slot) and no
+//     DADD for the reduced argument.
+// Shared-pipe cost: 3 DFMA + 1 DMUL = 8 cycles per warp, against 1 DADD + 3 DFMA + 1 DMUL + 2 conversions = 17 for
+// exp_scaled.  (A fully integer polynomial with IMAD.HI / IMAD.WIDE measured SLOWER: wide integer multiplies issue at
+// ~4.5 cycles and contend with the FP64 pipe -- tools/microbench/imad_peak.cu, profiles/r1_notes.md.)
+// Error: ep is rounded to 2^-32 table units twice (<= 2^-32 ln2/N relative, unbiased) + the polynomial.
+// Below EXP_NMIN the high word is clamped (result ~2^-1022, as exp_scaled); NaN does NOT propagate: callers flag dead
+// chains (Comp<CLS_D>::dead).
+__device__ __forceinline__ double exp_scaled_bits(double t, const double* __restrict__ tbl) {
+    constexpr int S = 20 - TBL_BITS;
+    constexpr int HI_MAGIC = 0x41380000;                                  // high word of FX_MAGIC
+    constexpr int HI_MIN = HI_MAGIC + EXP_NMIN;                           // high word of EXP_NMIN + FX_MAGIC
+    constexpr unsigned int FOLD = (unsigned int)(((unsigned long long)HI_MAGIC << S) & 0xffffffffull);
+    const int ht = max(__double2hiint(t), HI_MIN);
+    const unsigned int F = (unsigned int)__double2loint(t);
+    const double g = __hiloint2double((int)(0x3FF00000u | (F >> 12)), (int)(F << 20));
+    const double p = fma(g, fma(g, fma(g, EXQ_C3, EXQ_C2), EXQ_C1), EXQ_C0);
+    const char* tb = reinterpret_cast<const char*>(tbl);
+    const int off = (ht << 2) & ((TBL_N - 1) << 2);
+    const unsigned int hi = *reinterpret_cast<const unsigned int*>(tb + off) + ((unsigned int)ht << S) - FOLD;
+    const unsigned int lo = *reinterpret_cast<const unsigned int*>(tb + off + TBL_N * 4);
+    return __hiloint2double((int)hi, (int)lo) * p;
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {

@@ -15,7 +15,8 @@
 //     * exponential / exp_pist_flow: geometric recurrence v <- v*r^4, re-anchored by a true exp() at every
 //       chunk start; the mask tp >= tau(1-1/eta) is an integer compare against k0.
 //     * dispersion: w = tp^-1.5 * exp(-(1-x)^2/(4Dx)); the tp^-1.5 factor is folded into a second copy of X
-//       (Xd), the exponent is two FMAs on per-lag tables, exp() is the table-driven exp_scaled().
+//       (Xd), the exponent is two FMAs on the per-lag table {1/tp, tp}, exp() is the table-driven, conversion-free
+//       exp_scaled_bits().
 //     * piston: a gather of one row of X in the epilogue.
 //   Normalisation sum = column 0 (ones) of the same MMA.
 #pragma once
@@ -108,15 +109,16 @@ struct Comp<CLS_G> {
 
 template <>
 struct Comp<CLS_D> {
-    double ap, bp, cp, u;
+    double ap, bp, cp;
+    // exp_scaled_bits() does not propagate NaN -> WarpTiles::end() poisons the sums of dead chains instead
+    __device__ __forceinline__ bool dead() const { return ap != ap; }
     __device__ __forceinline__ void init(double tau, double, double D, double dtp, int L) {
-        bool ok = (tau > 0.0) && (D > 0.0);
+        bool ok = (tau > 0.0) && (D > 0.0) && (tau < 1.0e300) && (D < 1.0e300);
         double i4D = 1.0 / (4.0 * D);
-        // e = -(1-x)^2/(4Dx), x = tp/tau  ==  -(tau/4D)/tp + 1/(2D) - tp/(4D tau); pre-scaled by 32/ln2
+        // e = -(1-x)^2/(4Dx), x = tp/tau  ==  -(tau/4D)/tp + 1/(2D) - tp/(4D tau); pre-scaled by N/ln2
         ap = -EXP_K * tau * i4D;
         bp = -EXP_K * i4D / tau;
         cp = EXP_K * 2.0 * i4D;
-        u = 0.0;
         // Largest exponent over the lag grid: e(x) peaks (e = 0) at x = 1; if tau lies beyond the last lag the
         // maximum is at the last lag.  Below 2^-1022 every reference weight is (sub)denormal or exactly zero and
         // g/g.sum() is NaN or precision-less: the chain is declared dead -> NaN output.
@@ -125,18 +127,12 @@ struct Comp<CLS_D> {
             double emax = fma(ap, 1.0 / tpl, fma(bp, tpl, cp));
             ok = emax >= (double)EXP_NMIN;
         }
+        cp += FX_MAGIC;     // exp_scaled_bits takes ep + FX_MAGIC: folded into the constant term
         if (!ok) ap = __longlong_as_double(0x7ff8000000000000LL);
     }
-    __device__ __forceinline__ double first(int k, double dtp, double itpk, const double* tbl) {
-        double tp = ((k == 0) ? 1e-5 : (double)k) + dtp;
-        double w = exp_scaled(fma(ap, itpk, fma(bp, tp, cp)), tbl);
-        u = fma(bp, (double)(k + 4) + dtp, cp);
-        return w;
-    }
-    __device__ __forceinline__ double next(double itpk, const double* tbl) {
-        double w = exp_scaled(fma(ap, itpk, u), tbl);
-        u = fma(bp, 4.0, u);
-        return w;
+    // it = {1/tp, tp} of the lag (shared-memory table): two independent FMAs, no carried state
+    __device__ __forceinline__ double weight(double2 it, const double* tbl) const {
+        return exp_scaled_bits(fma(ap, it.x, fma(bp, it.y, cp)), tbl);
     }
 };
 
@@ -206,7 +202,7 @@ struct WarpTiles {
         int k = kc + j;
         const double* pf = ngrtd_smem + s.Xf + j * NCOL + r;
         const double* pd = ngrtd_smem + s.Xd + j * NCOL + r;
-        const double* pi = ngrtd_smem + s.itp + j;
+        const double2* pi = reinterpret_cast<const double2*>(ngrtd_smem + s.itp) + j;
         const double* px = ngrtd_smem + s.xraw + j;
         const double* pxd = ngrtd_smem + s.xrawd + j;
         const double* tbl = ngrtd_smem + s.tbl;
@@ -214,16 +210,16 @@ struct WarpTiles {
         {   // first group of the chunk: direct evaluation (handles tp_0 = 1e-5 and re-anchors the recurrences)
             double bf = pf[0];
             double bd = ANY_D ? pd[0] : 0.0;
-            double it = ANY_D ? pi[0] : 0.0;
+            double2 it = ANY_D ? pi[0] : make_double2(0.0, 0.0);
             double xr = DYN ? px[0] : 0.0;
             double xrd = (DYN && ANY_D) ? pxd[0] : 0.0;
 #pragma unroll
             for (int t = 0; t < NT; t++) {
                 double w1 = 0.0, w2 = 0.0;
                 if constexpr (C1 == CLS_G) { w1 = c1[t].first(k, dtp); dmma884(a1[t][0][0], a1[t][0][1], w1, bf); }
-                if constexpr (C1 == CLS_D) { w1 = c1[t].first(k, dtp, it, tbl); dmma884(a1[t][0][0], a1[t][0][1], w1, bd); }
+                if constexpr (C1 == CLS_D) { w1 = c1[t].weight(it, tbl); dmma884(a1[t][0][0], a1[t][0][1], w1, bd); }
                 if constexpr (C2 == CLS_G) { w2 = c2[t].first(k, dtp); dmma884(a2[t][0][0], a2[t][0][1], w2, bf); }
-                if constexpr (C2 == CLS_D) { w2 = c2[t].first(k, dtp, it, tbl); dmma884(a2[t][0][0], a2[t][0][1], w2, bd); }
+                if constexpr (C2 == CLS_D) { w2 = c2[t].weight(it, tbl); dmma884(a2[t][0][0], a2[t][0][1], w2, bd); }
                 if constexpr (DYN) {
                     double dvk = exp(-lam[t] * ((double)k + dtp));
                     double du = (k == 0) ? exp(-lam[t] * (1e-5 + dtp)) : dvk;
@@ -242,16 +238,17 @@ struct WarpTiles {
                 k += 4;
                 pf += 4 * NCOL;
                 double bf = pf[0];
-                double bd = 0.0, it = 0.0, xr = 0.0, xrd = 0.0;
+                double bd = 0.0, xr = 0.0, xrd = 0.0;
+                double2 it = make_double2(0.0, 0.0);
                 if constexpr (ANY_D) { pd += 4 * NCOL; pi += 4; bd = pd[0]; it = pi[0]; }
                 if constexpr (DYN) { px += 4; xr = px[0]; if constexpr (ANY_D) { pxd += 4; xrd = pxd[0]; } }
 #pragma unroll
                 for (int t = 0; t < NT; t++) {
                     double w1 = 0.0, w2 = 0.0;
                     if constexpr (C1 == CLS_G) { w1 = c1[t].next(k); dmma884(a1[t][u][0], a1[t][u][1], w1, bf); }
-                    if constexpr (C1 == CLS_D) { w1 = c1[t].next(it, tbl); dmma884(a1[t][u][0], a1[t][u][1], w1, bd); }
+                    if constexpr (C1 == CLS_D) { w1 = c1[t].weight(it, tbl); dmma884(a1[t][u][0], a1[t][u][1], w1, bd); }
                     if constexpr (C2 == CLS_G) { w2 = c2[t].next(k); dmma884(a2[t][u][0], a2[t][u][1], w2, bf); }
-                    if constexpr (C2 == CLS_D) { w2 = c2[t].next(it, tbl); dmma884(a2[t][u][0], a2[t][u][1], w2, bd); }
+                    if constexpr (C2 == CLS_D) { w2 = c2[t].weight(it, tbl); dmma884(a2[t][u][0], a2[t][u][1], w2, bd); }
                     if constexpr (DYN) {
                         double du = dv[t];
                         dv[t] *= d4[t];
@@ -265,16 +262,17 @@ struct WarpTiles {
             k += 4;
             pf += 4 * NCOL;
             double bf = pf[0];
-            double bd = 0.0, it = 0.0, xr = 0.0, xrd = 0.0;
+            double bd = 0.0, xr = 0.0, xrd = 0.0;
+                double2 it = make_double2(0.0, 0.0);
             if constexpr (ANY_D) { pd += 4 * NCOL; pi += 4; bd = pd[0]; it = pi[0]; }
             if constexpr (DYN) { px += 4; xr = px[0]; if constexpr (ANY_D) { pxd += 4; xrd = pxd[0]; } }
 #pragma unroll
             for (int t = 0; t < NT; t++) {
                 double w1 = 0.0, w2 = 0.0;
                 if constexpr (C1 == CLS_G) { w1 = c1[t].next(k); dmma884(a1[t][0][0], a1[t][0][1], w1, bf); }
-                if constexpr (C1 == CLS_D) { w1 = c1[t].next(it, tbl); dmma884(a1[t][0][0], a1[t][0][1], w1, bd); }
+                if constexpr (C1 == CLS_D) { w1 = c1[t].weight(it, tbl); dmma884(a1[t][0][0], a1[t][0][1], w1, bd); }
                 if constexpr (C2 == CLS_G) { w2 = c2[t].next(k); dmma884(a2[t][0][0], a2[t][0][1], w2, bf); }
-                if constexpr (C2 == CLS_D) { w2 = c2[t].next(it, tbl); dmma884(a2[t][0][0], a2[t][0][1], w2, bd); }
+                if constexpr (C2 == CLS_D) { w2 = c2[t].weight(it, tbl); dmma884(a2[t][0][0], a2[t][0][1], w2, bd); }
                 if constexpr (DYN) {
                     double du = dv[t];
                     dv[t] *= d4[t];
@@ -334,6 +332,7 @@ struct WarpTiles {
                 }
             } else {
                 double S = __shfl_sync(full, a1[t][0][0], lane & ~3);
+                if constexpr (C1 == CLS_D) { if (c1[t].dead()) S = c1[t].ap; }
                 x1[0] = a1[t][0][0] / S;
                 x1[1] = a1[t][0][1] / S;
                 if (DYN) {
@@ -353,6 +352,7 @@ struct WarpTiles {
                 }
             } else if constexpr (C2 != CLS_NONE) {
                 double S = __shfl_sync(full, a2[t][0][0], lane & ~3);
+                if constexpr (C2 == CLS_D) { if (c2[t].dead()) S = c2[t].ap; }
                 x2[0] = a2[t][0][0] / S;
                 x2[1] = a2[t][0][1] / S;
                 if (DYN) {
@@ -467,7 +467,7 @@ struct FwdCta {
         s.scratch = p; p += nwarps * NT * 8 * NCOL;
         s.Xf = p; p += lc_cap * NCOL;
         s.Xd = p; if (WT::ANY_D) p += lc_cap * NCOL;
-        s.itp = p; if (WT::ANY_D) p += lc_cap;
+        s.itp = p; if (WT::ANY_D) p += 2 * lc_cap;
         s.xraw = p; if (DYN) p += lc_cap;
         s.xrawd = p; if (DYN && WT::ANY_D) p += lc_cap;
         scratch_off = s.scratch + warp * NT * 8 * NCOL;
@@ -496,13 +496,13 @@ struct FwdCta {
         if (tid == 0) {
             const unsigned int bx = (unsigned int)len * NCOL * 8u, bl = (unsigned int)len * 8u;
             unsigned int total = bx;
-            if (WT::ANY_D) total += bx + bl;
+            if (WT::ANY_D) total += bx + 2u * bl;
             if (DYN) total += bl + (WT::ANY_D ? bl : 0u);
             mbar_expect_tx(bar, total);
             bulk_g2s(ngrtd_smem + s.Xf, pv.Xf + (size_t)kc * NCOL, bx, bar);
             if (WT::ANY_D) {
                 bulk_g2s(ngrtd_smem + s.Xd, pv.Xd + (size_t)kc * NCOL, bx, bar);
-                bulk_g2s(ngrtd_smem + s.itp, pv.itp + kc, bl, bar);
+                bulk_g2s(ngrtd_smem + s.itp, pv.itp + 2 * (size_t)kc, 2u * bl, bar);
             }
             if (DYN) {
                 bulk_g2s(ngrtd_smem + s.xraw, pv.xraw + kc, bl, bar);
