@@ -211,16 +211,13 @@ extern "C" int ngrtd_plan_create(ngrtd_plan** out, int32_t L, int32_t nseries, c
             }
         }
     }
-    std::vector<double> tbl(TBL_DOUBLES);
-    {
-        uint32_t* w = reinterpret_cast<uint32_t*>(tbl.data());
-        for (int i = 0; i < TBL_N; i++) {
-            double v = std::exp2((double)i / TBL_N);
-            uint64_t b;
-            std::memcpy(&b, &v, 8);
-            w[i] = (uint32_t)(b >> 32) - ((uint32_t)i << (20 - TBL_BITS));
-            w[TBL_N + i] = (uint32_t)(b & 0xffffffffu);
-        }
+    std::vector<double> tbl(TBL_N);     // the kernels replicate it TBL_REP times in shared memory
+    for (int i = 0; i < TBL_N; i++) {
+        double v = std::exp2((double)i / TBL_N);
+        uint64_t b;
+        std::memcpy(&b, &v, 8);
+        b -= (uint64_t)i << (32 + 20 - TBL_BITS);      // exponent insertion becomes one integer add (exp_scaled_bits)
+        std::memcpy(&tbl[i], &b, 8);
     }
 
     auto up = [&](double** d, const std::vector<double>& h) -> cudaError_t {
@@ -314,7 +311,10 @@ static int launch_forward_t(ngrtd_plan* P, const SlotMap& sm, const double* thet
     return NGRTD_OK;
 }
 
-constexpr int FWD_NT = 2, FWD_UA = 1, FWD_MAXW = 16;
+#ifndef NGRTD_FWD_MAXW
+#define NGRTD_FWD_MAXW 16
+#endif
+constexpr int FWD_NT = 2, FWD_UA = 1, FWD_MAXW = NGRTD_FWD_MAXW;
 
 template <int C1, int C2, bool DYN>
 static int launch_forward(ngrtd_plan* P, const SlotMap& sm, const double* theta, long long B, double* out,

@@ -12,44 +12,27 @@ constexpr int NSLOT = 11;               // ForwardMod.p_dict slots
 constexpr int MAX_TRACER = 8;
 constexpr int LC_MAX = 1024;            // lags resident in shared memory per chunk
 
-// table-driven exp(): exp(e) = 2^(n/N) * p(r),  n = rint(e*N/ln2),  r = e*N/ln2 - n in [-1/2, 1/2].
-// The N-entry table of 2^(j/N) is stored as two 32-bit arrays (high / low words).  With N = 32 any 32-lane gather from
-// a 128-byte array is bank-conflict free (one 4-byte slot per bank, equal slots broadcast): exactly two shared-memory
-// wavefronts per lookup.  (A 2048-entry double table measured 8 wavefronts per lookup and made the kernel LSU-bound.)
-// p(r) interpolates exp at Chebyshev nodes (near-minimax); max relative error: N=32/deg 4: 7.8e-14, N=64/deg 3: 4.5e-12,
-// N=128/deg 3: 2.8e-13.  Measured on cfg 3 (profiles/r1_notes.md): N=32/deg 4 72.5 cycles per tile-group, N=64/deg 3
-// 72.1, N=128/deg 3 70.5 (the extra bank conflicts of the 512-byte arrays cost less than the fourth DFMA): default N=128.
+// table-driven exp(): exp(e) = 2^(n/N) * q(g), n = floor(e*N/ln2), g = 1 + frac(e*N/ln2)  (exp_scaled_bits below).
+// The N-entry table of 2^(j/N) lives in shared memory as 8-byte entries, replicated TBL_REP times: lane l gathers from
+// copy l & (TBL_REP-1) at double index j*TBL_REP + copy.  A 64-bit shared load is served per half-warp; with 16 copies
+// every lane of a half-warp owns its own pair of banks and the gather is conflict-free (2 wavefronts per warp).
+// Measured (profiles/r1_notes.md): one copy as two 32-bit word arrays, N = 256: ~6.8 wavefronts per gather pair, LSU data
+// pipe 64 % busy; 16 copies: 46 % -- but the lag loop is held by the shared FP64/DMMA pipe (math-pipe-throttle stalls
+// at 67 % pipe activity), so throughput did not move, and 16 KB more shared memory pushed the sampler kernel into
+// chunked streaming.  Default: 4 copies (4 KB), N = 128.
 #ifndef NGRTD_TBL_BITS
-#define NGRTD_TBL_BITS 8
+#define NGRTD_TBL_BITS 7
+#endif
+#ifndef NGRTD_TBL_REP_BITS
+#define NGRTD_TBL_REP_BITS 2
 #endif
 constexpr int TBL_BITS = NGRTD_TBL_BITS;
 constexpr int TBL_N = 1 << TBL_BITS;
-constexpr int TBL_DOUBLES = TBL_N;      // shared-memory footprint in doubles (hi[N] + lo[N] as uint32)
+constexpr int TBL_REP_BITS = NGRTD_TBL_REP_BITS;
+constexpr int TBL_REP = 1 << TBL_REP_BITS;
+constexpr int TBL_DOUBLES = TBL_N * TBL_REP;      // shared-memory footprint in doubles
 constexpr double LN2 = 0.693147180559945309417232121458;
 constexpr double EXP_K = TBL_N / LN2;
-#if NGRTD_TBL_BITS == 5
-constexpr int EXP_DEG = 4;
-constexpr double EXP_C0 = 1.0, EXP_C1 = 0.02166084939172217, EXP_C2 = 0.00023459619819944503,
-                 EXP_C3 = 1.693863390316062e-06, EXP_C4 = 9.172607532633896e-09;
-#elif NGRTD_TBL_BITS == 6
-constexpr int EXP_DEG = 3;
-constexpr double EXP_C0 = 0.9999999999955212, EXP_C1 = 0.010830424696239445, EXP_C2 = 5.864919287197594e-05,
-                 EXP_C3 = 2.1173168199978455e-07, EXP_C4 = 0.0;
-#elif NGRTD_TBL_BITS == 7
-constexpr int EXP_DEG = 3;
-constexpr double EXP_C0 = 0.9999999999997201, EXP_C1 = 0.005415212348124269, EXP_C2 = 1.4662271345222707e-05,
-                 EXP_C3 = 2.64664311467397e-08, EXP_C4 = 0.0;
-#elif NGRTD_TBL_BITS == 8
-constexpr int EXP_DEG = 3;
-constexpr double EXP_C0 = 0.9999999999999825, EXP_C1 = 0.0027076061740622769, EXP_C2 = 3.6655661567589337e-06,
-                 EXP_C3 = 3.3083029837113949e-09, EXP_C4 = 0.0;
-#elif NGRTD_TBL_BITS == 9
-constexpr int EXP_DEG = 3;
-constexpr double EXP_C0 = 0.99999999999999891, EXP_C1 = 0.0013538030870311429, EXP_C2 = 9.1639143421807685e-07,
-                 EXP_C3 = 4.1353784454173436e-10, EXP_C4 = 0.0;
-#else
-#error "NGRTD_TBL_BITS must be 5..9"
-#endif
 // exp_scaled_bits: q(g) ~= exp((g - 1) ln2 / N) on g in [1, 2)  (tools/exp_poly_g.py: constants and error bounds)
 #if NGRTD_TBL_BITS == 7
 constexpr double EXQ_C0 = 0.99459942332194162, EXQ_C1 = 0.0053859675366433966, EXQ_C2 = 1.4582602945559778e-05,
@@ -92,7 +75,7 @@ struct PlanView {
     const double* itp;    // [Lpad][2] {1/tp, tp} (pad: 0, 0)
     const double* xraw;   // [Lpad] raw series of the per-chain-lambda tracer
     const double* xrawd;  // [Lpad] xraw * tp^-1.5
-    const double* tbl;    // [TBL_N] doubles = hi[TBL_N], lo[TBL_N] words of 2^(j/TBL_N)
+    const double* tbl;    // [TBL_N] 2^(j/TBL_N) with j << (20 - TBL_BITS) subtracted from the high word (see exp_scaled_bits)
     int ntracer;
     TracerDev tr[MAX_TRACER];
     int eta1_is_one, eta2_is_one;   // 'exponential' == exp_pist_flow with eta = 1 (bit-identical in the reference)
@@ -141,44 +124,21 @@ __device__ __forceinline__ ChainPar load_chain_par(const double* __restrict__ th
     return p;
 }
 
-// exp(e) for e <= ~0 given ep = e * N/ln2.  FP64-pipe cost: 1 DADD + deg DFMA + 1 DMUL (+ 2 conversions).
-//   * rounding: F2I.F64 / I2F.F64 on the conversion unit.  The magic-number alternative (ep + 1.5*2^52, two more
-//     DADDs, no conversions) measured 8 % slower in the full kernel (72.4 vs 78.2 cycles per tile-group,
-//     profiles/r1_notes.md) although the conversions also occupy the FP64 pipe for ~3.5 cycles each.
-//     F2I saturates for hugely negative exponents and maps NaN to 0 (r = NaN then poisons the result).
-//   * table: hi'[N] (uint32) followed by lo[N] (uint32), hi'[j] = hi(2^(j/N)) - (j << (20 - log2 N)), so the exponent
-//     insertion is ONE integer multiply-add: hi'[j] + n*2^(20 - log2 N) = hi[j] + ((n >> log2 N) << 20).
-//   * n is clamped at EXP_NMIN (result ~2^-1022) instead of flushing to zero: one IMNMX instead of a compare and two
-//     selects.  Chains whose largest weight would be below 2^-1022 are declared dead (NaN) in Comp<CLS_D>::init, which
-//     reproduces the reference's 0/0 = NaN when every weight underflows.
-__device__ __forceinline__ double exp_scaled(double ep, const double* __restrict__ tbl) {
-    const unsigned int* th = reinterpret_cast<const unsigned int*>(tbl);
-    int n = __double2int_rn(ep);
-    double r = ep - __int2double_rn(n);
-    double p = (EXP_DEG == 4) ? fma(r, fma(r, fma(r, fma(r, EXP_C4, EXP_C3), EXP_C2), EXP_C1), EXP_C0)
-                              : fma(r, fma(r, fma(r, EXP_C3, EXP_C2), EXP_C1), EXP_C0);
-    int nc = max(n, EXP_NMIN);
-    int off = (nc << 2) & ((TBL_N - 1) << 2);    // byte offset of the table slot
-    const char* tb = reinterpret_cast<const char*>(th);
-    int hi = (int)*reinterpret_cast<const unsigned int*>(tb + off) + nc * (1 << (20 - TBL_BITS));
-    int lo = (int)*reinterpret_cast<const unsigned int*>(tb + off + TBL_N * 4);
-    return __hiloint2double(hi, lo) * p;
-}
-
-// Conversion-free variant used by the dispersion lag loop.  t = ep + FX_MAGIC; the addition is folded into the caller's
-// FMA chain (cp + FX_MAGIC is a per-chain constant), so it costs nothing.  With 2^20 <= t < 2^21 the mantissa of t IS ep
-// in fixed point: high word bits 0..19 = floor(ep) + 2^19, low word = the 32-bit fraction F of ep.
+// exp(e) for e <= ~0, given t = ep + FX_MAGIC with ep = e*N/ln2.  The addition is folded into the caller's FMA chain
+// (cp + FX_MAGIC is a per-chain constant), so it costs nothing.  With 2^20 <= t < 2^21 the mantissa of t IS ep in fixed
+// point: high word bits 0..19 = floor(ep) + 2^19, low word = the 32-bit fraction F of ep.
 //   * table slot / exponent insertion come from the high word on the integer pipes (the 2^19 bias and the exponent
-//     field of t fold into one immediate);
+//     field of t fold into one immediate; the table stores 2^(j/N) with j << (20 - log2 N) subtracted from its high word);
 //   * g = 1 + F 2^-32 is assembled from the bits of F (two shifts, one OR) and p = q(g) = exp((g-1) ln2/N) is a cubic
-//     in g: no F2I / I2F (each costs ~3.5 cycles of the shared FP64/DMMA pipe on top of the XU slot) and no
-//     DADD for the reduced argument.
-// Shared-pipe cost: 3 DFMA + 1 DMUL = 8 cycles per warp, against 1 DADD + 3 DFMA + 1 DMUL + 2 conversions = 17 for
-// exp_scaled.  (A fully integer polynomial with IMAD.HI / IMAD.WIDE measured SLOWER: wide integer multiplies issue at
-// ~4.5 cycles and contend with the FP64 pipe -- tools/microbench/imad_peak.cu, profiles/r1_notes.md.)
+//     in g: no F2I / I2F conversions and no DADD for the reduced argument.
+// Shared FP64/DMMA-pipe cost: 3 DFMA + 1 DMUL.  History (profiles/r1_notes.md): the first version rounded with F2I/I2F
+// (XU pipe) and a centred polynomial; a fully integer polynomial with IMAD.HI / IMAD.WIDE measured SLOWER (wide integer
+// multiplies issue at ~4.5 cycles and contend with the FP64 pipe -- tools/microbench/imad_peak.cu).
 // Error: ep is rounded to 2^-32 table units twice (<= 2^-32 ln2/N relative, unbiased) + the polynomial.
-// Below EXP_NMIN the high word is clamped (result ~2^-1022, as exp_scaled); NaN does NOT propagate: callers flag dead
-// chains (Comp<CLS_D>::dead).
+// Below EXP_NMIN the high word is clamped (result ~2^-1022) instead of flushing to zero: one VIMNMX instead of a compare
+// and two selects.  NaN does NOT propagate through the integer path: chains whose largest weight would be below 2^-1022,
+// or with NaN parameters, are declared dead in Comp<CLS_D>::init and poisoned in the epilogue, which reproduces the
+// reference's 0/0 = NaN when every weight underflows.
 __device__ __forceinline__ double exp_scaled_bits(double t, const double* __restrict__ tbl) {
     constexpr int S = 20 - TBL_BITS;
     constexpr int HI_MAGIC = 0x41380000;                                  // high word of FX_MAGIC
@@ -188,11 +148,11 @@ __device__ __forceinline__ double exp_scaled_bits(double t, const double* __rest
     const unsigned int F = (unsigned int)__double2loint(t);
     const double g = __hiloint2double((int)(0x3FF00000u | (F >> 12)), (int)(F << 20));
     const double p = fma(g, fma(g, fma(g, EXQ_C3, EXQ_C2), EXQ_C1), EXQ_C0);
-    const char* tb = reinterpret_cast<const char*>(tbl);
-    const int off = (ht << 2) & ((TBL_N - 1) << 2);
-    const unsigned int hi = *reinterpret_cast<const unsigned int*>(tb + off) + ((unsigned int)ht << S) - FOLD;
-    const unsigned int lo = *reinterpret_cast<const unsigned int*>(tb + off + TBL_N * 4);
-    return __hiloint2double((int)hi, (int)lo) * p;
+    // tbl points at this lane's copy: entry j is at tbl[j * TBL_REP]
+    const int off = (ht << (3 + TBL_REP_BITS)) & ((TBL_N - 1) << (3 + TBL_REP_BITS));
+    const double T = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(tbl) + off);
+    const unsigned int hi = (unsigned int)__double2hiint(T) + ((unsigned int)ht << S) - FOLD;
+    return __hiloint2double((int)hi, __double2loint(T)) * p;
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {

@@ -205,7 +205,7 @@ struct WarpTiles {
         const double2* pi = reinterpret_cast<const double2*>(ngrtd_smem + s.itp) + j;
         const double* px = ngrtd_smem + s.xraw + j;
         const double* pxd = ngrtd_smem + s.xrawd + j;
-        const double* tbl = ngrtd_smem + s.tbl;
+        const double* tbl = ngrtd_smem + s.tbl + (lane & (TBL_REP - 1));   // this lane's copy of the exp table
         const double dtp = pv.dtp;
         {   // first group of the chunk: direct evaluation (handles tp_0 = 1e-5 and re-anchors the recurrences)
             double bf = pf[0];
@@ -462,7 +462,7 @@ struct FwdCta {
         lane = tid & 31;
         warp = tid >> 5;
         int p = 0;
-        s.tbl = p; p += TBL_DOUBLES;       // first: keeps the 128-byte bank alignment of the two word arrays
+        s.tbl = p; p += TBL_DOUBLES;       // first: 128-byte aligned, so copy c of every entry sits in banks 2c, 2c+1
         s.bar = p; p += 2;
         s.scratch = p; p += nwarps * NT * 8 * NCOL;
         s.Xf = p; p += lc_cap * NCOL;
@@ -478,7 +478,7 @@ struct FwdCta {
         phase = 0;
         if (tid == 0) mbar_init(reinterpret_cast<unsigned long long*>(ngrtd_smem + s.bar), 1);
         if (WT::ANY_D) {
-            for (int i = tid; i < TBL_DOUBLES; i += nthreads) ngrtd_smem[s.tbl + i] = pv.tbl[i];
+            for (int i = tid; i < TBL_DOUBLES; i += nthreads) ngrtd_smem[s.tbl + i] = pv.tbl[i >> TBL_REP_BITS];
         }
         __syncthreads();
         pending = false;
