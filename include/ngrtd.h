@@ -124,6 +124,10 @@ int ngrtd_rtd_weights_dev(int32_t mod_type, int32_t L, double dtp, const double*
  *      (the reference's `FM_mu` attribute) or NULL.  Feed g to ngrtd_convolve_g_dev for the concentration.              */
 int ngrtd_rtd_weights_fdm_dev(int32_t L, double dtp, const double* tau_d, const double* D_d, const double* bbar_d,
                               const double* phi_d, int64_t B, double* g_d, double* fm_mu_d, void* stream);
+/* ---- same with an externally supplied advective RTD (frac_rtd_numba, conv utils :66-97; update_pars(f_tadv_ext=...) :142,
+ *      :250-252): f_tadv_ext [L] on the lag grid, shared by the B (bbar, Phi_im) sets, linearly interpolated (np.interp). */
+int ngrtd_rtd_weights_fdm_ext_dev(int32_t L, double dtp, const double* f_tadv_ext_d, const double* bbar_d,
+                                  const double* phi_d, int64_t B, double* g_d, double* fm_mu_d, void* stream);
 /* ---- tracer_conv_integral.convolve(g_tau=...) tail (:305-340): decay/ingrowth + input assembly + dot
  *      for externally supplied weights g[B, L]; series [L] newest-first, lag_index [L] or NULL.      */
 int ngrtd_convolve_g_dev(int32_t L, double dtp, const double* g_d, int64_t B, const double* series_d,

@@ -69,6 +69,7 @@ _PROTOS = {
     "ngrtd_forward_loglik_host": ([_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "ngrtd_rtd_weights_dev": ([_i32, _i32, _dbl, _vp, _vp, _vp, _i64, _vp, _vp], ctypes.c_int),
     "ngrtd_rtd_weights_fdm_dev": ([_i32, _dbl, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp], ctypes.c_int),
+    "ngrtd_rtd_weights_fdm_ext_dev": ([_i32, _dbl, _vp, _vp, _vp, _i64, _vp, _vp, _vp], ctypes.c_int),
     "ngrtd_convolve_g_dev": ([_i32, _dbl, _vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp], ctypes.c_int),
     "ngrtd_ce_dev": ([_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _vp, _vp], ctypes.c_int),
     "ngrtd_ce_host": ([_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _vp], ctypes.c_int),

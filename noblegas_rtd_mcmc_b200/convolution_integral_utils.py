@@ -4,7 +4,8 @@ B200 through libngrtd.so.  Same names, kwargs and mutating-attribute behaviour a
 give batched results of shape [B].
 
 'frac_inf_diff' (fracture / matrix diffusion with a dispersion advective RTD, :36-63,238-266) is evaluated by a
-dedicated quadrature kernel and convolved through the external-weights path.  Not provided: 'frac_inf_diff.mint'
+dedicated quadrature kernel (dispersion or caller-supplied advective RTD `f_tadv_ext`, :66-97) and convolved through the
+external-weights path.  Not provided: 'frac_inf_diff.mint'
 (an older pure-Python duplicate that prints on every call, :199-235), the external advective RTD `f_tadv_ext`
 (:66-97) and the dead 'SF6' accumulation branch (:330-331, J_sf6 is never set by any caller).
 """
@@ -63,8 +64,6 @@ class tracer_conv_integral():
     # ------------------------------------------------------------------ helpers
     def _check_model(self):
         if self.mod_type == "frac_inf_diff":
-            if getattr(self, "f_tadv_ext", None) is not None:
-                raise NotImplementedError("frac_inf_diff with an external advective RTD (f_tadv_ext) is not provided")
             return
         if self.mod_type not in _MODS:
             if self.mod_type == "frac_inf_diff.mint":
@@ -103,13 +102,30 @@ class tracer_conv_integral():
         tp += dtp
         self.tau_list = tp.copy()
         if self.mod_type == "frac_inf_diff":
-            B, scalar = self._batch(self.tau, self.D, self.bbar, self.Phi_im)
             dev = torch.device("cuda")
-            t = [torch.from_numpy(self._col(v, B)).to(dev) for v in (self.tau, self.D, self.bbar, self.Phi_im)]
+            fext = getattr(self, "f_tadv_ext", None)
+            try:                                                # the reference's test for "an external RTD was given" (:250-252)
+                len(fext)
+            except TypeError:
+                fext = None
+            if fext is not None:
+                fext = np.ascontiguousarray(fext, dtype=np.float64)
+                if fext.ndim != 1 or len(fext) != L:            # the reference only prints a warning (:79-80) and then fails in interp
+                    raise ValueError("f_tadv_ext must have the length of the tracer input function (%d)" % L)
+                B, scalar = self._batch(self.bbar, self.Phi_im)
+                t = [torch.from_numpy(self._col(v, B)).to(dev) for v in (self.bbar, self.Phi_im)]
+                fe = torch.from_numpy(fext).to(dev)
+            else:
+                B, scalar = self._batch(self.tau, self.D, self.bbar, self.Phi_im)
+                t = [torch.from_numpy(self._col(v, B)).to(dev) for v in (self.tau, self.D, self.bbar, self.Phi_im)]
             g = torch.empty((B, L), dtype=torch.float64, device=dev)
             mu = torch.empty(B, dtype=torch.float64, device=dev)
-            _lib.check(_lib.lib.ngrtd_rtd_weights_fdm_dev(L, dtp, _lib.dptr(t[0]), _lib.dptr(t[1]), _lib.dptr(t[2]), _lib.dptr(t[3]),
-                                                          B, _lib.dptr(g), _lib.dptr(mu), _lib.stream_ptr()))
+            if fext is not None:
+                _lib.check(_lib.lib.ngrtd_rtd_weights_fdm_ext_dev(L, dtp, _lib.dptr(fe), _lib.dptr(t[0]), _lib.dptr(t[1]), B,
+                                                                  _lib.dptr(g), _lib.dptr(mu), _lib.stream_ptr()))
+            else:
+                _lib.check(_lib.lib.ngrtd_rtd_weights_fdm_dev(L, dtp, _lib.dptr(t[0]), _lib.dptr(t[1]), _lib.dptr(t[2]), _lib.dptr(t[3]),
+                                                              B, _lib.dptr(g), _lib.dptr(mu), _lib.stream_ptr()))
             out, m = g.cpu().numpy(), mu.cpu().numpy()
             self.FM_mu = float(m[0]) if scalar else m          # mean travel time (:264-265)
             return out[0] if scalar else out

@@ -589,9 +589,25 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return t;
 }
 
+// np.interp(x, tp[:n], fp[:n]) on the lag grid tp[0] = 1e-5 + dtp, tp[k] = k + dtp (numpy's arithmetic: slope*(x-xp[j])+fp[j])
+__device__ __forceinline__ double fdm_interp(double x, const double* __restrict__ fp, int n, double dtp) {
+    auto xp = [&](int k) { return ((k == 0) ? 1e-5 : (double)k) + dtp; };
+    if (x < xp(0)) return fp[0];
+    if (!(x < xp(n - 1))) return fp[n - 1];
+    int j = (int)floor(x - dtp);
+    j = max(0, min(j, n - 2));
+    while (j > 0 && x < xp(j)) j--;
+    while (j < n - 2 && !(x < xp(j + 1))) j++;
+    if (x == xp(j)) return fp[j];
+    double slope = (fp[j + 1] - fp[j]) / (xp(j + 1) - xp(j));
+    return __dadd_rn(__dmul_rn(slope, x - xp(j)), fp[j]);
+}
+
+// fext == nullptr: dispersion advective RTD (frac_rtd_numba_disp, :36-63); else the caller's advective RTD on the lag
+// grid, linearly interpolated (frac_rtd_numba, :66-97)
 __global__ void __launch_bounds__(128) k_fdm_lag(int L, double dtp, const double* __restrict__ tau_, const double* __restrict__ D_,
                                                  const double* __restrict__ bbar_, const double* __restrict__ phi_,
-                                                 double* __restrict__ f) {
+                                                 const double* __restrict__ fext, double* __restrict__ f) {
     __shared__ double tadv_s[FDM_NQ], tret_s[FDM_NQ], fret_s[FDM_NQ], fadv_s[FDM_NQ];
     __shared__ double red[4];
     const int i = blockIdx.x;
@@ -600,7 +616,7 @@ __global__ void __launch_bounds__(128) k_fdm_lag(int L, double dtp, const double
         if (threadIdx.x == 0) f[b * (long long)L] = 0.0;
         return;
     }
-    const double tau = tau_[b], D = D_[b], bbar = bbar_[b], phi = phi_[b];
+    const double tau = fext ? 1.0 : tau_[b], D = fext ? 1.0 : D_[b], bbar = bbar_[b], phi = phi_[b];
     const double D_o = (2.3e-9) * 60 * 60 * 24 * 365;                        // :244
     const double kappa = phi * sqrt((D_o * (phi * phi)) * 1);                // :247
     const double T = (double)i + dtp;
@@ -611,7 +627,9 @@ __global__ void __launch_bounds__(128) k_fdm_lag(int L, double dtp, const double
         double tadv = exp10(y);
         double x = tadv / tau;
         double om = 1. - x;
-        double fadv = ((1. / tau) / (sqrt(4. * 3.14159265358979323846 * D * x))) * (1. / x) * exp(-1. * ((om * om) / (4. * D * x)));   // :34
+        double fadv;
+        if (fext) fadv = fdm_interp(tadv, fext, i + 1, dtp);                                                                           // :88
+        else fadv = ((1. / tau) / (sqrt(4. * 3.14159265358979323846 * D * x))) * (1. / x) * exp(-1. * ((om * om) / (4. * D * x)));     // :34
         double tret = T - tadv;
         double Beta = tadv / bbar;
         double fret = (kappa * Beta) / (2 * sqrt(3.14159265358979323846) * pow(tret, 1.5)) *
@@ -663,7 +681,20 @@ extern "C" int ngrtd_rtd_weights_fdm_dev(int32_t L, double dtp, const double* ta
     if (B <= 0) return B == 0 ? NGRTD_OK : fail(NGRTD_EINVAL, "B < 0");
     if (B > 65535) return fail(NGRTD_EINVAL, "rtd_weights_fdm: at most 65,535 parameter sets per call");
     cudaStream_t st = (cudaStream_t)stream;
-    k_fdm_lag<<<dim3((unsigned)L, (unsigned)B), 128, 0, st>>>(L, dtp, tau_d, D_d, bbar_d, phi_d, g_d);
+    k_fdm_lag<<<dim3((unsigned)L, (unsigned)B), 128, 0, st>>>(L, dtp, tau_d, D_d, bbar_d, phi_d, nullptr, g_d);
+    CUDA_TRY(cudaGetLastError());
+    k_fdm_post<<<(unsigned)B, 256, 0, st>>>(L, dtp, g_d, fm_mu_d);
+    CUDA_TRY(cudaGetLastError());
+    return NGRTD_OK;
+}
+
+extern "C" int ngrtd_rtd_weights_fdm_ext_dev(int32_t L, double dtp, const double* f_tadv_ext_d, const double* bbar_d,
+                                             const double* phi_d, int64_t B, double* g_d, double* fm_mu_d, void* stream) {
+    if (L < 2 || !f_tadv_ext_d || !bbar_d || !phi_d || !g_d) return fail(NGRTD_EINVAL, "rtd_weights_fdm_ext: bad arguments");
+    if (B <= 0) return B == 0 ? NGRTD_OK : fail(NGRTD_EINVAL, "B < 0");
+    if (B > 65535) return fail(NGRTD_EINVAL, "rtd_weights_fdm_ext: at most 65,535 parameter sets per call");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_fdm_lag<<<dim3((unsigned)L, (unsigned)B), 128, 0, st>>>(L, dtp, nullptr, nullptr, bbar_d, phi_d, f_tadv_ext_d, g_d);
     CUDA_TRY(cudaGetLastError());
     k_fdm_post<<<(unsigned)B, 256, 0, st>>>(L, dtp, g_d, fm_mu_d);
     CUDA_TRY(cudaGetLastError());

@@ -88,6 +88,31 @@ def ess_mean(a):
     return _ess_raw(_split(np.asarray(a, dtype=np.float64)))
 
 
+def ess_tail(a):
+    """min of the ESS of the 5 % and 95 % quantile indicators (ArviZ `_ess_tail`)."""
+    a = np.asarray(a, dtype=np.float64)
+    out = []
+    for q in (0.05, 0.95):
+        ind = (a <= np.quantile(a, q)).astype(np.float64)
+        out.append(_ess_raw(_split(ind)))
+    return float(min(out))
+
+
+def ess_sd(a):
+    """ArviZ 0.11 `_ess_sd`: min of the ESS of x and of x^2 on split chains."""
+    s = _split(np.asarray(a, dtype=np.float64))
+    return float(min(_ess_raw(s), _ess_raw(s ** 2)))
+
+
+def mcse_sd(a):
+    """ArviZ 0.11 `_mcse_sd`: sd * sqrt(e (1 - 1/ess)^(ess-1) - 1) with ess = ess_sd."""
+    a = np.asarray(a, dtype=np.float64)
+    e = ess_sd(a)
+    if not (e == e) or e <= 1.0:
+        return float("nan")
+    return float(a.std(ddof=1) * np.sqrt(np.exp(1.0) * (1.0 - 1.0 / e) ** (e - 1.0) - 1.0))
+
+
 def hdi(x, prob=0.94):
     x = np.sort(np.asarray(x, dtype=np.float64).ravel())
     n = len(x)
@@ -97,8 +122,21 @@ def hdi(x, prob=0.94):
     return float(x[i]), float(x[i + k])
 
 
+SUMMARY_COLUMNS = ("mean", "sd", "hdi_3%", "hdi_97%", "mcse_mean", "mcse_sd", "ess_bulk", "ess_tail", "r_hat", "median")
+
+
+def summary_csv(path, posterior):
+    """Write `summary(posterior)` as a CSV laid out like ng_interp/ng_optPLM1.csv (first column = variable name)."""
+    rows = summary(posterior)
+    with open(path, "w") as f:
+        f.write("," + ",".join(SUMMARY_COLUMNS) + "\n")
+        for k, r in rows.items():
+            f.write(k + "," + ",".join(repr(float(r[c])) for c in SUMMARY_COLUMNS) + "\n")
+
+
 def summary(posterior):
-    """posterior: dict var -> array [chain, draw].  Returns dict var -> row with the az.summary columns + median."""
+    """posterior: dict var -> array [chain, draw].  Returns dict var -> row with the columns of the reference's summary
+    tables (ng_interp/ng_optPLM*.csv: az.summary + median), in the same order (SUMMARY_COLUMNS)."""
     out = {}
     for k, a in posterior.items():
         a = np.asarray(a, dtype=np.float64)
@@ -106,8 +144,8 @@ def summary(posterior):
         em = ess_mean(a)
         lo, hi = hdi(a)
         out[k] = {"mean": float(a.mean()), "sd": float(sd), "hdi_3%": lo, "hdi_97%": hi,
-                  "mcse_mean": float(sd / np.sqrt(em)) if em == em and em > 0 else float("nan"),
-                  "ess_bulk": ess_bulk(a), "r_hat": rhat(a), "median": float(np.median(a))}
+                  "mcse_mean": float(sd / np.sqrt(em)) if em == em and em > 0 else float("nan"), "mcse_sd": mcse_sd(a),
+                  "ess_bulk": ess_bulk(a), "ess_tail": ess_tail(a), "r_hat": rhat(a), "median": float(np.median(a))}
     return out
 
 

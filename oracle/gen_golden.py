@@ -221,6 +221,20 @@ def main():
             out[key + "/C"] = np.array(m.convolve())
         out[key + "/par"] = np.array([kw["tau"], kw["D"], kw["bbar"], kw["Phi_im"]])
     out["c12_500"] = c500.to_numpy().ravel()[::-1].copy()
+    # external advective RTD (frac_rtd_numba, :66-97): a gamma-shaped and a dispersion-shaped RTD on the yearly lag grid
+    tpe = np.arange(500, dtype=float)
+    ext = {"d": tpe * np.exp(-tpe / 15.0), "e": np.where(tpe > 0, np.exp(-(1 - np.maximum(tpe, 1e-9) / 40.0) ** 2 / (4 * 0.2 * np.maximum(tpe, 1e-9) / 40.0))
+                                                         / np.maximum(tpe, 1e-9) ** 1.5, 0.0)}
+    for key, kw in (("d", dict(bbar=1e-3, Phi_im=0.02)), ("e", dict(bbar=5e-4, Phi_im=0.05))):
+        fe = ext[key] / ext[key].sum()
+        m = conv.tracer_conv_integral(c500.copy(), c500.index[-1])
+        m.update_pars(mod_type="frac_inf_diff", t_half=25.0, f_tadv_ext=fe, **kw)
+        with np.errstate(all="ignore"):
+            out[key + "/g"] = m.gen_g_tp()
+            out[key + "/FM_mu"] = np.array(m.FM_mu)
+            out[key + "/C"] = np.array(m.convolve())
+        out[key + "/par"] = np.array([kw["bbar"], kw["Phi_im"]])
+        out[key + "/f_tadv_ext"] = fe
     np.savez_compressed(os.path.join(GOLD, "fdm_weights.npz"), **out)
 
     # ---- CFC / SF6 corrections (utils/cfc_utils.py), SURVEY 8f-2 ----

@@ -225,3 +225,14 @@ def test_frac_inf_diff_dropin_golden():
     m.D, m.bbar, m.Phi_im = np.array([0.3, 0.05]), np.array([1e-3, 5e-4]), np.array([0.02, 0.05])
     out = m.convolve()
     assert out.shape == (2,) and abs(out[0] - float(z["a/C"])) < 1e-10 * out[0] and abs(out[1] - float(z["b/C"])) < 1e-10 * out[1]
+    for k in "de":                                        # caller-supplied advective RTD (frac_rtd_numba, :66-97)
+        bbar, phi = z[k + "/par"]
+        m = tracer_conv_integral(c12.copy(), c12.index[-1])
+        m.update_pars(mod_type="frac_inf_diff", t_half=25.0, bbar=bbar, Phi_im=phi, f_tadv_ext=z[k + "/f_tadv_ext"])
+        g = m.gen_g_tp()
+        assert rel_err(g, z[k + "/g"]) < 1e-10, k
+        assert abs(m.FM_mu - float(z[k + "/FM_mu"])) < 1e-10 * m.FM_mu
+        assert abs(m.convolve() - float(z[k + "/C"])) < 1e-10 * abs(float(z[k + "/C"]))
+    with pytest.raises(ValueError):
+        m.update_pars(mod_type="frac_inf_diff", bbar=1e-3, Phi_im=0.02, f_tadv_ext=np.ones(7))
+        m.gen_g_tp()

@@ -246,3 +246,10 @@ def test_frac_inf_diff_weights_golden():
         C = O.convolve(z["c12_500"], tp, g.reshape(1, -1), O.thalf_2_lambda(25.0))[0]
         assert abs(C - float(z[k + "/C"])) < 1e-12 * abs(C)
     assert abs(float(z["a/FM_mu"]) - 86.31699496976702) < 1e-11
+    for k in "de":                                          # caller-supplied advective RTD (frac_rtd_numba, :66-97)
+        bbar, phi = z[k + "/par"]
+        g, mu = O.frac_inf_diff_weights(tp, None, None, bbar, phi, f_tadv_ext=z[k + "/f_tadv_ext"])
+        assert rel_err(g, z[k + "/g"]) < 1e-12, k
+        assert abs(mu - float(z[k + "/FM_mu"])) < 1e-12 * mu
+        C = O.convolve(z["c12_500"], tp, g.reshape(1, -1), O.thalf_2_lambda(25.0))[0]
+        assert abs(C - float(z[k + "/C"])) < 1e-12 * abs(C)

@@ -142,3 +142,29 @@ def test_trace_npz_roundtrip(tmp_path):
     assert np.allclose(dg.summary(tr["posterior"])["tau1"]["mean"], post["tau1"].mean())
     with pytest.raises(ValueError):
         dg.save_trace(tmp_path / "bad.npz", {"x": np.zeros(5)})
+
+
+def test_summary_columns_match_reference_tables(tmp_path):
+    """diagnostics.summary carries the columns of the reference's ng_optPLM*.csv (az.summary + median), in order; for
+    iid draws ESS ~ N and MCSE follow their textbook values."""
+    from noblegas_rtd_mcmc_b200 import diagnostics as dg
+    assert dg.SUMMARY_COLUMNS == ("mean", "sd", "hdi_3%", "hdi_97%", "mcse_mean", "mcse_sd", "ess_bulk", "ess_tail", "r_hat", "median")
+    rng = np.random.default_rng(11)
+    x = rng.normal(3.0, 2.0, size=(4, 2500))
+    row = dg.summary({"x": x})["x"]
+    assert tuple(row) == dg.SUMMARY_COLUMNS
+    n = x.size
+    assert 0.7 * n < row["ess_bulk"] < 1.3 * n and 0.6 * n < row["ess_tail"] < 1.4 * n
+    assert abs(row["mcse_mean"] / (2.0 / np.sqrt(n)) - 1) < 0.2
+    assert abs(row["mcse_sd"] / (2.0 / np.sqrt(2 * n)) - 1) < 0.35
+    assert abs(row["r_hat"] - 1) < 0.01
+    # an AR(1) chain has far fewer effective draws
+    y = np.zeros((4, 2500))
+    e = rng.normal(size=y.shape)
+    for t in range(1, y.shape[1]):
+        y[:, t] = 0.9 * y[:, t - 1] + e[:, t]
+    r2 = dg.summary({"y": y})["y"]
+    assert r2["ess_bulk"] < 0.15 * n and r2["ess_tail"] < 0.5 * n
+    dg.summary_csv(tmp_path / "s.csv", {"x": x})
+    head = open(tmp_path / "s.csv").readline().strip()
+    assert head == ",mean,sd,hdi_3%,hdi_97%,mcse_mean,mcse_sd,ess_bulk,ess_tail,r_hat,median"
