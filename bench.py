@@ -62,11 +62,12 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_indices):
+        """gpu_indices: "0" or "0,1,...": rank 0 samples every GPU of the job (one nvidia-smi process per node)."""
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_indices), "--query-gpu=" + self.Q,
                                        "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
@@ -83,13 +84,14 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, per_gpu = [], [], set(), {}
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
             try:
                 sm.append(float(c[1])); mx.append(float(c[2]))
+                per_gpu.setdefault(c[0], []).append(float(c[1]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
@@ -103,6 +105,8 @@ class ClockSampler:
         if sm:
             load = [s for s in sm if s > 0.5 * max(mx)] or sm
             out.update(sm_mhz=float(np.median(load)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            if len(per_gpu) > 1:      # median under load of every GPU of the job: a slow rank shows up here
+                out["sm_mhz_per_gpu"] = {g: float(np.median([s for s in v if s > 0.5 * max(mx)] or v)) for g, v in sorted(per_gpu.items())}
         return out
 
 
@@ -202,9 +206,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(",".join(str(i) for i in range(world)) if world > 1 else local) if rank == 0 else None
     for i in range(args.warmup):
         step(i)
+    if world > 1:
+        # ranks reach this point at different times (plan build, NCCL init): align them once, warm up again, and only
+        # then take the bracketing barrier -- its wait is then short and no GPU idles (and down-clocks) before step 0
+        barrier()
+        for i in range(args.warmup):
+            step(i)
     barrier()
     # ---- timed region: K steps, per-launch CUDA events on the launching stream ----
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -222,13 +232,17 @@ def main():
     # keep the GPU under the same load long enough for nvidia-smi to see the clocks of this kernel
     t_probe = time.perf_counter()
     i = 0
-    while rank == 0 and time.perf_counter() - t_probe < 1.0:
+    while time.perf_counter() - t_probe < 1.0:          # every rank: rank 0's nvidia-smi samples all GPUs of the job
         for _ in range(50):
             step(i); i += 1
         torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
+    per_rank = None
     if world > 1:
         t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [round(float(x[0]) / args.steps, 5) for x in allt]       # ms per step of every rank (the max is reported)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, kern_ms = float(t[0]), float(t[1])
     value = world * B * T_COUNTED * args.steps / (total_ms * 1e-3)
@@ -331,7 +345,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * len(pn) * 8, "d2h_bytes_per_step": B * 8,
                         "ms_per_step": 1e3 * e2e_s / args.steps},
                 "gpu_launches": args.steps,
-                "clocks": clocks,
+                "clocks": clocks, "per_rank_ms_per_step": per_rank,
                 "roofline": {"bound": "tensor", "pipe": "fp64: DMMA.8x8x4 (tensor sub-pipe) shares the FP64 pipe with DFMA",
                              "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                              "frac": achieved / FP64_PEAK_TFLOPS, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
