@@ -343,7 +343,9 @@ def main():
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * len(pn) * 8, "d2h_bytes_per_step": B * 8,
-                        "ms_per_step": 1e3 * e2e_s / args.steps},
+                        "ms_per_step": 1e3 * e2e_s / args.steps,
+                        "transport": "pinned host theta read by the kernel over PCIe (one TMA bulk copy per 16-chain unit, "
+                                     "next unit prefetched); logp stored straight into the pinned host buffer"},
                 "gpu_launches": args.steps,
                 "clocks": clocks, "per_rank_ms_per_step": per_rank,
                 "roofline": {"bound": "tensor", "pipe": "fp64: DMMA.8x8x4 (tensor sub-pipe) shares the FP64 pipe with DFMA",

@@ -106,7 +106,7 @@ def hptr(a):
     if a is None:
         return None
     assert a.flags["C_CONTIGUOUS"]
-    return a.ctypes.data_as(ctypes.c_void_p)
+    return ctypes.c_void_p(a.ctypes.data)
 
 
 def f64(a):
@@ -117,11 +117,20 @@ def i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
+_SLOT_ARRAYS = {}
+
+
 def slot_array(par_names):
-    try:
-        return i32([SLOT[p] for p in par_names])
-    except KeyError as e:
-        raise ValueError("unknown parameter name %s (known: %s)" % (e, sorted(SLOT)))
+    key = tuple(par_names)
+    a = _SLOT_ARRAYS.get(key)
+    if a is None:
+        try:
+            a = i32([SLOT[p] for p in key])
+        except KeyError as e:
+            raise ValueError("unknown parameter name %s (known: %s)" % (e, sorted(SLOT)))
+        a.setflags(write=False)
+        _SLOT_ARRAYS[key] = a
+    return a
 
 
 def stream_ptr(stream=None):

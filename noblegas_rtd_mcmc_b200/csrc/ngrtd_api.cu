@@ -2,6 +2,7 @@
 // No torch types anywhere; device pointers and a stream handle come from the caller.
 #include "../../include/ngrtd.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -29,6 +30,11 @@ static int fail(int code, const std::string& msg) {
             return fail(NGRTD_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e__));               \
     } while (0)
 
+constexpr int HOST_PARTS_MAX = 8;
+#ifndef NGRTD_STAGE_DEFAULT
+#define NGRTD_STAGE_DEFAULT 0
+#endif
+
 struct ngrtd_plan {
     int device = 0;
     int nsm = 0;
@@ -41,7 +47,9 @@ struct ngrtd_plan {
     // workspace of the *_host entry points
     double *w_theta = nullptr, *w_out = nullptr, *w_logp = nullptr, *w_nu = nullptr;
     size_t w_theta_n = 0, w_out_n = 0, w_logp_n = 0, w_nu_n = 0;
-    cudaStream_t hstream = nullptr, hstream2 = nullptr;
+    // host-buffer pipeline: copy-in stream, compute stream, copy-out stream + one event pair per part
+    cudaStream_t hstream = nullptr, hstream2 = nullptr, hstream3 = nullptr;
+    cudaEvent_t ev_in[HOST_PARTS_MAX] = {}, ev_k[HOST_PARTS_MAX] = {};
 };
 
 static int cls_of(int mod) {
@@ -230,7 +238,16 @@ extern "C" int ngrtd_plan_create(ngrtd_plan** out, int32_t L, int32_t nseries, c
         (e = up(&P->ditp, itp)) != cudaSuccess || (e = up(&P->dxraw, xraw)) != cudaSuccess ||
         (e = up(&P->dxrawd, xrawd)) != cudaSuccess || (e = up(&P->dtbl, tbl)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&P->hstream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&P->hstream2, cudaStreamNonBlocking)) != cudaSuccess) {
+        (e = cudaStreamCreateWithFlags(&P->hstream2, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&P->hstream3, cudaStreamNonBlocking)) != cudaSuccess) {
+        ngrtd_plan_destroy(P);
+        return fail(NGRTD_ECUDA, std::string("plan upload: ") + cudaGetErrorString(e));
+    }
+    for (int i = 0; i < HOST_PARTS_MAX && e == cudaSuccess; i++) {
+        e = cudaEventCreateWithFlags(&P->ev_in[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&P->ev_k[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
         ngrtd_plan_destroy(P);
         return fail(NGRTD_ECUDA, std::string("plan upload: ") + cudaGetErrorString(e));
     }
@@ -259,6 +276,11 @@ extern "C" int ngrtd_plan_destroy(ngrtd_plan* P) {
     cudaFree(P->w_theta); cudaFree(P->w_out); cudaFree(P->w_logp); cudaFree(P->w_nu);
     if (P->hstream) cudaStreamDestroy(P->hstream);
     if (P->hstream2) cudaStreamDestroy(P->hstream2);
+    if (P->hstream3) cudaStreamDestroy(P->hstream3);
+    for (int i = 0; i < HOST_PARTS_MAX; i++) {
+        if (P->ev_in[i]) cudaEventDestroy(P->ev_in[i]);
+        if (P->ev_k[i]) cudaEventDestroy(P->ev_k[i]);
+    }
     delete P;
     return NGRTD_OK;
 }
@@ -285,7 +307,7 @@ static int pick_warps(long long nunits, int nsm, int maxw) {
 
 template <int C1, int C2, bool DYN, int NT, int UA, int MAXW>
 static int launch_forward_t(ngrtd_plan* P, const SlotMap& sm, const double* theta, long long B, double* out,
-                            double* logp, const LikPar& lik, cudaStream_t st, int warps_req) {
+                            double* logp, const LikPar& lik, cudaStream_t st, int stage, int warps_req) {
     using WT = WarpTiles<C1, C2, DYN, NT, UA>;
     const int Lloop = (WT::ANY_G && !WT::ANY_D && P->pv.Kc < P->pv.L) ? P->pv.Kc : P->Lpad;
     int lc_cap = WT::ANY_LOOP ? std::min(Lloop, LC_MAX) : 0;
@@ -296,6 +318,8 @@ static int launch_forward_t(ngrtd_plan* P, const SlotMap& sm, const double* thet
     sh += (size_t)lc_cap * NCOL;
     if (WT::ANY_D) sh += (size_t)lc_cap * NCOL + 2 * (size_t)lc_cap;
     if (DYN) sh += lc_cap + (WT::ANY_D ? lc_cap : 0);
+    if (sm.ndim > NSLOT) stage = 0;                                  // staging slots are sized for <= NSLOT columns
+    if (stage) sh = ((sh + 1) & ~(size_t)1) + (size_t)warps * (NT * 8 * sm.ndim + 1) + 1;
     sh *= sizeof(double);
     auto kern = k_forward<C1, C2, DYN, NT, UA, MAXW>;
     static thread_local size_t configured = 0;
@@ -306,7 +330,7 @@ static int launch_forward_t(ngrtd_plan* P, const SlotMap& sm, const double* thet
     long long want = (nunits + warps - 1) / warps;
     int grid = (int)std::min<long long>(want, P->nsm);
     if (grid < 1) grid = 1;
-    kern<<<grid, warps * 32, sh, st>>>(P->pv, sm, theta, B, out, logp, lik, lc_cap);
+    kern<<<grid, warps * 32, sh, st>>>(P->pv, sm, theta, B, out, logp, lik, lc_cap, stage);
     CUDA_TRY(cudaGetLastError());
     return NGRTD_OK;
 }
@@ -318,36 +342,36 @@ constexpr int FWD_NT = 2, FWD_UA = 1, FWD_MAXW = NGRTD_FWD_MAXW;
 
 template <int C1, int C2, bool DYN>
 static int launch_forward(ngrtd_plan* P, const SlotMap& sm, const double* theta, long long B, double* out,
-                          double* logp, const LikPar& lik, cudaStream_t st) {
+                          double* logp, const LikPar& lik, cudaStream_t st, int stage) {
     FwdTune t = env_tune();
 #ifdef NGRTD_TUNE
     // development build: every (NT, UA) variant of the looped kernels is compiled and selectable by env var
     if constexpr (!DYN && C1 != CLS_P && C2 != CLS_P) {
         int mw = (t.warps > 16) ? 24 : (t.warps > 8) ? 16 : 8;
 #define NGRTD_VARIANT(NT_, UA_, MW_) \
-        if (t.nt == NT_ && t.ua == UA_ && mw == MW_) return launch_forward_t<C1, C2, DYN, NT_, UA_, MW_>(P, sm, theta, B, out, logp, lik, st, t.warps);
+        if (t.nt == NT_ && t.ua == UA_ && mw == MW_) return launch_forward_t<C1, C2, DYN, NT_, UA_, MW_>(P, sm, theta, B, out, logp, lik, st, stage, t.warps);
         NGRTD_VARIANT(1, 2, 8) NGRTD_VARIANT(2, 1, 8) NGRTD_VARIANT(2, 2, 8) NGRTD_VARIANT(4, 1, 8)
         NGRTD_VARIANT(1, 1, 16) NGRTD_VARIANT(1, 2, 16) NGRTD_VARIANT(2, 2, 16) NGRTD_VARIANT(3, 1, 16)
         NGRTD_VARIANT(1, 1, 24) NGRTD_VARIANT(2, 1, 24)
 #undef NGRTD_VARIANT
     }
 #endif
-    return launch_forward_t<C1, C2, DYN, FWD_NT, FWD_UA, FWD_MAXW>(P, sm, theta, B, out, logp, lik, st, t.warps);
+    return launch_forward_t<C1, C2, DYN, FWD_NT, FWD_UA, FWD_MAXW>(P, sm, theta, B, out, logp, lik, st, stage, t.warps);
 }
 
 template <int C1, bool DYN>
 static int dispatch_c2(ngrtd_plan* P, const SlotMap& sm, const double* theta, long long B, double* out, double* logp,
-                       const LikPar& lik, cudaStream_t st) {
+                       const LikPar& lik, cudaStream_t st, int stage) {
 #ifdef NGRTD_EXP   /* timing-experiment build: only the three looped kernels of the benchmark */
-    if (P->cls2 == CLS_NONE) return launch_forward<C1, CLS_NONE, DYN>(P, sm, theta, B, out, logp, lik, st);
-    if constexpr (C1 == CLS_G) if (P->cls2 == CLS_D) return launch_forward<C1, CLS_D, DYN>(P, sm, theta, B, out, logp, lik, st);
+    if (P->cls2 == CLS_NONE) return launch_forward<C1, CLS_NONE, DYN>(P, sm, theta, B, out, logp, lik, st, stage);
+    if constexpr (C1 == CLS_G) if (P->cls2 == CLS_D) return launch_forward<C1, CLS_D, DYN>(P, sm, theta, B, out, logp, lik, st, stage);
     return fail(NGRTD_EINVAL, "experiment build: model pair not compiled");
 #else
     switch (P->cls2) {
-        case CLS_NONE: return launch_forward<C1, CLS_NONE, DYN>(P, sm, theta, B, out, logp, lik, st);
-        case CLS_P: return launch_forward<C1, CLS_P, DYN>(P, sm, theta, B, out, logp, lik, st);
-        case CLS_G: return launch_forward<C1, CLS_G, DYN>(P, sm, theta, B, out, logp, lik, st);
-        case CLS_D: return launch_forward<C1, CLS_D, DYN>(P, sm, theta, B, out, logp, lik, st);
+        case CLS_NONE: return launch_forward<C1, CLS_NONE, DYN>(P, sm, theta, B, out, logp, lik, st, stage);
+        case CLS_P: return launch_forward<C1, CLS_P, DYN>(P, sm, theta, B, out, logp, lik, st, stage);
+        case CLS_G: return launch_forward<C1, CLS_G, DYN>(P, sm, theta, B, out, logp, lik, st, stage);
+        case CLS_D: return launch_forward<C1, CLS_D, DYN>(P, sm, theta, B, out, logp, lik, st, stage);
     }
     return fail(NGRTD_EINVAL, "bad model class");
 #endif
@@ -355,15 +379,15 @@ static int dispatch_c2(ngrtd_plan* P, const SlotMap& sm, const double* theta, lo
 
 template <bool DYN>
 static int dispatch_c1(ngrtd_plan* P, const SlotMap& sm, const double* theta, long long B, double* out, double* logp,
-                       const LikPar& lik, cudaStream_t st) {
+                       const LikPar& lik, cudaStream_t st, int stage) {
     switch (P->cls1) {
 #ifdef NGRTD_EXP
         case CLS_P: return fail(NGRTD_EINVAL, "experiment build: model pair not compiled");
 #else
-        case CLS_P: return dispatch_c2<CLS_P, DYN>(P, sm, theta, B, out, logp, lik, st);
+        case CLS_P: return dispatch_c2<CLS_P, DYN>(P, sm, theta, B, out, logp, lik, st, stage);
 #endif
-        case CLS_G: return dispatch_c2<CLS_G, DYN>(P, sm, theta, B, out, logp, lik, st);
-        case CLS_D: return dispatch_c2<CLS_D, DYN>(P, sm, theta, B, out, logp, lik, st);
+        case CLS_G: return dispatch_c2<CLS_G, DYN>(P, sm, theta, B, out, logp, lik, st, stage);
+        case CLS_D: return dispatch_c2<CLS_D, DYN>(P, sm, theta, B, out, logp, lik, st, stage);
     }
     return fail(NGRTD_EINVAL, "bad model class");
 }
@@ -383,7 +407,7 @@ static int make_slotmap(SlotMap& sm, int ndim, const int32_t* slot_of_col, bool 
 }
 
 static int forward_common(ngrtd_plan* P, const double* theta, long long B, int ndim, const int32_t* slot_of_col,
-                          double* out, double* logp, const LikPar& lik, cudaStream_t st) {
+                          double* out, double* logp, const LikPar& lik, cudaStream_t st, int stage) {
     if (!P) return fail(NGRTD_EINVAL, "null plan");
     if (B < 0) return fail(NGRTD_EINVAL, "B < 0");
     if (B == 0) return NGRTD_OK;
@@ -394,17 +418,29 @@ static int forward_common(ngrtd_plan* P, const double* theta, long long B, int n
     // the per-chain-lambda path is only needed when thalf_cfc is actually sampled (run_age_mcmc_utils.py:107:
     // `'thalf_cfc' in self.p_names`); otherwise those tracers fall back to lambda = 0 through the same path.
 #ifndef NGRTD_EXP
-    if (P->dyn) return dispatch_c1<true>(P, sm, theta, B, out, logp, lik, st);
+    if (P->dyn) return dispatch_c1<true>(P, sm, theta, B, out, logp, lik, st, stage);
 #endif
-    return dispatch_c1<false>(P, sm, theta, B, out, logp, lik, st);
+    return dispatch_c1<false>(P, sm, theta, B, out, logp, lik, st, stage);
+}
+
+// Parameter staging mode of k_forward: 0 = per-lane global loads, 1 = TMA bulk copy per unit with prefetch of the next
+// unit, 2 = staged with plain lane loads (see k_forward).  NGRTD_STAGE overrides (development / A-B measurements).
+static int default_stage() {
+    const char* e = getenv("NGRTD_STAGE");
+    return e ? atoi(e) : NGRTD_STAGE_DEFAULT;
+}
+
+static int forward_dev_stage(ngrtd_plan* P, const double* theta_d, int64_t B, int32_t ndim, const int32_t* slot_of_col,
+                             double* out_d, void* stream, int stage) {
+    if (!out_d) return fail(NGRTD_EINVAL, "out is null");
+    LikPar lik{};
+    lik.kind = -1;
+    return forward_common(P, theta_d, B, ndim, slot_of_col, out_d, nullptr, lik, (cudaStream_t)stream, stage);
 }
 
 extern "C" int ngrtd_forward_dev(ngrtd_plan* P, const double* theta_d, int64_t B, int32_t ndim,
                                  const int32_t* slot_of_col, double* out_d, void* stream) {
-    if (!out_d) return fail(NGRTD_EINVAL, "out is null");
-    LikPar lik{};
-    lik.kind = -1;
-    return forward_common(P, theta_d, B, ndim, slot_of_col, out_d, nullptr, lik, (cudaStream_t)stream);
+    return forward_dev_stage(P, theta_d, B, ndim, slot_of_col, out_d, stream, default_stage());
 }
 
 static int fill_lik(LikPar& lik, const ngrtd_plan* P, int kind, const double* obs_mu, const double* obs_sd,
@@ -423,16 +459,24 @@ static int fill_lik(LikPar& lik, const ngrtd_plan* P, int kind, const double* ob
     return NGRTD_OK;
 }
 
-extern "C" int ngrtd_forward_loglik_dev(ngrtd_plan* P, const double* theta_d, int64_t B, int32_t ndim,
-                                        const int32_t* slot_of_col, int32_t lik_kind, const double* obs_mu,
-                                        const double* obs_sd, const double* nu_d, double* logp_d,
-                                        double* model_out_d, void* stream) {
+static int forward_loglik_dev_stage(ngrtd_plan* P, const double* theta_d, int64_t B, int32_t ndim,
+                                    const int32_t* slot_of_col, int32_t lik_kind, const double* obs_mu,
+                                    const double* obs_sd, const double* nu_d, double* logp_d, double* model_out_d,
+                                    void* stream, int stage) {
     if (!P) return fail(NGRTD_EINVAL, "null plan");
     if (!logp_d) return fail(NGRTD_EINVAL, "logp is null");
     LikPar lik{};
     int rc = fill_lik(lik, P, lik_kind, obs_mu, obs_sd, nu_d);
     if (rc) return rc;
-    return forward_common(P, theta_d, B, ndim, slot_of_col, model_out_d, logp_d, lik, (cudaStream_t)stream);
+    return forward_common(P, theta_d, B, ndim, slot_of_col, model_out_d, logp_d, lik, (cudaStream_t)stream, stage);
+}
+
+extern "C" int ngrtd_forward_loglik_dev(ngrtd_plan* P, const double* theta_d, int64_t B, int32_t ndim,
+                                        const int32_t* slot_of_col, int32_t lik_kind, const double* obs_mu,
+                                        const double* obs_sd, const double* nu_d, double* logp_d,
+                                        double* model_out_d, void* stream) {
+    return forward_loglik_dev_stage(P, theta_d, B, ndim, slot_of_col, lik_kind, obs_mu, obs_sd, nu_d, logp_d, model_out_d,
+                                    stream, default_stage());
 }
 
 static int grow(double** p, size_t* have, size_t need) {
@@ -450,6 +494,15 @@ static int grow(double** p, size_t* have, size_t need) {
 // half and the device->host copy of the first overlap with the kernels (the copies are ~40 % of a serial call at the
 // cfg-3 batch: 3.7 MB in, 0.5 MB out over PCIe against a 0.12 ms kernel).  Pinned host memory is needed for the overlap;
 // pageable buffers still work (the runtime stages them).
+// device-visible alias of a pinned / registered host pointer (UVA), or nullptr for pageable memory
+static const double* mapped_host_ptr(const double* h) {
+    if (!h) return nullptr;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+    return static_cast<const double*>(a.devicePointer);
+}
+
 static int forward_host_common(ngrtd_plan* P, const double* theta_h, int64_t B, int32_t ndim, const int32_t* slot_of_col,
                                int want_lik, int32_t lik_kind, const double* obs_mu, const double* obs_sd,
                                const double* nu_h, double* logp_h, double* model_out_h) {
@@ -459,36 +512,80 @@ static int forward_host_common(ngrtd_plan* P, const double* theta_h, int64_t B, 
     CUDA_TRY(cudaSetDevice(P->device));
     const int nt = P->pv.ntracer;
     int rc;
+    const bool need_nu = want_lik && lik_kind == NGRTD_LIK_STUDENTT;
+    if (need_nu && !nu_h) return fail(NGRTD_EINVAL, "student-t needs nu");
+    // ---- zero-copy mode: pinned (page-locked, mapped) host buffers are handed to ONE kernel launch directly.  The
+    // kernel pulls each unit's parameter rows over PCIe with a TMA bulk copy (prefetching the next unit under the
+    // current one) and writes logp straight into the caller's buffer, so there is no staged copy in front of the first
+    // unit or behind the last one.  model_out (scattered 8-byte stores) still goes through a device buffer.
+    {
+        const char* mode_s = getenv("NGRTD_HOST_MODE");
+        const bool allow_mapped = !(mode_s && strcmp(mode_s, "copy") == 0);
+        const double* theta_m = allow_mapped ? mapped_host_ptr(theta_h) : nullptr;
+        const double* nu_m = (allow_mapped && need_nu) ? mapped_host_ptr(nu_h) : nullptr;
+        if (theta_m && ndim <= NSLOT && (!need_nu || nu_m)) {
+            double* logp_m = want_lik ? const_cast<double*>(mapped_host_ptr(logp_h)) : nullptr;
+            if (want_lik && !logp_m && (rc = grow(&P->w_logp, &P->w_logp_n, (size_t)B))) return rc;
+            if (model_out_h && (rc = grow(&P->w_out, &P->w_out_n, (size_t)B * nt))) return rc;
+            cudaStream_t st = P->hstream2;
+            const char* stg_s = getenv("NGRTD_STAGE_MAPPED");
+            const int stg = stg_s ? atoi(stg_s) : 1;
+            if (want_lik)
+                rc = forward_loglik_dev_stage(P, theta_m, B, ndim, slot_of_col, lik_kind, obs_mu, obs_sd, nu_m,
+                                              logp_m ? logp_m : P->w_logp, model_out_h ? P->w_out : nullptr, st, stg);
+            else
+                rc = forward_dev_stage(P, theta_m, B, ndim, slot_of_col, P->w_out, st, stg);
+            if (rc) return rc;
+            if (want_lik && !logp_m)
+                CUDA_TRY(cudaMemcpyAsync(logp_h, P->w_logp, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+            if (model_out_h)
+                CUDA_TRY(cudaMemcpyAsync(model_out_h, P->w_out, (size_t)B * nt * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            return NGRTD_OK;
+        }
+    }
     if ((rc = grow(&P->w_theta, &P->w_theta_n, (size_t)B * ndim))) return rc;
     if (want_lik && (rc = grow(&P->w_logp, &P->w_logp_n, (size_t)B))) return rc;
     if (model_out_h && (rc = grow(&P->w_out, &P->w_out_n, (size_t)B * nt))) return rc;
-    const bool need_nu = want_lik && lik_kind == NGRTD_LIK_STUDENTT;
-    if (need_nu) {
-        if (!nu_h) return fail(NGRTD_EINVAL, "student-t needs nu");
-        if ((rc = grow(&P->w_nu, &P->w_nu_n, (size_t)B))) return rc;
-    }
-    const int nparts = B >= 32768 ? 2 : 1;
-    const int64_t half = nparts == 2 ? ((B / 2 + 15) & ~15LL) : B;        // unit-aligned split
-    cudaStream_t streams[2] = {P->hstream, P->hstream2};
+    if (need_nu && (rc = grow(&P->w_nu, &P->w_nu_n, (size_t)B))) return rc;
+    // Pipeline: all parts are copied in back to back on the copy-in stream; the compute stream runs part c as soon as
+    // its event fires; the copy-out stream drains part c behind its kernel.  The copy engines and the SMs then work
+    // concurrently for all but the first copy-in and the last copy-out.  Parts are unit-aligned (16 chains).  Measured
+    // at the cfg-3 batch (65,536 chains): 1 part 0.226 ms, 2 parts 0.208, 4 parts 0.208, 6-8 parts 0.26-0.28 (a part
+    // below ~16k chains no longer fills the persistent grid of 2,368 warps x 16 chains).
+    const char* parts_s = getenv("NGRTD_HOST_PARTS");
+    const int parts_env = parts_s ? atoi(parts_s) : 0;
+    int nparts = parts_env > 0 ? parts_env : (int)std::min<int64_t>(2, B / 16384);
+    nparts = std::max(1, std::min(nparts, HOST_PARTS_MAX));
+    const int64_t part = nparts > 1 ? (((B + nparts - 1) / nparts + 15) & ~15LL) : B;
+    cudaStream_t s_in = P->hstream, s_k = P->hstream2, s_out = P->hstream3;
     for (int c = 0; c < nparts; c++) {
-        const int64_t b0 = c * half, n = (c == nparts - 1) ? B - b0 : half;
-        cudaStream_t st = streams[c];
+        const int64_t b0 = c * part, n = std::min<int64_t>(part, B - b0);
+        if (n <= 0) break;
         CUDA_TRY(cudaMemcpyAsync(P->w_theta + b0 * ndim, theta_h + b0 * ndim, (size_t)n * ndim * sizeof(double),
-                                 cudaMemcpyHostToDevice, st));
-        if (need_nu) CUDA_TRY(cudaMemcpyAsync(P->w_nu + b0, nu_h + b0, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+                                 cudaMemcpyHostToDevice, s_in));
+        if (need_nu) CUDA_TRY(cudaMemcpyAsync(P->w_nu + b0, nu_h + b0, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s_in));
+        CUDA_TRY(cudaEventRecord(P->ev_in[c], s_in));
+    }
+    for (int c = 0; c < nparts; c++) {
+        const int64_t b0 = c * part, n = std::min<int64_t>(part, B - b0);
+        if (n <= 0) break;
+        CUDA_TRY(cudaStreamWaitEvent(s_k, P->ev_in[c], 0));
         if (want_lik)
             rc = ngrtd_forward_loglik_dev(P, P->w_theta + b0 * ndim, n, ndim, slot_of_col, lik_kind, obs_mu, obs_sd,
                                           need_nu ? P->w_nu + b0 : nullptr, P->w_logp + b0,
-                                          model_out_h ? P->w_out + b0 * nt : nullptr, st);
+                                          model_out_h ? P->w_out + b0 * nt : nullptr, s_k);
         else
-            rc = ngrtd_forward_dev(P, P->w_theta + b0 * ndim, n, ndim, slot_of_col, P->w_out + b0 * nt, st);
+            rc = ngrtd_forward_dev(P, P->w_theta + b0 * ndim, n, ndim, slot_of_col, P->w_out + b0 * nt, s_k);
         if (rc) return rc;
-        if (want_lik) CUDA_TRY(cudaMemcpyAsync(logp_h + b0, P->w_logp + b0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaEventRecord(P->ev_k[c], s_k));
+        CUDA_TRY(cudaStreamWaitEvent(s_out, P->ev_k[c], 0));
+        if (want_lik) CUDA_TRY(cudaMemcpyAsync(logp_h + b0, P->w_logp + b0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s_out));
         if (model_out_h)
             CUDA_TRY(cudaMemcpyAsync(model_out_h + b0 * nt, P->w_out + b0 * nt, (size_t)n * nt * sizeof(double),
-                                     cudaMemcpyDeviceToHost, st));
+                                     cudaMemcpyDeviceToHost, s_out));
     }
-    for (int c = 0; c < nparts; c++) CUDA_TRY(cudaStreamSynchronize(streams[c]));
+    CUDA_TRY(cudaStreamSynchronize(s_out));    // the last copy-out is behind every kernel and every copy-in
     return NGRTD_OK;
 }
 

@@ -559,21 +559,27 @@ struct FwdCta {
         sched_i = lockstep ? (long long)blockIdx.x : (long long)(warp / (nwarps >= 4 ? 4 : nwarps));
         sched_update();
     }
-    __device__ __forceinline__ void sched_update() {
+    __device__ __forceinline__ long long unit_of(long long si) const {
         if (!lockstep) {
             const int spc = nwarps >= 4 ? 4 : nwarps;
-            unit = ((long long)blockIdx.x * spc + (warp % spc)) + sched_i * ((long long)gridDim.x * spc);
-            active = true;
-        } else {
-            unit = sched_i * nwarps + warp;
-            active = unit < sched_n;
+            return ((long long)blockIdx.x * spc + (warp % spc)) + si * ((long long)gridDim.x * spc);
         }
+        return si * nwarps + warp;
     }
+    __device__ __forceinline__ long long sched_step() const {
+        return lockstep ? (long long)gridDim.x : (long long)(nwarps / (nwarps >= 4 ? 4 : nwarps));
+    }
+    __device__ __forceinline__ void sched_update() {
+        unit = unit_of(sched_i);
+        active = lockstep ? unit < sched_n : true;
+    }
+    // the unit this warp will work on after the current one (>= sched_n: none) -- used to prefetch its parameters
+    __device__ __forceinline__ long long sched_peek() const { return unit_of(sched_i + sched_step()); }
     __device__ __forceinline__ bool sched_valid() const {
         return lockstep ? sched_i < (sched_n + nwarps - 1) / nwarps : unit < sched_n;
     }
     __device__ __forceinline__ void sched_next() {
-        sched_i += lockstep ? (long long)gridDim.x : (long long)(nwarps / (nwarps >= 4 ? 4 : nwarps));
+        sched_i += sched_step();
         sched_update();
     }
 };
@@ -601,12 +607,21 @@ __device__ __forceinline__ double lik_reduce(int kind, int ntracer, int j, const
 }
 
 // ---------------------------------------------------------------- the forward (+ likelihood) kernel
+// Parameter staging (stage != 0).  The parameter rows of a unit (NT*8 chains x ndim doubles, contiguous in theta) are
+// brought into a per-warp shared-memory slot by ONE TMA bulk copy issued by lane 0 against the warp's own mbarrier, and
+// the copy for the warp's NEXT unit is issued as soon as the current rows are in registers, so it has a whole unit
+// (~50 us) to land.  This makes theta traffic one large request per unit instead of 7-11 scattered 8-byte loads per lane,
+// which is what lets the *_host entry points hand the kernel a pointer to PINNED HOST memory (zero-copy over PCIe: the
+// first round of units streams in while the SMs start, the second round is prefetched under the first) instead of a
+// staged cudaMemcpyAsync.  Units whose byte count or source address is not a multiple of 16 (ragged last unit, odd
+// row offsets) are staged with plain lane loads.
 template <int C1, int C2, bool DYN, int NT, int UA, int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, 1)
 k_forward(PlanView pv, SlotMap sm, const double* __restrict__ theta, long long B, double* __restrict__ out,
-          double* __restrict__ logp, LikPar lik, int lc_cap) {
+          double* __restrict__ logp, LikPar lik, int lc_cap, int stage) {
     FwdCta<C1, C2, DYN, NT, UA> cta(pv);
-    cta.setup(lc_cap);
+    int p_end = cta.setup(lc_cap);
+    p_end = (p_end + 1) & ~1;
     const int j = cta.lane & 3, r = cta.lane >> 2;
     const long long nunits = (B + NT * 8 - 1) / (NT * 8);
     double ob[2], is[2], lc[2];                 // the lane's two tracers (j, j+4)
@@ -615,16 +630,53 @@ k_forward(PlanView pv, SlotMap sm, const double* __restrict__ theta, long long B
         int tr = min(j + 4 * q, MAX_TRACER - 1);
         ob[q] = lik.obs[tr]; is[q] = lik.isd[tr]; lc[q] = lik.lc[tr];
     }
-    for (cta.sched_begin(nunits); cta.sched_valid(); cta.sched_next()) {
+    const int th_unit = NT * 8 * sm.ndim;       // doubles per staged unit
+    double* const stg = ngrtd_smem + p_end + cta.warp * th_unit;
+    unsigned long long* const tbar = reinterpret_cast<unsigned long long*>(ngrtd_smem + p_end + cta.nwarps * th_unit) + cta.warp;
+    unsigned int tphase = 0;
+    bool staged_tma = false;
+    // stage the parameter rows of unit un into this warp's slot (all lanes call; previous readers are past a __syncwarp)
+#define NGRTD_STAGE_UNIT(un)                                                                            \
+    do {                                                                                                \
+        const long long c0_ = (un) * (NT * 8);                                                          \
+        const long long n_ = min((long long)(NT * 8), B - c0_) * sm.ndim;                               \
+        const double* src_ = theta + c0_ * sm.ndim;                                                     \
+        staged_tma = stage == 1 && ((n_ & 1) == 0) && ((reinterpret_cast<unsigned long long>(src_) & 15ull) == 0); \
+        if (staged_tma) {                                                                               \
+            if (cta.lane == 0) {                                                                        \
+                mbar_expect_tx(tbar, (unsigned int)n_ * 8u);                                            \
+                bulk_g2s(stg, src_, (unsigned int)n_ * 8u, tbar);                                       \
+            }                                                                                           \
+        } else {                                                                                        \
+            for (int i_ = cta.lane; i_ < (int)n_; i_ += 32) stg[i_] = src_[i_];                         \
+        }                                                                                               \
+    } while (0)
+    cta.sched_begin(nunits);
+    if (stage) {
+        if (cta.lane == 0) mbar_init(tbar, 1);
+        __syncwarp();
+        if (cta.sched_valid() && cta.active) NGRTD_STAGE_UNIT(cta.unit);
+    }
+    for (; cta.sched_valid(); cta.sched_next()) {
         const long long u = cta.unit;
         const bool active = cta.active, lockstep = cta.lockstep;
         ChainPar par[NT];
         long long chain[NT];
+        if (stage && active) {
+            if (staged_tma) { mbar_wait(tbar, tphase); tphase ^= 1u; }
+            __syncwarp();
+        }
 #pragma unroll
         for (int t = 0; t < NT; t++) {
             chain[t] = (u * NT + t) * 8 + r;
             long long cl = chain[t] < B ? chain[t] : B - 1;
-            par[t] = load_chain_par(theta, sm, active ? cl : 0, pv, cta.need_J);
+            if (stage && active) par[t] = load_chain_par(stg, sm, cl - u * (NT * 8), pv, cta.need_J);
+            else par[t] = load_chain_par(theta, sm, active ? cl : 0, pv, cta.need_J);
+        }
+        if (stage && active) {
+            __syncwarp();                                   // every lane holds its rows: the slot is free again
+            const long long un = cta.sched_peek();
+            if (un < nunits) NGRTD_STAGE_UNIT(un);
         }
         double val[NT][2];
         cta.eval(par, active, lockstep, val);
@@ -643,6 +695,7 @@ k_forward(PlanView pv, SlotMap sm, const double* __restrict__ theta, long long B
             }
         }
     }
+#undef NGRTD_STAGE_UNIT
     if (cta.pending) cta.wait_chunk();      // warps without work must not exit under an in-flight bulk copy
 }
 

@@ -131,3 +131,55 @@ def test_posterior_predictive_batch_matches_loop():
         assert abs(m.convolve() - pp["H3"][s]) <= 1e-12 * abs(pp["H3"][s])
     mu, err = mc.observations()
     assert abs(np.median(pp["CFC12"]) - mu[0]) < 4 * err[0]          # the fit explains the observation
+
+
+def test_pinned_host_zero_copy_and_staging_modes_are_bitwise_identical(monkeypatch):
+    """The *_host entry points read pinned (mapped) host buffers straight from the kernel (TMA bulk copy per 16-chain unit,
+    next unit prefetched) and fall back to staged copies for pageable memory; the device entry points can stage theta the
+    same way (NGRTD_STAGE).  Every route must give the same bits, at ragged batch sizes (partial last unit, odd row count
+    x odd ndim => lane-load staging of the last unit) and with the per-chain nu of the Student-T likelihood."""
+    import torch
+    from helpers import synth_plan
+    from noblegas_rtd_mcmc_b200 import synthetic
+    pn = list(synthetic.PAR_NAMES_CFG3)
+    plan, _, _ = synth_plan("exp_pist_flow", "dispersion", pn)
+    obs = np.array([8.0, 40.0, 150.0, 300.0, 50.0, 5.0, 1e-8])
+    sd = 0.05 * obs
+    for B in (1, 15, 16, 37, 4099, 33333, 65536):
+        theta = synthetic.theta_cfg3_informative(B, 21)
+        theta[: B // 2] = synthetic.theta_cfg3(B // 2, 22)
+        nu = np.random.default_rng(B).uniform(5.0, 30.0, B)
+        monkeypatch.setenv("NGRTD_STAGE", "0")
+        th_d = torch.from_numpy(theta).cuda()
+        nu_d = torch.from_numpy(nu).cuda()
+        model_d = torch.empty((B, 7), dtype=torch.float64, device="cuda")
+        ref_t = plan.forward_loglik_dev(th_d, pn, obs, sd, "studentt", nu_t=nu_d, model_t=model_d).cpu().numpy()
+        ref_n = plan.forward_loglik_dev(th_d, pn, obs, sd, "normal").cpu().numpy()
+        ref_m = model_d.cpu().numpy()
+        for stage in ("1", "2"):
+            monkeypatch.setenv("NGRTD_STAGE", stage)
+            model_d.zero_()
+            got = plan.forward_loglik_dev(th_d, pn, obs, sd, "studentt", nu_t=nu_d, model_t=model_d).cpu().numpy()
+            assert np.array_equal(got, ref_t, equal_nan=True), (B, stage)
+            assert np.array_equal(model_d.cpu().numpy(), ref_m, equal_nan=True), (B, stage)
+        monkeypatch.setenv("NGRTD_STAGE", "0")
+        th_p = torch.from_numpy(theta).pin_memory()
+        nu_p = torch.from_numpy(nu).pin_memory()
+        lp_p = torch.empty(B, dtype=torch.float64).pin_memory()
+        for mode in ("mapped", "copy"):
+            monkeypatch.setenv("NGRTD_HOST_MODE", mode)
+            lp_p.fill_(7.0)
+            plan.forward_loglik_host(th_p.numpy(), pn, obs, sd, "studentt", nu=nu_p.numpy(), logp_out=lp_p.numpy())
+            assert np.array_equal(lp_p.numpy(), ref_t, equal_nan=True), (B, mode)
+            lp, model = plan.forward_loglik_host(th_p.numpy(), pn, obs, sd, "normal", want_model=True)   # pageable outputs
+            assert np.array_equal(lp, ref_n, equal_nan=True) and np.array_equal(model, ref_m, equal_nan=True), (B, mode)
+            assert np.array_equal(plan.forward_host(th_p.numpy(), pn), ref_m, equal_nan=True), (B, mode)
+        # pageable theta always takes the staged-copy pipeline
+        assert np.array_equal(plan.forward_loglik_host(theta, pn, obs, sd, "normal"), ref_n, equal_nan=True)
+        # a pinned slice whose rows start at an address that is not a multiple of 16 bytes (lane-load staging)
+        if B > 16:
+            flat = torch.empty(B * 7 + 1, dtype=torch.float64).pin_memory()
+            flat[1:] = torch.from_numpy(theta).reshape(-1)
+            odd = flat.numpy()[1:].reshape(B, 7)
+            monkeypatch.setenv("NGRTD_HOST_MODE", "mapped")
+            assert np.array_equal(plan.forward_loglik_host(odd, pn, obs, sd, "normal"), ref_n, equal_nan=True)
