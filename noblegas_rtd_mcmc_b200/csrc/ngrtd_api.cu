@@ -265,6 +265,8 @@ extern "C" int ngrtd_plan_create(ngrtd_plan** out, int32_t L, int32_t nseries, c
     pv.eta1_is_one = (mod_type1 == NGRTD_MOD_EXPONENTIAL);
     pv.eta2_is_one = (mod_type2 == NGRTD_MOD_EXPONENTIAL);
     pv.default_log10J = std::log10(j_flux(1., 2700, 1000, 3.0, 10.0, 0.05));   // run_age_mcmc_utils.py:90-91
+    pv.tpl = (double)(L - 1) + dtp + ((L == 1) ? 1e-5 : 0.0);
+    pv.itpl = 1.0 / pv.tpl;
     *out = P;
     return NGRTD_OK;
 }

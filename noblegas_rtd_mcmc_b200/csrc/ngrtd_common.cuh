@@ -87,6 +87,7 @@ struct PlanView {
     int Kc;                         // first lag of the analytic tail (multiple of 4); Kc >= Lpad: no tail
     ColTail ct[NCOL];
     double dyn_bg;                  // constant value of the per-chain-lambda series beyond Kc
+    double tpl, itpl;               // last lag of the grid, tp[L-1], and its reciprocal (dispersion dead-chain rule)
 };
 
 struct SlotMap {
@@ -95,7 +96,7 @@ struct SlotMap {
 };
 
 struct ChainPar {
-    double tau1, tau2, f1, f2, eta1, eta2, D1, D2, Jlin, lam_cfc, lamsf6;
+    double tau1, tau2, f1, f2, eta1, eta2, D1, D2, log10J, lam_cfc, lamsf6;   // J = 10**log10J is formed in WarpTiles::begin
 };
 
 __device__ __forceinline__ ChainPar load_chain_par(const double* __restrict__ theta, const SlotMap& sm,
@@ -114,8 +115,7 @@ __device__ __forceinline__ ChainPar load_chain_par(const double* __restrict__ th
     p.eta2 = pv.eta2_is_one ? 1.0 : get(5, 0.0);
     p.D1 = get(6, 0.0);
     p.D2 = get(7, 0.0);
-    p.Jlin = 0.0;
-    if (need_J) p.Jlin = exp10(get(8, pv.default_log10J));       // J = 10**p_dict['J'] (:101)
+    p.log10J = need_J ? get(8, pv.default_log10J) : 0.0;         // J = 10**p_dict['J'] (:101), see WarpTiles::begin
     {
         int c = sm.col_of_slot[9];
         p.lam_cfc = c >= 0 ? (LN2 / row[c]) : 0.0;               // thalf_2_lambda (:146-152)

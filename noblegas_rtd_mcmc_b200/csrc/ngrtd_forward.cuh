@@ -94,6 +94,22 @@ struct Comp<CLS_G> {
         r4 = exp(-4.0 * er);
         v = 0.0;
     }
+    // same, with the quotients 1/eta (IEEE-rounded: it enters the reference's mask threshold), eta/tau and
+    // exp(-4 eta/tau) supplied by the lane-split prologue of WarpTiles::begin
+    __device__ __forceinline__ void init_q(double tau, double inv_eta, double er_, double r4_, double dtp) {
+        double thr = __dmul_rn(tau, __dsub_rn(1.0, inv_eta));
+        double tp0 = 1e-5 + dtp;
+        if (thr <= tp0) {
+            k0 = 0;
+        } else {
+            double c = ceil(thr - dtp);
+            k0 = (c >= 1073741824.0) ? 1073741824 : max(1, (int)c);
+        }
+        tpk0 = (k0 == 0) ? tp0 : (double)k0 + dtp;
+        er = er_;
+        r4 = r4_;
+        v = 0.0;
+    }
     // direct evaluation at lag k (first group of a chunk); primes the recurrence for lag k+4
     __device__ __forceinline__ double first(int k, double dtp) {
         double vk = exp(-er * (((double)k + dtp) - tpk0));
@@ -128,6 +144,19 @@ struct Comp<CLS_D> {
             ok = emax >= (double)EXP_NMIN;
         }
         cp += FX_MAGIC;     // exp_scaled_bits takes ep + FX_MAGIC: folded into the constant term
+        if (!ok) ap = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    // same, with i4D = 1/(4D) and bq = -(N/ln2)/(4 D tau) supplied by the lane-split prologue of WarpTiles::begin
+    __device__ __forceinline__ void init_q(double tau, double D, double i4D, double bq, const PlanView& pv) {
+        bool ok = (tau > 0.0) && (D > 0.0) && (tau < 1.0e300) && (D < 1.0e300);
+        ap = -EXP_K * tau * i4D;
+        bp = bq;
+        cp = EXP_K * 2.0 * i4D;
+        if (ok && tau > pv.tpl) {
+            double emax = fma(ap, pv.itpl, fma(bp, pv.tpl, cp));
+            ok = emax >= (double)EXP_NMIN;
+        }
+        cp += FX_MAGIC;
         if (!ok) ap = __longlong_as_double(0x7ff8000000000000LL);
     }
     // it = {1/tp, tp} of the lag (shared-memory table): two independent FMAs, no carried state
@@ -178,17 +207,61 @@ struct WarpTiles {
     Comp<C2> c2[NT];
     double a1[NT][UA][2], a2[NT][UA][2];   // UA independent DMMA accumulator chains per tile and component
     double dv[NT], d4[NT], lam[NT], ad1[NT], ad2[NT];
+    double Jl[NT];                          // J = 10**log10J (run_age_mcmc_utils.py:101)
 
-    __device__ __forceinline__ void begin(const ChainPar (&p)[NT], const PlanView& pv) {
+    // Per-chain set-up.  The 4 lanes (r, 0..3) of a chain would otherwise repeat the same divisions and exponentials
+    // (~25-40 FP64 instructions each on the pipe the lag loops of the other warps need), so the work is split: every
+    // lane performs ONE division and ONE exp() with its own operands and the results are exchanged by shuffles.
+    //   division slots: lanes 0,1 component 1, lanes 2,3 component 2
+    //       exponential class: 1/eta (IEEE-rounded, it enters the mask threshold) and eta/tau
+    //       dispersion:        0.25/D = 1/(4D) and -(N/ln2)/4 / (D tau)
+    //   exp slots: lane 0 J = exp(ln10 * log10 J) (argument product carried in two pieces), lane 1 / 2 the 4-lag decay
+    //       factor exp(-4 eta/tau) of component 1 / 2, lane 3 exp(-4 lambda) of a per-chain decay constant.
+    __device__ __forceinline__ void begin(const ChainPar (&p)[NT], const PlanView& pv, int lane, bool need_J) {
+        const int j = lane & 3, base = lane & ~3;
+        const unsigned full = 0xffffffffu;
 #pragma unroll
         for (int t = 0; t < NT; t++) {
-            c1[t].init(p[t].tau1, p[t].eta1, p[t].D1, pv.dtp, pv.L);
-            c2[t].init(p[t].tau2, p[t].eta2, p[t].D2, pv.dtp, pv.L);
+            double q[4] = {0.0, 0.0, 0.0, 0.0};
+            if constexpr (LOOP1 || LOOP2) {
+                double num = 1.0, den = 1.0;
+                if constexpr (C1 == CLS_G) { if (j == 0) den = p[t].eta1; if (j == 1) { num = p[t].eta1; den = p[t].tau1; } }
+                if constexpr (C1 == CLS_D) { if (j == 0) { num = 0.25; den = p[t].D1; } if (j == 1) { num = -0.25 * EXP_K; den = p[t].D1 * p[t].tau1; } }
+                if constexpr (C2 == CLS_G) { if (j == 2) den = p[t].eta2; if (j == 3) { num = p[t].eta2; den = p[t].tau2; } }
+                if constexpr (C2 == CLS_D) { if (j == 2) { num = 0.25; den = p[t].D2; } if (j == 3) { num = -0.25 * EXP_K; den = p[t].D2 * p[t].tau2; } }
+                const double qq = __ddiv_rn(num, den);
+                if constexpr (LOOP1) { q[0] = __shfl_sync(full, qq, base); q[1] = __shfl_sync(full, qq, base + 1); }
+                if constexpr (LOOP2) { q[2] = __shfl_sync(full, qq, base + 2); q[3] = __shfl_sync(full, qq, base + 3); }
+            }
+            double e[4] = {0.0, 0.0, 0.0, 0.0};
+            {
+                constexpr double LN10_HI = 2.302585092994045901, LN10_LO = -2.1707562233822494e-16;
+                double ea = 0.0, el = 0.0;
+                if (j == 0 && need_J) {
+                    ea = p[t].log10J * LN10_HI;
+                    el = fma(p[t].log10J, LN10_HI, -ea) + p[t].log10J * LN10_LO;
+                }
+                if constexpr (C1 == CLS_G) { if (j == 1) ea = -4.0 * q[1]; }
+                if constexpr (C2 == CLS_G) { if (j == 2) ea = -4.0 * q[3]; }
+                if (DYN) { if (j == 3) ea = -4.0 * p[t].lam_cfc; }
+                double ee = exp(ea);
+                ee = fma(ee, el, ee);
+                Jl[t] = need_J ? __shfl_sync(full, ee, base) : 0.0;
+                if constexpr (C1 == CLS_G) e[1] = __shfl_sync(full, ee, base + 1);
+                if constexpr (C2 == CLS_G) e[2] = __shfl_sync(full, ee, base + 2);
+                if (DYN) e[3] = __shfl_sync(full, ee, base + 3);
+            }
+            if constexpr (C1 == CLS_G) c1[t].init_q(p[t].tau1, q[0], q[1], e[1], pv.dtp);
+            else if constexpr (C1 == CLS_D) c1[t].init_q(p[t].tau1, p[t].D1, q[0], q[1], pv);
+            else c1[t].init(p[t].tau1, p[t].eta1, p[t].D1, pv.dtp, pv.L);
+            if constexpr (C2 == CLS_G) c2[t].init_q(p[t].tau2, q[2], q[3], e[2], pv.dtp);
+            else if constexpr (C2 == CLS_D) c2[t].init_q(p[t].tau2, p[t].D2, q[2], q[3], pv);
+            else c2[t].init(p[t].tau2, p[t].eta2, p[t].D2, pv.dtp, pv.L);
 #pragma unroll
             for (int u = 0; u < UA; u++) a1[t][u][0] = a1[t][u][1] = a2[t][u][0] = a2[t][u][1] = 0.0;
             if (DYN) {
                 lam[t] = p[t].lam_cfc;
-                d4[t] = exp(-4.0 * lam[t]);
+                d4[t] = e[3];
                 dv[t] = 0.0;
                 ad1[t] = ad2[t] = 0.0;
             }
@@ -321,6 +394,27 @@ struct WarpTiles {
             }
             double m[2], md = 0.0;
             double x1[2], x2[2] = {0.0, 0.0}, xd1 = 0.0, xd2 = 0.0;
+            // Normalisation: the sums S1, S2 (column 0) are inverted ONCE per chain -- lane 0 takes 1/S1, lane 1 1/S2 --
+            // and broadcast, instead of 4-6 divisions in every lane.  a * (1/S) differs from a / S by <= 1.5 ulp; when
+            // 1/S would leave the normal range (S subnormal: every weight underflowed) the plain division is kept so
+            // that such chains behave exactly as before (decided per chain: results never depend on warp neighbours).
+            double S1 = 1.0, S2 = 1.0, r1 = 1.0, r2 = 1.0;
+            bool use_div = false;
+            if constexpr (LOOP1) {
+                S1 = __shfl_sync(full, a1[t][0][0], lane & ~3);
+                if constexpr (C1 == CLS_D) { if (c1[t].dead()) S1 = c1[t].ap; }
+            }
+            if constexpr (LOOP2) {
+                S2 = __shfl_sync(full, a2[t][0][0], lane & ~3);
+                if constexpr (C2 == CLS_D) { if (c2[t].dead()) S2 = c2[t].ap; }
+            }
+            if constexpr (LOOP1 || LOOP2) {
+                const double den = (LOOP1 && (!LOOP2 || (j & 1) == 0)) ? S1 : S2;
+                const double rr = __ddiv_rn(1.0, den);
+                use_div = (LOOP1 && fabs(S1) < 1e-290) || (LOOP2 && fabs(S2) < 1e-290);   // per chain, not per warp
+                if constexpr (LOOP1) r1 = __shfl_sync(full, rr, lane & ~3);
+                if constexpr (LOOP2) r2 = __shfl_sync(full, rr, (lane & ~3) + (LOOP1 ? 1 : 0));
+            }
             // component 1
             if constexpr (C1 == CLS_P) {
                 int ix = c1[t].ix;
@@ -331,15 +425,20 @@ struct WarpTiles {
                     xd1 = pv.xraw[ix] * exp(-p[t].lam_cfc * tp);
                 }
             } else {
-                double S = __shfl_sync(full, a1[t][0][0], lane & ~3);
-                if constexpr (C1 == CLS_D) { if (c1[t].dead()) S = c1[t].ap; }
-                x1[0] = a1[t][0][0] / S;
-                x1[1] = a1[t][0][1] / S;
+                double s = 0.0;
                 if (DYN) {
-                    double s = ad1[t];
+                    s = ad1[t];
                     s += __shfl_xor_sync(full, s, 1);
                     s += __shfl_xor_sync(full, s, 2);
-                    xd1 = s / S;
+                }
+                if (use_div) {
+                    x1[0] = a1[t][0][0] / S1;
+                    x1[1] = a1[t][0][1] / S1;
+                    if (DYN) xd1 = s / S1;
+                } else {
+                    x1[0] = a1[t][0][0] * r1;
+                    x1[1] = a1[t][0][1] * r1;
+                    if (DYN) xd1 = s * r1;
                 }
             }
             if constexpr (C2 == CLS_P) {
@@ -351,15 +450,20 @@ struct WarpTiles {
                     xd2 = pv.xraw[ix] * exp(-p[t].lam_cfc * tp);
                 }
             } else if constexpr (C2 != CLS_NONE) {
-                double S = __shfl_sync(full, a2[t][0][0], lane & ~3);
-                if constexpr (C2 == CLS_D) { if (c2[t].dead()) S = c2[t].ap; }
-                x2[0] = a2[t][0][0] / S;
-                x2[1] = a2[t][0][1] / S;
+                double s = 0.0;
                 if (DYN) {
-                    double s = ad2[t];
+                    s = ad2[t];
                     s += __shfl_xor_sync(full, s, 1);
                     s += __shfl_xor_sync(full, s, 2);
-                    xd2 = s / S;
+                }
+                if (use_div) {
+                    x2[0] = a2[t][0][0] / S2;
+                    x2[1] = a2[t][0][1] / S2;
+                    if (DYN) xd2 = s / S2;
+                } else {
+                    x2[0] = a2[t][0][0] * r2;
+                    x2[1] = a2[t][0][1] * r2;
+                    if (DYN) xd2 = s * r2;
                 }
             }
             // cout = f1*cout1 + f2*cout2 (run_age_mcmc_utils.py:154); cout2 = 0.0 without a second component
@@ -380,7 +484,7 @@ struct WarpTiles {
                         v = md;
                     } else {
                         double va = td.col_a >= 0 ? sc[td.col_a] : 0.0;
-                        v = td.col_b >= 0 ? va + p[t].Jlin * sc[td.col_b] : va;
+                        v = td.col_b >= 0 ? va + Jl[t] * sc[td.col_b] : va;
                     }
                     if (td.sf6) v *= (1.0 + p[t].lamsf6);
                 }
@@ -525,7 +629,7 @@ struct FwdCta {
     // take part in the chunk loads and barriers).
     __device__ __forceinline__ void eval(const ChainPar (&par)[NT], bool active, bool lockstep, double (&val)[NT][2]) {
         WT w;
-        w.begin(par, pv);
+        w.begin(par, pv, lane, need_J);
         if (!lockstep) {
             if (pending) { wait_chunk(); pending = false; }
             w.chunk(s, pv, 0, Lloop / 4, lane);

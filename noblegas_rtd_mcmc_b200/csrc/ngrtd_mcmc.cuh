@@ -281,7 +281,7 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
                 p.eta2 = pv.eta2_is_one ? 1.0 : vals[5];
                 p.D1 = vals[6];
                 p.D2 = vals[7];
-                p.Jlin = cta.need_J ? exp10(vals[8]) : 0.0;
+                p.log10J = vals[8];
                 p.lam_cfc = (sv.sampled_mask & (1u << 9)) ? LN2 / vals[9] : 0.0;
                 p.lamsf6 = vals[10];
                 nu[t] = sv.nu_sampled ? sv.nu_lo + (sv.nu_hi - sv.nu_lo) * vals[VAL_NU] : sv.nu_fixed;

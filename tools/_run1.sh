@@ -1,4 +1,4 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/s2_tests.txt
+python -m pytest tests -m gpu -x -q 2>&1 | tail -40 > gpurun_out/s2_tests.txt
 cat gpurun_out/s2_tests.txt
-python bench.py > gpurun_out/bench_s2_b.json 2> gpurun_out/bench_s2_b.err; tail -c 1500 gpurun_out/bench_s2_b.err; python -c "
-import json; d=json.load(open('gpurun_out/bench_s2_b.json')); print(d['value'], d['e2e'], d['roofline']['frac'], d['sampler']['value'])"
+python tools/quick_bench.py > gpurun_out/s2_quick.txt 2>&1; cat gpurun_out/s2_quick.txt
+python tools/parity_err.py > gpurun_out/s2_parity.txt 2>&1; tail -15 gpurun_out/s2_parity.txt
