@@ -1,4 +1,3 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -40 > gpurun_out/s2_tests.txt
-cat gpurun_out/s2_tests.txt
-python tools/quick_bench.py > gpurun_out/s2_quick.txt 2>&1; cat gpurun_out/s2_quick.txt
-python tools/parity_err.py > gpurun_out/s2_parity.txt 2>&1; tail -15 gpurun_out/s2_parity.txt
+python tools/ng_probe2.py
+for s in 0 1 0 1; do NGRTD_STAGE=$s python bench.py --steps 100 --warmup 10 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('stage $s', d['value'], d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['frac'], d['e2e']['value'])"; done
