@@ -114,6 +114,18 @@ int ngrtd_forward_loglik_dev(ngrtd_plan* plan, const double* theta_d, int64_t B,
 int ngrtd_forward_loglik_host(ngrtd_plan* plan, const double* theta_h, int64_t B, int32_t ndim,
                               const int32_t* slot_of_col, int32_t lik_kind, const double* obs_mu,
                               const double* obs_sd, const double* nu_h, double* logp_h, double* model_out_h);
+/* ---- the same call split into submit + wait, for callers that evaluate INDEPENDENT batches back to back (the
+ *  reference's Monte-Carlo sweeps and posterior-predictive loops: aux_scripts/age_modeling_mcmc.rtd_explore.py:277-359,
+ *  run_age_mcmc.py:243-319).  Up to NGRTD_HOST_SLOTS batches are in flight: the host->device copy of batch i+1 and the
+ *  device->host copy of batch i-1 run under the kernel of batch i.  theta_h / nu_h must stay valid and logp_h /
+ *  model_out_h must not be read until ngrtd_host_wait(plan, slot) returns; pinned host memory is needed for the overlap
+ *  (pageable buffers work, the copies then block the submitting thread).  A busy slot is an error (wait first).       */
+#define NGRTD_HOST_SLOTS 4
+int ngrtd_forward_loglik_host_submit(ngrtd_plan* plan, const double* theta_h, int64_t B, int32_t ndim,
+                                     const int32_t* slot_of_col, int32_t lik_kind, const double* obs_mu,
+                                     const double* obs_sd, const double* nu_h, double* logp_h, double* model_out_h,
+                                     int32_t slot);
+int ngrtd_host_wait(ngrtd_plan* plan, int32_t slot);
 
 /* ---- tracer_conv_integral.gen_g_tp() (conv utils :155-281): normalised RTD weights g[B, L],
  *      one model, parameters tau/eta/D [B] (eta, D may be NULL when unused).                        */

@@ -67,6 +67,8 @@ _PROTOS = {
     "ngrtd_forward_host": ([_vp, _vp, _i64, _i32, _vp, _vp], ctypes.c_int),
     "ngrtd_forward_loglik_dev": ([_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "ngrtd_forward_loglik_host": ([_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "ngrtd_forward_loglik_host_submit": ([_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32], ctypes.c_int),
+    "ngrtd_host_wait": ([_vp, _i32], ctypes.c_int),
     "ngrtd_rtd_weights_dev": ([_i32, _i32, _dbl, _vp, _vp, _vp, _i64, _vp, _vp], ctypes.c_int),
     "ngrtd_rtd_weights_fdm_dev": ([_i32, _dbl, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp], ctypes.c_int),
     "ngrtd_rtd_weights_fdm_ext_dev": ([_i32, _dbl, _vp, _vp, _vp, _i64, _vp, _vp, _vp], ctypes.c_int),
@@ -174,6 +176,7 @@ class Plan:
                                     len(tracers), arr, MOD[mod_type1], MOD[mod_type2] if mod_type2 else 0, device))
         self.handle = h
         self.ntracer = len(tracers)
+        self._inflight = {}
 
     def close(self):
         if getattr(self, "handle", None):
@@ -205,6 +208,29 @@ class Plan:
         check(lib.ngrtd_forward_loglik_host(self.handle, hptr(theta), B, ndim, hptr(slot_array(par_names)), LIK[kind],
                                             hptr(f64(obs_mu)), hptr(f64(obs_sd)), hptr(nu_a), hptr(logp), hptr(model)))
         return (logp, model) if want_model else logp
+
+    HOST_SLOTS = 4
+
+    def forward_loglik_host_submit(self, theta, par_names, obs_mu, obs_sd, kind="normal", nu=None, want_model=False,
+                                   logp_out=None, model_out=None, slot=0):
+        """Asynchronous form of forward_loglik_host for independent batches (Monte-Carlo sweeps, posterior-predictive
+        loops): enqueue copy-in -> kernel -> copy-out for this batch and return at once; up to HOST_SLOTS batches are in
+        flight and their copies overlap the kernels of their neighbours.  Returns (logp[, model]) arrays that are valid
+        after host_wait(slot).  Pass pinned (page-locked) arrays for theta / logp_out / model_out to get the overlap."""
+        theta = f64(np.atleast_2d(theta))
+        B, ndim = theta.shape
+        logp = np.empty(B) if logp_out is None else logp_out
+        model = (np.empty((B, self.ntracer)) if model_out is None else model_out) if (want_model or model_out is not None) else None
+        nu_a = None if nu is None else f64(np.broadcast_to(nu, (B,)))
+        check(lib.ngrtd_forward_loglik_host_submit(self.handle, hptr(theta), B, ndim, hptr(slot_array(par_names)), LIK[kind],
+                                                   hptr(f64(obs_mu)), hptr(f64(obs_sd)), hptr(nu_a), hptr(logp), hptr(model),
+                                                   int(slot)))
+        self._inflight[int(slot)] = (theta, nu_a, logp, model)       # keep the buffers alive until host_wait
+        return (logp, model) if model is not None else logp
+
+    def host_wait(self, slot=0):
+        check(lib.ngrtd_host_wait(self.handle, int(slot)))
+        self._inflight.pop(int(slot), None)
 
     # ---- device buffers (torch CUDA tensors in / out, no synchronisation) ----
     def forward_dev(self, theta_t, par_names, out_t=None, stream=None):

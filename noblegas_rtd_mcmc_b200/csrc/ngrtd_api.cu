@@ -50,6 +50,13 @@ struct ngrtd_plan {
     // host-buffer pipeline: copy-in stream, compute stream, copy-out stream + one event pair per part
     cudaStream_t hstream = nullptr, hstream2 = nullptr, hstream3 = nullptr;
     cudaEvent_t ev_in[HOST_PARTS_MAX] = {}, ev_k[HOST_PARTS_MAX] = {};
+    // submit / wait slots (ngrtd_forward_loglik_host_submit): own device buffers and events per slot
+    struct HostSlot {
+        double *theta = nullptr, *nu = nullptr, *logp = nullptr, *out = nullptr;
+        size_t theta_n = 0, nu_n = 0, logp_n = 0, out_n = 0;
+        cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_done = nullptr;
+        bool busy = false;
+    } slots[NGRTD_HOST_SLOTS];
 };
 
 static int cls_of(int mod) {
@@ -247,6 +254,11 @@ extern "C" int ngrtd_plan_create(ngrtd_plan** out, int32_t L, int32_t nseries, c
         e = cudaEventCreateWithFlags(&P->ev_in[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&P->ev_k[i], cudaEventDisableTiming);
     }
+    for (int i = 0; i < NGRTD_HOST_SLOTS && e == cudaSuccess; i++) {
+        e = cudaEventCreateWithFlags(&P->slots[i].ev_in, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&P->slots[i].ev_k, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&P->slots[i].ev_done, cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) {
         ngrtd_plan_destroy(P);
         return fail(NGRTD_ECUDA, std::string("plan upload: ") + cudaGetErrorString(e));
@@ -282,6 +294,13 @@ extern "C" int ngrtd_plan_destroy(ngrtd_plan* P) {
     for (int i = 0; i < HOST_PARTS_MAX; i++) {
         if (P->ev_in[i]) cudaEventDestroy(P->ev_in[i]);
         if (P->ev_k[i]) cudaEventDestroy(P->ev_k[i]);
+    }
+    for (auto& sl : P->slots) {
+        if (sl.busy && sl.ev_done) cudaEventSynchronize(sl.ev_done);
+        cudaFree(sl.theta); cudaFree(sl.nu); cudaFree(sl.logp); cudaFree(sl.out);
+        if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+        if (sl.ev_k) cudaEventDestroy(sl.ev_k);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
     }
     delete P;
     return NGRTD_OK;
@@ -588,6 +607,56 @@ static int forward_host_common(ngrtd_plan* P, const double* theta_h, int64_t B, 
                                      cudaMemcpyDeviceToHost, s_out));
     }
     CUDA_TRY(cudaStreamSynchronize(s_out));    // the last copy-out is behind every kernel and every copy-in
+    return NGRTD_OK;
+}
+
+// ---- submit / wait: one batch per slot, copy-in / compute / copy-out on the plan's three streams (FIFO across slots), so
+// the copies of neighbouring batches run under the kernel of the current one.
+extern "C" int ngrtd_forward_loglik_host_submit(ngrtd_plan* P, const double* theta_h, int64_t B, int32_t ndim,
+                                                const int32_t* slot_of_col, int32_t lik_kind, const double* obs_mu,
+                                                const double* obs_sd, const double* nu_h, double* logp_h,
+                                                double* model_out_h, int32_t slot) {
+    if (!P) return fail(NGRTD_EINVAL, "null plan");
+    if (slot < 0 || slot >= NGRTD_HOST_SLOTS) return fail(NGRTD_EINVAL, "submit: slot out of range");
+    if (!theta_h || !logp_h) return fail(NGRTD_EINVAL, "null host buffer");
+    if (B < 0) return fail(NGRTD_EINVAL, "B < 0");
+    auto& sl = P->slots[slot];
+    if (sl.busy) return fail(NGRTD_EINVAL, "submit: slot " + std::to_string(slot) + " is busy (call ngrtd_host_wait first)");
+    if (B == 0) return NGRTD_OK;
+    const bool need_nu = lik_kind == NGRTD_LIK_STUDENTT;
+    if (need_nu && !nu_h) return fail(NGRTD_EINVAL, "student-t needs nu");
+    CUDA_TRY(cudaSetDevice(P->device));
+    const int nt = P->pv.ntracer;
+    int rc;
+    if ((rc = grow(&sl.theta, &sl.theta_n, (size_t)B * ndim))) return rc;
+    if ((rc = grow(&sl.logp, &sl.logp_n, (size_t)B))) return rc;
+    if (model_out_h && (rc = grow(&sl.out, &sl.out_n, (size_t)B * nt))) return rc;
+    if (need_nu && (rc = grow(&sl.nu, &sl.nu_n, (size_t)B))) return rc;
+    cudaStream_t s_in = P->hstream, s_k = P->hstream2, s_out = P->hstream3;
+    CUDA_TRY(cudaMemcpyAsync(sl.theta, theta_h, (size_t)B * ndim * sizeof(double), cudaMemcpyHostToDevice, s_in));
+    if (need_nu) CUDA_TRY(cudaMemcpyAsync(sl.nu, nu_h, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, s_in));
+    CUDA_TRY(cudaEventRecord(sl.ev_in, s_in));
+    CUDA_TRY(cudaStreamWaitEvent(s_k, sl.ev_in, 0));
+    rc = ngrtd_forward_loglik_dev(P, sl.theta, B, ndim, slot_of_col, lik_kind, obs_mu, obs_sd, need_nu ? sl.nu : nullptr,
+                                  sl.logp, model_out_h ? sl.out : nullptr, s_k);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(sl.ev_k, s_k));
+    CUDA_TRY(cudaStreamWaitEvent(s_out, sl.ev_k, 0));
+    CUDA_TRY(cudaMemcpyAsync(logp_h, sl.logp, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+    if (model_out_h)
+        CUDA_TRY(cudaMemcpyAsync(model_out_h, sl.out, (size_t)B * nt * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+    CUDA_TRY(cudaEventRecord(sl.ev_done, s_out));
+    sl.busy = true;      // the slot's buffers are reused only after ngrtd_host_wait(slot)
+    return NGRTD_OK;
+}
+
+extern "C" int ngrtd_host_wait(ngrtd_plan* P, int32_t slot) {
+    if (!P) return fail(NGRTD_EINVAL, "null plan");
+    if (slot < 0 || slot >= NGRTD_HOST_SLOTS) return fail(NGRTD_EINVAL, "wait: slot out of range");
+    auto& sl = P->slots[slot];
+    if (!sl.busy) return NGRTD_OK;
+    sl.busy = false;
+    CUDA_TRY(cudaEventSynchronize(sl.ev_done));
     return NGRTD_OK;
 }
 

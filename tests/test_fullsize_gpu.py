@@ -183,3 +183,39 @@ def test_pinned_host_zero_copy_and_staging_modes_are_bitwise_identical(monkeypat
             odd = flat.numpy()[1:].reshape(B, 7)
             monkeypatch.setenv("NGRTD_HOST_MODE", "mapped")
             assert np.array_equal(plan.forward_loglik_host(odd, pn, obs, sd, "normal"), ref_n, equal_nan=True)
+
+
+def test_host_submit_wait_pipeline_matches_sync_calls():
+    """ngrtd_forward_loglik_host_submit / ngrtd_host_wait: several independent batches in flight (copy-in, kernel and
+    copy-out of neighbouring batches overlap) give exactly the results of the synchronous call; a busy slot is refused."""
+    import torch
+    from helpers import synth_plan
+    from noblegas_rtd_mcmc_b200 import _lib, synthetic
+    pn = list(synthetic.PAR_NAMES_CFG3)
+    plan, _, _ = synth_plan("exp_pist_flow", "dispersion", pn)
+    obs = np.array([8.0, 40.0, 150.0, 300.0, 50.0, 5.0, 1e-8])
+    sd = 0.05 * obs
+    sizes = [65536, 4099, 33333, 16, 65536, 1, 20000, 65536]
+    thetas = [torch.from_numpy(synthetic.theta_cfg3_informative(B, 100 + i)).pin_memory() for i, B in enumerate(sizes)]
+    nus = [torch.from_numpy(np.random.default_rng(i).uniform(5.0, 30.0, B)).pin_memory() for i, B in enumerate(sizes)]
+    want = [plan.forward_loglik_host(t.numpy(), pn, obs, sd, "studentt", nu=n.numpy(), want_model=True) for t, n in zip(thetas, nus)]
+    outs = [torch.empty(B, dtype=torch.float64).pin_memory() for B in sizes]
+    mods = [torch.empty((B, 7), dtype=torch.float64).pin_memory() for B in sizes]
+    depth = plan.HOST_SLOTS
+    for i in range(len(sizes) + depth):
+        if i >= depth:
+            k = i - depth
+            plan.host_wait(k % depth)
+            assert np.array_equal(outs[k].numpy(), want[k][0], equal_nan=True), k
+            assert np.array_equal(mods[k].numpy(), want[k][1], equal_nan=True), k
+        if i < len(sizes):
+            plan.forward_loglik_host_submit(thetas[i].numpy(), pn, obs, sd, "studentt", nu=nus[i].numpy(),
+                                            logp_out=outs[i].numpy(), model_out=mods[i].numpy(), slot=i % depth)
+    plan.forward_loglik_host_submit(thetas[3].numpy(), pn, obs, sd, "normal", logp_out=outs[3].numpy(), slot=1)
+    with pytest.raises(_lib.NgrtdError):
+        plan.forward_loglik_host_submit(thetas[3].numpy(), pn, obs, sd, "normal", logp_out=outs[3].numpy(), slot=1)
+    plan.host_wait(1)
+    plan.host_wait(1)                                   # waiting on an idle slot is a no-op
+    assert np.array_equal(outs[3].numpy(), plan.forward_loglik_host(thetas[3].numpy(), pn, obs, sd, "normal"), equal_nan=True)
+    with pytest.raises(_lib.NgrtdError):
+        plan.host_wait(99)

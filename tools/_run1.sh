@@ -1,3 +1,3 @@
-python tools/ng_probe2.py
-for s in 0 1 0 1; do NGRTD_STAGE=$s python bench.py --steps 100 --warmup 10 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('stage $s', d['value'], d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['frac'], d['e2e']['value'])"; done
+python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+python bench.py --steps 200 --warmup 20 > gpurun_out/s2_bench_c.json 2> gpurun_out/s2_bench_c.err; tail -5 gpurun_out/s2_bench_c.err; python -c "
+import json; d=json.load(open('gpurun_out/s2_bench_c.json')); print(d['value'], d['roofline']['frac'], json.dumps(d['e2e'], indent=1), d['ess'])"
