@@ -1,1 +1,1 @@
-python -m pytest tests/test_reference_traces.py -x -q 2>&1 | tail -15
+python tools/_slack.py
