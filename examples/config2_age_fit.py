@@ -3,8 +3,10 @@ input series -- exp_pist_flow RTD, tracers CFC12 + SF6 + H3 + He4_ter, savenum [
 contamination), DEMetropolisZ(tune_interval=1000), tune 10,000 + 10,000 draws, 3 chains, random_seed 123423.
 
 The driver below mirrors run_age_mcmc.py:122-231 (okw / pkw / ckw construction) with our drop-in `conv_mcmc`.
-Observations: MAP values of map_dict.pk; ens_dict.pk is a missing blob of the reference, so the ensemble
-spread is replaced by the 5 % analytical error alone (obs_err = 0 + 0.05 * obs_mu).
+Observations: ens_dict.pk is a missing blob of the reference, so the observation ensembles are rebuilt from what the
+reference's own traces reveal: obs_mu = `observed_data/like` of conv_traces/<well>...123.netcdf (tests/golden/age_traces.json)
+and obs_err = ens.std() + 0.05 obs_mu from tests/golden/age_obs_err.json (H3 a priori, the others estimated from the
+single-tracer traces, oracle/fit_obs_err.py).  With them the run reproduces the reference's posterior (printed beside ours).
 
     python examples/config2_age_fit.py [well] [chains]      (keep chains <= ~4096: the full trace is downloaded and summarised on the host)
 
@@ -26,8 +28,6 @@ from noblegas_rtd_mcmc_b200 import diagnostics
 from noblegas_rtd_mcmc_b200 import noble_gas_utils as ng_utils
 from noblegas_rtd_mcmc_b200.run_age_mcmc_utils import conv_mcmc
 
-MAP = {"CFC12": {"PLM1": 36.3828, "PLM6": 11.9068, "PLM7": 11.8899}, "SF6": {"PLM1": 1.2453, "PLM6": 16.4893, "PLM7": 0.2939},
-       "H3": {"PLM1": 4.8688, "PLM6": 4.1549, "PLM7": 4.3231}, "He4_ter": {"PLM1": 8.8e-9, "PLM6": 1.051e-7, "PLM7": 3.59e-8}}
 
 
 def main():
@@ -40,7 +40,14 @@ def main():
     L = len(C["H3"])
     C_in_dict = {k: pd.DataFrame({k: v[::-1]}, index=np.arange(L - 1, -1, -1)) for k, v in C.items()}
     obs_perr = {"CFC12": 0.05, "SF6": 10.0 if ww == "PLM6" else 0.05, "H3": 0.05, "He4_ter": 0.05}      # run_age_mcmc.py:100-114
-    okw = {tt: {"obs_df": np.array([MAP[tt][ww]]), "obs_perr": obs_perr[tt]} for tt in tracers}
+    import json
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "age_traces.json")))["traces"]["%s.%s.%s.123" % (ww, ".".join(tracers), mod_type1)]
+    rel = json.load(open(os.path.join(ROOT, "tests", "golden", "age_obs_err.json")))["rel"]
+    okw = {}
+    for i, tt in enumerate(tracers):
+        mu_t = ref["obs_mu"][i]
+        std_t = max(rel[tt][ww] - obs_perr[tt], 0.0) * mu_t              # ens.std(): a two-point ensemble with this mean and spread
+        okw[tt] = {"obs_df": np.array([mu_t - std_t, mu_t + std_t]), "obs_perr": obs_perr[tt]}
     pkw = {"tau1_low": 1.0, "tau1_high": 1000.0}
     par_names = ["tau1"]
     if mod_type1 == "exp_pist_flow":
@@ -72,9 +79,11 @@ def main():
     print("well %s  %d chains x 20,000 steps x %d tracers: sampling_time %.2f s (reference, 3 chains: 296-324 s); "
           "whole sample_mcmc call incl. CUDA context, plan upload and trace download %.2f s" % (
               ww, chains, len(tracers), idata["sample_stats"]["sampling_time"], dt))
-    print("%-10s %10s %10s %10s %10s %8s" % ("", "mean", "sd", "median", "ess_bulk", "r_hat"))
+    print("%-10s %10s %10s %10s %10s %8s | %10s %10s %10s  (reference trace, pymc3)" % ("", "mean", "sd", "median", "ess_bulk", "r_hat", "mean", "sd", "median"))
     for k, r in summ.items():
-        print("%-10s %10.4g %10.4g %10.4g %10.0f %8.3f" % (k, r["mean"], r["sd"], r["median"], r["ess_bulk"], r["r_hat"]))
+        rv = ref["vars"].get(k)
+        tail = " | %10.4g %10.4g %10.4g" % (rv["mean"], rv["sd"], rv["q"][9]) if rv else ""
+        print("%-10s %10.4g %10.4g %10.4g %10.0f %8.3f%s" % (k, r["mean"], r["sd"], r["median"], r["ess_bulk"], r["r_hat"], tail))
     pp = mc_conv.posterior_predictive()
     mu, err = mc_conv.observations()
     for i, t in enumerate(tracers):
