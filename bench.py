@@ -186,6 +186,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # rank 0 prints ONE JSON line on stdout: NCCL's version banner / warnings (NCCL_DEBUG=VERSION|WARN|INFO write to
+        # stdout by default) go to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     pn = list(synthetic.PAR_NAMES_CFG3)
     plan, _, _ = synth_plan("exp_pist_flow", "dispersion", pn, device=local)
