@@ -322,14 +322,14 @@ def main():
     smp.close()
     # ---- informational: ESS/s (BASELINE.json's secondary metric) on config 1, the noble-gas closed-equilibrium fit of
     #      well PLM1 with the reference's sampler settings (DEMetropolisZ, tune 10,000 / tune_interval 5,000), whose
-    #      posterior is validated against the reference's own summaries (tests/test_sampler_gpu.py).  65,536 chains per
+    #      posterior is validated against the reference's own summaries (tests/test_sampler_gpu.py).  262,144 chains per
     #      GPU x 5,000 recorded draws, 2,048-slot history ring; per-chain Welford moments all-gathered over NCCL; many-chain ESS estimate. ----
     import json as _json
     from noblegas_rtd_mcmc_b200 import distributed as ngdist
     from noblegas_rtd_mcmc_b200.noble_gas_mcmc import mcmc_model
     fx = _json.load(open(os.path.join(ROOT, "tests", "golden", "ng_posterior.json")))["wells"]["PLM1"]
     mdl = mcmc_model(fx["obs"], mcmc_model.well_elev["PLM1"])
-    NGC = 65536        # 32,768 chains leave the one-chain-per-thread CE kernel latency-bound (3.4 warps per sub-partition)
+    NGC = 262144       # one chain per thread, 92 registers: 5 warps per sub-partition need >= 242k chains (32,768 chains: 1.7)
     warm = Sampler(mdl.build_priors(), mdl.obs_mu, mdl.obs_sd, 64, plan=None, gases=mdl.gases, lik="studentt",
                    nu_range=(1.0, 30.0), tune_interval=5000, hist_cap=8, seed=1, device=local)
     warm.run(4, tune=True, stream=stream)          # first launch of k_mcmc_ng: module load, outside the timed region

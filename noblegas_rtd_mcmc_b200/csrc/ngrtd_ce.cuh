@@ -74,6 +74,41 @@ __device__ __forceinline__ double ce_eval(int what, int gas, double E, double T,
 
 struct GasList { int n; int id[5]; };
 
+// ---- sampler path (k_mcmc_ng): ce_exc(True) of several gases at one parameter vector, S = 0.  Same formulae as ce_eval,
+// with the work that does not depend on the gas done once per step (1/t, vapour pressure) and the divisions folded:
+//   ln K = A0 + it (A1 + it (A2 + it A3)),  C_eq = z (P - P_v) exp(-ln K) 22414/18,
+//   C_ex = (1-F) Ae z / (1 + F Ae z / C_eq) = (1-F) Ae z C_eq / (C_eq + F Ae z)          (also for the -9999 sentinel)
+// One exp and one division per gas instead of one exp, one log, one more exp (the Setchenow factor, == 1 at S = 0) and
+// eight divisions; results agree with ce_eval to a few ulp (tests/test_sampler_gpu.py compares trajectories with the
+// numpy restatement of the reference formulae).  Helium goes through ce_eval (its solubility is derived from argon's).
+struct CeStep {
+    double it, pda, num_c;     // 1/t (t = T_K / 1000), P - P_v, 22414/18
+    bool neg, bad;             // T < 0 -> -9999 sentinel (:227-228); T_K <= 0 -> NaN (log of a negative number in the reference)
+};
+__device__ __forceinline__ CeStep ce_step(double T, double P) {
+    CeStep c;
+    const double T_k = T + 273.15;
+    c.it = 1000.0 / T_k;
+    c.pda = P - ce_vapor_pressure(T);
+    c.num_c = 22414. / 18.;
+    c.neg = T < 0.0;
+    c.bad = !(T_k > 0.0);
+    return c;
+}
+__device__ __forceinline__ double ce_exc_step(int gas, const CeStep& c, double E, double T, double Ae, double F, double P) {
+    if (gas == 0) return ce_eval(0, 0, E, T, Ae, F, P, 0.0);
+    if (c.bad) return __longlong_as_double(0x7ff8000000000000LL);
+    const double lnK = c_sol[gas][0] + c.it * (c_sol[gas][1] + c.it * (c_sol[gas][2] + c.it * c_sol[gas][3]));
+    const double z = c_atm_std[gas];
+    const double C_eq = c.neg ? -9999.0 : (z * c.pda) * exp(-lnK) * c.num_c;
+    const double fa = F * Ae * z;
+    return ((1.0 - F) * Ae * z) * C_eq / (C_eq + fa) + C_eq;
+}
+// lapse_rate (:112) with pow(x, a) as exp(a log x): |log x| < 0.1 here, so the product a log x carries < 1e-16 absolute error
+__device__ __forceinline__ double ce_lapse_rate_step(double E) {
+    return exp(5.2561 * log(1.0 - .0065 * E / 288.15)) * 0.000101325;
+}
+
 __global__ void k_ce(int what, GasList gl, const double* __restrict__ E, const double* __restrict__ T,
                      const double* __restrict__ Ae, const double* __restrict__ F, const double* __restrict__ P,
                      double S, long long B, double* __restrict__ out) {

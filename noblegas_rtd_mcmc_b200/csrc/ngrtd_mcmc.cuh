@@ -354,7 +354,11 @@ __global__ void k_mcmc_ng(SamplerView sv, RunArgs ra) {
     if (chain >= sv.B) return;
     const long long gchain = sv.chain_offset + chain;
     double qs[ND_MAX], qp[ND_MAX], vals[NVAL];
-    for (int d = 0; d < sv.nd; d++) qs[d] = sv.q[chain * sv.nd + d];
+    double vn[ND_MAX], vp[ND_MAX];          // natural values of the current state / of the proposal (recorded without re-transforming)
+    for (int d = 0; d < sv.nd; d++) {
+        qs[d] = sv.q[chain * sv.nd + d];
+        transform_dim(sv.pr[d], qs[d], vn[d]);
+    }
     for (int v = 0; v < NVAL; v++) vals[v] = sv.val_defaults[v];
     double logp = sv.logp[chain], lamb = sv.lamb[chain], scal = sv.scal[chain];
     int acc_win = sv.acc_win[chain];
@@ -390,18 +394,20 @@ __global__ void k_mcmc_ng(SamplerView sv, RunArgs ra) {
             qp[d] = qn;
             double v;
             lps += transform_dim(sv.pr[d], qn, v);
+            vp[d] = v;
             vals[sv.pr[d].target] = v;
         }
         // forward model: ce_exc_wrapper (ng_interp/noble_gas_mcmc.py:205-213) with T from the lapse-rate line (:240)
         double Ae = exp10(vals[0]), F = exp10(vals[1]), E = vals[2];
         double T = (E - vals[4]) / vals[3];
-        double P = ce_lapse_rate(E);
+        double P = ce_lapse_rate_step(E);
+        const CeStep cs = ce_step(T, P);
         double nu = sv.nu_sampled ? sv.nu_lo + (sv.nu_hi - sv.nu_lo) * vals[VAL_NU] : sv.nu_fixed;
         double cst = sv.lik_kind == 1 ? lik_studentt_const(nu) : 0.0;
         double ll = 0.0;
         const long long grp = sv.cpg > 0 ? gchain / sv.cpg : 0;
         for (int g = 0; g < sv.gases.n; g++) {
-            double mu = ce_eval(0, sv.gases.id[g], E, T, Ae, F, P, 0.0);
+            double mu = ce_exc_step(sv.gases.id[g], cs, E, T, Ae, F, P);
             double ob = sv.cpg > 0 ? sv.g_obs[grp * sv.gases.n + g] : sv.obs[g];
             double is = sv.cpg > 0 ? sv.g_isd[grp * sv.gases.n + g] : sv.isd[g];
             double lc = sv.cpg > 0 ? sv.g_lc[grp * sv.gases.n + g] : sv.lc[g];
@@ -411,7 +417,7 @@ __global__ void k_mcmc_ng(SamplerView sv, RunArgs ra) {
         double delta = lpn - logp;
         bool acc = ra.mode == 1 || (isfinite(delta) && log(u01(sel.z, sel.w)) < delta);
         if (acc) {
-            for (int d = 0; d < sv.nd; d++) qs[d] = qp[d];
+            for (int d = 0; d < sv.nd; d++) { qs[d] = qp[d]; vn[d] = vp[d]; }
             logp = lpn;
             if (ra.mode == 0) { acc_win++; acc_tot++; }
         }
@@ -420,11 +426,7 @@ __global__ void k_mcmc_ng(SamplerView sv, RunArgs ra) {
             for (int d = 0; d < sv.nd; d++) sv.hist[ho + d] = qs[d];
             if (ra.record && ((i - ra.step0) % ra.thin) == 0) {
                 long long draw = ra.draw0 + (i - ra.step0) / ra.thin;
-                for (int d = 0; d < sv.nd; d++) {
-                    double v;
-                    transform_dim(sv.pr[d], qs[d], v);
-                    record_dim(sv, ra, chain, d, v, draw);
-                }
+                for (int d = 0; d < sv.nd; d++) record_dim(sv, ra, chain, d, vn[d], draw);
             }
         }
     }
