@@ -147,7 +147,11 @@ __device__ __forceinline__ double exp_scaled_bits(double t, const double* __rest
     const int ht = max(__double2hiint(t), HI_MIN);
     const unsigned int F = (unsigned int)__double2loint(t);
     const double g = __hiloint2double((int)(0x3FF00000u | (F >> 12)), (int)(F << 20));
+#ifdef NGRTD_ESTRIN
+    const double p = fma(g * g, fma(g, EXQ_C3, EXQ_C2), fma(g, EXQ_C1, EXQ_C0));      // depth 2 instead of 3, one more FP64 op
+#else
     const double p = fma(g, fma(g, fma(g, EXQ_C3, EXQ_C2), EXQ_C1), EXQ_C0);
+#endif
     // tbl points at this lane's copy: entry j is at tbl[j * TBL_REP]
     const int off = (ht << (3 + TBL_REP_BITS)) & ((TBL_N - 1) << (3 + TBL_REP_BITS));
     const double T = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(tbl) + off);
