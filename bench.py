@@ -39,8 +39,8 @@ F_STEP = 2.0 * L * (T_COUNTED + 1) * N_COMP          # 23,520 algorithmic flops 
 # DFMA 36.2-36.5 TFLOP/s burst and sustained, DMMA.8x8x4 36.96; MEASURED_PEAKS.json carries no FP64 entry.
 FP64_PEAK_TFLOPS = 36.45
 # dram__bytes_read.sum + dram__bytes_write.sum of k_forward at this workload, one `ncu --set full` capture
-# (profiles/r1_ncu_forward_summary.txt); per launch.
-NCU_DRAM_BYTES_PER_LAUNCH = 3.87e6
+# (profiles/r1_ncu_forward_summary_final.txt: dram__bytes_read.sum 4.17 MB, dram__bytes_write.sum 0); per launch.
+NCU_DRAM_BYTES_PER_LAUNCH = 4.17e6
 METRIC = "likelihood evals/sec (chains x draws x tracers)"
 UNIT = "tracer-likelihood evals/s"
 
