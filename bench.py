@@ -157,10 +157,35 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries loaded later may chat on fd 1 (NCCL prints its version banner
+    there whenever NCCL_DEBUG is VERSION / WARN / INFO), so fd 1 is pointed at stderr for the run and the JSON line is
+    written to the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -186,9 +211,6 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # rank 0 prints ONE JSON line on stdout: NCCL's version banner / warnings (NCCL_DEBUG=VERSION|WARN|INFO write to
-        # stdout by default) go to stderr instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     pn = list(synthetic.PAR_NAMES_CFG3)
     plan, _, _ = synth_plan("exp_pist_flow", "dispersion", pn, device=local)
@@ -391,7 +413,7 @@ def main():
                                             "MEASURED_PEAKS.json has no FP64 entry",
                              "kernel": "k_forward<G,D>", "kernel_ms": kern_ms, "flops_per_chain": F_STEP},
                 "cpu_baseline": cpu, "sampler": sampler_info, "ess": ess_info, "checksum_logp": checksum}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
