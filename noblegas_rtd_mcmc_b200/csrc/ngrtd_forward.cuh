@@ -305,6 +305,43 @@ struct WarpTiles {
         // steady state: UA groups per iteration, each group feeding its own accumulator set so that
         // consecutive DMMAs of one tile are independent (hides the DMMA dependent-issue latency)
         int g = 1;
+#ifdef NGRTD_BURST
+        // experiment (profiles/r1_notes.md, "burst"): weights of TWO lag groups first, then their DMMAs back to back, so that
+        // the shared pipe alternates less often between DFMA and DMMA work
+        if constexpr (!DYN) {
+            for (; g + 2 <= ngroups; g += 2) {
+                double bf[2], bd[2] = {0.0, 0.0};
+                double w1[NT][2], w2[NT][2];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    k += 4;
+                    pf += 4 * NCOL;
+                    bf[u] = pf[0];
+                    double2 it = make_double2(0.0, 0.0);
+                    if constexpr (ANY_D) { pd += 4 * NCOL; pi += 4; bd[u] = pd[0]; it = pi[0]; }
+#pragma unroll
+                    for (int t = 0; t < NT; t++) {
+                        w1[t][u] = w2[t][u] = 0.0;
+                        if constexpr (C1 == CLS_G) w1[t][u] = c1[t].next(k);
+                        if constexpr (C1 == CLS_D) w1[t][u] = c1[t].weight(it, tbl);
+                        if constexpr (C2 == CLS_G) w2[t][u] = c2[t].next(k);
+                        if constexpr (C2 == CLS_D) w2[t][u] = c2[t].weight(it, tbl);
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < NT; t++)
+                    asm volatile("" : "+d"(w1[t][0]), "+d"(w1[t][1]), "+d"(w2[t][0]), "+d"(w2[t][1]));
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+#pragma unroll
+                    for (int t = 0; t < NT; t++) {
+                        if constexpr (LOOP1) dmma884(a1[t][0][0], a1[t][0][1], w1[t][u], (C1 == CLS_D) ? bd[u] : bf[u]);
+                        if constexpr (LOOP2) dmma884(a2[t][0][0], a2[t][0][1], w2[t][u], (C2 == CLS_D) ? bd[u] : bf[u]);
+                    }
+                }
+            }
+        }
+#endif
         for (; g + UA <= ngroups; g += UA) {
 #pragma unroll
             for (int u = 0; u < UA; u++) {
