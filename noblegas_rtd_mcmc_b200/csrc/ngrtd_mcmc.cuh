@@ -349,7 +349,10 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
 
 // ---------------------------------------------------------------- noble-gas CE model: one chain per thread
 // value registers (ng_interp/noble_gas_mcmc.py:224-250): 0 log10 Ae, 1 log10 F, 2 E, 3 m, 4 b, 11 nu_;  T = (E - b)/m
-__global__ void k_mcmc_ng(SamplerView sv, RunArgs ra) {
+#ifndef NGRTD_NG_MINBLOCKS
+#define NGRTD_NG_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(64, NGRTD_NG_MINBLOCKS) k_mcmc_ng(SamplerView sv, RunArgs ra) {
     const long long chain = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (chain >= sv.B) return;
     const long long gchain = sv.chain_offset + chain;
