@@ -231,3 +231,31 @@ def test_joint_exp_pist_flow_inversion_matches_reference_trace(well):
     if well != "PLM1":
         assert in_mode.mean() > 0.95, in_mode.mean()
     _compare(fx, t, names, tr[:, in_mode, :], skip=("nu_",))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tracer", ["CFC12", "SF6", "He4_ter"])
+def test_device_sampler_reproduces_single_tracer_traces(tracer):
+    """The nine remaining `<well>.<tracer>.exponential.0` inversions on the device sampler (reference settings, 256 chains) against
+    the quantiles of the pymc3 traces; obs_err is the one scalar per trace of tests/golden/age_obs_err.json (in sample)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fit_obs_err as F
+    from helpers import real_plan
+    from noblegas_rtd_mcmc_b200.sampler import Sampler, prior
+    fx, rel = fixture(), json.load(open(OBS_ERR))["rel"]
+    p = np.array(fx["qgrid"]) / 100.0
+    plan, _ = real_plan("exponential", False, ["tau1"], [tracer])
+    for well in ("PLM1", "PLM6", "PLM7"):
+        t = fx["traces"]["%s.%s.exponential.0" % (well, tracer)]
+        obs, v = t["obs_mu"][0], t["vars"]["tau1"]
+        smp = Sampler([prior("uniform", "tau1", 1.0, F.TAU_HI[tracer]), prior("beta", "nu_", 2.0, 0.1)], np.array([obs]),
+                      np.array([rel[tracer][well] * obs]), 256, plan=plan, lik="studentt", nu_range=(5.0, 30.0),
+                      tune_interval=1000, hist_cap=20000, seed=123423)
+        tau = smp.sample(10000, 10000, thin=5).cpu().numpy()[:, :, 0].ravel()
+        smp.close()
+        Fq = np.array([(tau <= q).mean() for q in v["q"]])
+        sig = np.sqrt(p * (1.0 - p) / min(v["ess_bulk"], v["ess_tail"]))
+        assert np.all(np.abs(Fq - p) < 4.5 * sig + 0.005), (tracer, well, np.round(Fq - p, 4))
+        assert abs(tau.mean() - v["mean"]) < 4.0 * v["mcse_mean"] + 0.01 * v["sd"], (tracer, well, tau.mean(), v["mean"])
+
