@@ -12,8 +12,9 @@
  *     ngrtd_last_error() returns a thread-local message for the last failure.
  *   - `*_dev` entry points take DEVICE pointers plus a CUDA stream handle (cudaStream_t cast to
  *     void*; NULL = default stream); they enqueue work and return without synchronising.
- *   - `*_host` entry points take HOST pointers (pinned or pageable), copy in, run, copy out and
- *     synchronise before returning.
+ *   - `*_host` entry points take HOST pointers and synchronise before returning.  Pinned (page-locked) parameter and
+ *     logp buffers are read / written by the kernel directly (zero-copy over PCIe); pageable buffers go through a
+ *     staged copy-in / kernel / copy-out pipeline.  Same results either way.
  *   - all floating point data is IEEE double; matrices are row-major; batches are [B, n].
  *   - numerical pathologies propagate as NaN / the -9999 sentinel exactly like the reference
  *     (no error is raised for bad parameter values).

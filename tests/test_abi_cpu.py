@@ -72,3 +72,16 @@ def test_dropin_signatures_match_reference():
     assert list(inspect.signature(ram.ForwardMod.__init__).parameters) == ["self", "conv_kwgs", "par_names", "tracer"]
     assert list(inspect.signature(ram.ForwardMod.perform).parameters) == ["self", "node", "inputs", "outputs"]
     assert ng.J_flux(1, 2700, 1000, 3.7, 10.2, 0.05) == 3.7657277999999995e-11
+
+
+def test_header_is_plain_c_and_links(lib, tmp_path):
+    """include/ngrtd.h compiles as strict C99 and examples/c_abi_demo.c links against libngrtd.so (it runs on a GPU box only)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "c_abi_demo")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-O1", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "c_abi_demo.c"), "-o", exe, "-L" + os.path.dirname(SO), "-lngrtd",
+                           "-Wl,-rpath," + os.path.dirname(SO), "-lm"])
+    assert os.path.exists(exe)
