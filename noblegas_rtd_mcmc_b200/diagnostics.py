@@ -182,7 +182,24 @@ def save_trace(path, posterior, sample_stats=None, attrs=None):
 
 
 def load_trace(path):
-    """Inverse of `save_trace`: returns {"posterior": {...}, "sample_stats": {...}, "attrs": {...}}."""
+    """Inverse of `save_trace`: returns {"posterior": {...}, "sample_stats": {...}, "attrs": {...}}.
+    A NetCDF-4 / HDF5 file -- the format the reference itself writes with `az.to_netcdf` (run_age_mcmc_utils.py:425) and reads
+    with `az.from_netcdf` (:434) -- is recognised by its signature and read with `netcdf4_reader.read_trace`: same layout, plus
+    `observed_data`; coordinate variables (`chain`, `draw`, `*_dim_0`) are dropped and `attrs` are those of the posterior group."""
+    with open(path, "rb") as fh:
+        magic = fh.read(8)
+    if magic == b"\x89HDF\r\n\x1a\n":
+        from . import netcdf4_reader
+        raw = netcdf4_reader.read_trace(path)
+        tr = {"posterior": {}, "sample_stats": {}, "observed_data": {}, "attrs": {}}
+        for grp in ("posterior", "sample_stats", "observed_data"):
+            for k, v in raw.get(grp, {}).items():
+                if k in ("chain", "draw") or k.endswith("_dim_0"):
+                    continue
+                tr[grp][k] = v
+        for k, v in raw["attrs"].get("posterior", {}).items():
+            tr["attrs"][k] = v.reshape(-1)[0].item() if isinstance(v, np.ndarray) and v.size == 1 else v
+        return tr
     tr = {"posterior": {}, "sample_stats": {}, "attrs": {}}
     with np.load(path) as z:
         for k in z.files:

@@ -92,6 +92,22 @@ def test_netcdf4_reader_reproduces_the_fixture():
         assert np.array_equal(tr["sample_stats"]["accepted"].mean(), t["accept_rate"])
 
 
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree only exists in the build container")
+def test_load_trace_reads_the_reference_netcdf_like_its_own_npz(tmp_path):
+    """diagnostics.load_trace on a reference trace -> the layout of our own traces; summary() then gives az.summary's columns."""
+    from noblegas_rtd_mcmc_b200 import diagnostics as D
+    tr = D.load_trace(os.path.join(REF, "PLM1.CFC12.SF6.H3.He4_ter.exp_pist_flow.123.netcdf"))
+    assert sorted(tr["posterior"]) == ["J", "eta1", "lamsf6", "nu", "nu_", "tau1", "thalf_cfc", "thalf_cfc_"]
+    assert tr["posterior"]["tau1"].shape == (3, 10000) and tr["observed_data"]["like"].shape == (4,)
+    assert tr["attrs"]["inference_library"] == "pymc3" and 296.0 < tr["attrs"]["sampling_time"] < 324.0
+    summ = D.summary({k: tr["posterior"][k] for k in ("tau1", "eta1")})
+    fxv = fixture()["traces"]["PLM1.CFC12.SF6.H3.He4_ter.exp_pist_flow.123"]["vars"]
+    assert summ["tau1"]["ess_bulk"] == pytest.approx(fxv["tau1"]["ess_bulk"]) and summ["eta1"]["r_hat"] == pytest.approx(fxv["eta1"]["r_hat"])
+    D.save_trace(str(tmp_path / "t.npz"), tr["posterior"], tr["sample_stats"], tr["attrs"])
+    back = D.load_trace(str(tmp_path / "t.npz"))
+    assert np.array_equal(back["posterior"]["tau1"], tr["posterior"]["tau1"])
+
+
 @pytest.mark.parametrize("well", ["PLM1", "PLM6", "PLM7"])
 def test_reference_h3_posteriors_match_the_restated_model(well):
     """pymc3's own draws vs the exact posterior of the restated prior x Student-T likelihood x oracle forward model:
