@@ -18,6 +18,21 @@ pri = [prior("uniform", "tau1", 1.0, 1000.0), prior("beta", "nu_", 2.0, 0.1), pr
        prior("uniform", "tau2", 50.0, 15000.0), prior("uniform", "f1", 0.01, 0.99),
        prior("beta", "thalf_cfc", 2.0, 2.0, lo=5.0, hi=35.0), prior("halfnormal", "lamsf6", 0.5 / 3)]
 p = np.array(fx["qgrid"]) / 100
+smp = Sampler(pri, obs, sd, 1024, plan=plan, lik="studentt", nu_range=(5.0, 30.0), f2_from_f1=True, tune_interval=1000, hist_cap=20000, seed=123423)
+tr = smp.sample(10000, 10000, thin=5).cpu().numpy(); smp.close()
+names = [q["target"] for q in pri]
+t2 = tr[:, :, names.index("tau2")]
+young = (t2 < 200.0).mean(axis=0)                 # per chain: share of draws with the piston component younger than 200 yr
+print("share of draws with tau2 < 200 per chain: quantiles", np.round(np.percentile(young, [0, 10, 25, 50, 75, 90, 100]), 3))
+for label, sel in (("all chains", young >= 0), ("chains with < 2 %% young-piston draws (%d)" % (young < 0.02).sum(), young < 0.02),
+                   ("chains with > 20 %% young-piston draws (%d)" % (young > 0.2).sum(), young > 0.2)):
+    print(label)
+    if sel.sum() == 0:
+        continue
+    for i, nm in enumerate(names):
+        v = t["vars"][nm]; a = tr[:, sel, i].ravel()
+        F = np.array([(a <= x).mean() for x in v["q"]])
+        print("     %-10s ours %10.4g +- %-9.3g ref %10.4g +- %-9.3g  max|F-p| %.3f" % (nm, a.mean(), a.std(), v["mean"], v["sd"], np.abs(F - p).max()))
 for label, sdv in (("as fitted", sd), ("SF6 error x 100 (uninformative)", sd * np.array([1, 100.0, 1, 1])), ("CFC12 error x 100", sd * np.array([100.0, 1, 1, 1])),
                    ("H3 error x 100", sd * np.array([1, 1, 100.0, 1])), ("He4 error x 100", sd * np.array([1, 1, 1, 100.0]))):
     smp = Sampler(pri, obs, sdv, 512, plan=plan, lik="studentt", nu_range=(5.0, 30.0), f2_from_f1=True, tune_interval=1000, hist_cap=20000, seed=123423)
