@@ -311,7 +311,12 @@ def main():
                 plan.forward_loglik_host_submit(host_thetas[i % 8].numpy(), pn, obs, sd, "normal", logp_out=hls[i % DEPTH],
                                                 slot=i % DEPTH)
 
-    e2e_pipelined(4)
+    # Warm-up of this call path: every (host buffer, slot) pair once (8 buffers x DEPTH slots) and long enough (>= 10 ms of
+    # back-to-back batches) that the timed run does not start behind the idle gap of the pinned allocations above -- with
+    # 4 warm-up batches the first timed run of a process sometimes measured 0.15-0.18 ms/step while every later run of
+    # the same process measured 0.114 (profiles/r1_notes.md, "e2e warm-up").
+    e2e_warm = max(args.warmup, 100)
+    e2e_pipelined(e2e_warm)
     e2e_s = timed(lambda: e2e_pipelined(args.steps))
     e2e_value = world * B * T_COUNTED * args.steps / e2e_s
 
@@ -395,7 +400,7 @@ def main():
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * len(pn) * 8, "d2h_bytes_per_step": B * 8,
-                        "ms_per_step": 1e3 * e2e_s / args.steps,
+                        "ms_per_step": 1e3 * e2e_s / args.steps, "warmup_steps": e2e_warm,
                         "note": "theta of a step was just written by the copy engine (L2-warm); `value` rotates 40 batches so "
                                 "that its theta comes from HBM",
                         "call": "ngrtd_forward_loglik_host_submit / ngrtd_host_wait, %d independent batches in flight: pinned "

@@ -174,8 +174,8 @@ extern "C" int ngrtd_plan_create(ngrtd_plan** out, int32_t L, int32_t nseries, c
                 else if (ck.mode == 2) v = (lag_index ? lag_index[k] : (double)k) * dec;     // :323 index * J
                 else v = series[(size_t)k * nseries + ck.series] * dec;
             }
-            Xf[(size_t)k * NCOL + c] = v;
-            Xd[(size_t)k * NCOL + c] = v * p15[k];
+            Xf[(size_t)xf_index(k, (int)c)] = v;
+            Xd[(size_t)xf_index(k, (int)c)] = v * p15[k];
         }
         if (P->dyn && dyn_series >= 0) {
             xraw[k] = series[(size_t)k * nseries + dyn_series];

@@ -12,6 +12,22 @@ constexpr int NSLOT = 11;               // ForwardMod.p_dict slots
 constexpr int MAX_TRACER = 8;
 constexpr int LC_MAX = 1024;            // lags resident in shared memory per chunk
 
+// Layout of the folded tables Xf / Xd (global and shared memory alike), addressed through xf_index(lag, column).
+// Default: plain [lag][8 columns] rows.  The B fragment of DMMA.8x8x4 makes lane (r = lane >> 2, j = lane & 3) read
+// X[4g + j][r]; a 64-bit shared load is served per half-warp (lanes 0-15: r = 0..3), which with plain rows covers
+// 4 x 32 bytes at a 64-byte stride -- lags j and j + 2 fall on the same banks and every B-fragment load costs 4 wavefronts
+// instead of 2 (ncu source page).  -DNGRTD_XF_SWIZZLE stores each group of 4 lags as [column half][lag][column & 3] so
+// that a half-warp reads one contiguous 128-byte line (2 wavefronts per load).  Measured on the B200 (profiles/r1_notes.md,
+// "session 3"): bit-identical results, all GPU tests green, forward launch 0.1153 -> 0.1170 ms, sampler -2 % -- the lag
+// loop is held by the FP64/DMMA pipe, not by the LSU data pipe, so the plain layout stays the default.
+__host__ __device__ __forceinline__ int xf_index(int k, int c) {
+#ifdef NGRTD_XF_SWIZZLE
+    return (k >> 2) * (4 * NCOL) + (c >> 2) * 16 + (k & 3) * 4 + (c & 3);
+#else
+    return k * NCOL + c;
+#endif
+}
+
 // table-driven exp(): exp(e) = 2^(n/N) * q(g), n = floor(e*N/ln2), g = 1 + frac(e*N/ln2)  (exp_scaled_bits below).
 // The N-entry table of 2^(j/N) lives in shared memory as 8-byte entries, replicated TBL_REP times: lane l gathers from
 // copy l & (TBL_REP-1) at double index j*TBL_REP + copy.  A 64-bit shared load is served per half-warp; with 16 copies

@@ -10,7 +10,7 @@
 //   chains, K = lags).  tcgen05 has no FP64 kind, so the reduction runs on the FP64 pipe as
 //   mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4): one warp instruction = 8 chains x 4 lags x 8 columns.  Lane
 //   (r = lane>>2, j = lane&3) GENERATES the weight of chain r at lag 4g+j in registers (A fragment), loads
-//   X[4g+j][r] from shared memory (B fragment, conflict-free 256 B row group), and owns output columns
+//   X[4g+j][r] from shared memory (B fragment; layout: xf_index() in ngrtd_common.cuh), and owns output columns
 //   2j, 2j+1 of chain r (C fragment).  Weights never touch memory.
 //     * exponential / exp_pist_flow: geometric recurrence v <- v*r^4, re-anchored by a true exp() at every
 //       chunk start; the mask tp >= tau(1-1/eta) is an integer compare against k0.
@@ -273,8 +273,8 @@ struct WarpTiles {
         if (!ANY_LOOP) return;
         const int j = lane & 3, r = lane >> 2;
         int k = kc + j;
-        const double* pf = ngrtd_smem + s.Xf + j * NCOL + r;
-        const double* pd = ngrtd_smem + s.Xd + j * NCOL + r;
+        const double* pf = ngrtd_smem + s.Xf + xf_index(j, r);     // chunks start at multiples of 4 lags
+        const double* pd = ngrtd_smem + s.Xd + xf_index(j, r);
         const double2* pi = reinterpret_cast<const double2*>(ngrtd_smem + s.itp) + j;
         const double* px = ngrtd_smem + s.xraw + j;
         const double* pxd = ngrtd_smem + s.xrawd + j;
@@ -305,6 +305,16 @@ struct WarpTiles {
         // steady state: UA groups per iteration, each group feeding its own accumulator set so that
         // consecutive DMMAs of one tile are independent (hides the DMMA dependent-issue latency)
         int g = 1;
+        // {1/tp, tp} of the lane's lag.  Beyond the first group of a chunk tp = k + dtp is an exactly representable
+        // integer, so with -DNGRTD_TP_DADD it is carried in a register (+= 4.0, exact) and only 1/tp is loaded: one LDS.64
+        // (2 wavefronts) instead of one LDS.128 (4 wavefronts) per group, for one DADD per group shared by the NT tiles.
+        // Experiment (profiles/r1_notes.md, "session 3"): forward launch -1.6 %, sampler step +4.5 % -> not the default.
+#ifdef NGRTD_TP_DADD
+        double tpk = (double)k + dtp;
+#define NGRTD_LOAD_IT(it_) do { tpk += 4.0; (it_).x = pi[0].x; (it_).y = tpk; } while (0)
+#else
+#define NGRTD_LOAD_IT(it_) do { (it_) = pi[0]; } while (0)
+#endif
 #ifdef NGRTD_BURST
         // experiment (profiles/r1_notes.md, "burst"): weights of TWO lag groups first, then their DMMAs back to back, so that
         // the shared pipe alternates less often between DFMA and DMMA work
@@ -350,7 +360,7 @@ struct WarpTiles {
                 double bf = pf[0];
                 double bd = 0.0, xr = 0.0, xrd = 0.0;
                 double2 it = make_double2(0.0, 0.0);
-                if constexpr (ANY_D) { pd += 4 * NCOL; pi += 4; bd = pd[0]; it = pi[0]; }
+                if constexpr (ANY_D) { pd += 4 * NCOL; pi += 4; bd = pd[0]; NGRTD_LOAD_IT(it); }
                 if constexpr (DYN) { px += 4; xr = px[0]; if constexpr (ANY_D) { pxd += 4; xrd = pxd[0]; } }
 #pragma unroll
                 for (int t = 0; t < NT; t++) {
@@ -374,7 +384,7 @@ struct WarpTiles {
             double bf = pf[0];
             double bd = 0.0, xr = 0.0, xrd = 0.0;
                 double2 it = make_double2(0.0, 0.0);
-            if constexpr (ANY_D) { pd += 4 * NCOL; pi += 4; bd = pd[0]; it = pi[0]; }
+            if constexpr (ANY_D) { pd += 4 * NCOL; pi += 4; bd = pd[0]; NGRTD_LOAD_IT(it); }
             if constexpr (DYN) { px += 4; xr = px[0]; if constexpr (ANY_D) { pxd += 4; xrd = pxd[0]; } }
 #pragma unroll
             for (int t = 0; t < NT; t++) {
@@ -392,6 +402,8 @@ struct WarpTiles {
             }
         }
     }
+
+#undef NGRTD_LOAD_IT
 
     // normalise, mix the two components, apply tracer rules; lane (r, j) returns the outputs of tracers
     // j, j+4 of chain r in val[0..1] (NaN-propagating exactly like f1*cout1 + f2*cout2 of the reference)
@@ -455,8 +467,8 @@ struct WarpTiles {
             // component 1
             if constexpr (C1 == CLS_P) {
                 int ix = c1[t].ix;
-                x1[0] = pv.Xf[ix * NCOL + 2 * j];
-                x1[1] = pv.Xf[ix * NCOL + 2 * j + 1];
+                x1[0] = pv.Xf[xf_index(ix, 2 * j)];
+                x1[1] = pv.Xf[xf_index(ix, 2 * j + 1)];
                 if (DYN) {
                     double tp = ((ix == 0) ? 1e-5 : (double)ix) + pv.dtp;
                     xd1 = pv.xraw[ix] * exp(-p[t].lam_cfc * tp);
@@ -480,8 +492,8 @@ struct WarpTiles {
             }
             if constexpr (C2 == CLS_P) {
                 int ix = c2[t].ix;
-                x2[0] = pv.Xf[ix * NCOL + 2 * j];
-                x2[1] = pv.Xf[ix * NCOL + 2 * j + 1];
+                x2[0] = pv.Xf[xf_index(ix, 2 * j)];
+                x2[1] = pv.Xf[xf_index(ix, 2 * j + 1)];
                 if (DYN) {
                     double tp = ((ix == 0) ? 1e-5 : (double)ix) + pv.dtp;
                     xd2 = pv.xraw[ix] * exp(-p[t].lam_cfc * tp);
