@@ -212,6 +212,16 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    numa = None
+    if world > 1:
+        # one process per GPU: keep each rank (and the pinned host buffers it allocates below) on its GPU's NUMA node
+        from noblegas_rtd_mcmc_b200 import distributed as ngdist0
+        try:
+            pr = torch.cuda.get_device_properties(local)
+            numa = ngdist0.bind_to_gpu_numa("%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id))
+        except Exception as exc:                                   # never let placement tuning stop a benchmark
+            numa = "unchanged (%s)" % type(exc).__name__
+        print("rank %d: cpu placement %s" % (rank, numa), file=sys.stderr, flush=True)
     pn = list(synthetic.PAR_NAMES_CFG3)
     plan, _, _ = synth_plan("exp_pist_flow", "dispersion", pn, device=local)
     B = CHAINS_PER_GPU
@@ -410,7 +420,7 @@ def main():
                                               "theta over PCIe (one TMA bulk copy per 16-chain unit, next unit prefetched) and stores "
                                               "logp straight into the pinned host buffer"}},
                 "gpu_launches": args.steps,
-                "clocks": clocks, "per_rank_ms_per_step": per_rank,
+                "clocks": clocks, "per_rank_ms_per_step": per_rank, "cpu_placement": numa,
                 "roofline": {"bound": "tensor", "pipe": "fp64: DMMA.8x8x4 (tensor sub-pipe) shares the FP64 pipe with DFMA",
                              "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                              "frac": achieved / FP64_PEAK_TFLOPS, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,

@@ -4,6 +4,38 @@ goes through the gloo backend."""
 import numpy as np
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(pci_bus_id, sysfs_root="/sys/bus/pci/devices"):
+    """Pin the calling process to the CPUs next to its GPU (one process per GPU on a multi-socket box), so that pinned host
+    buffers allocated afterwards are first-touched on the GPU's own NUMA node and the host-buffer entry points do not pull
+    their parameter batches across the socket interconnect.  Deliberately conservative: acts only when sysfs reports a NUMA
+    node >= 0 for the device and its local CPU list is a non-empty strict subset of the CPUs this process may run on; in
+    every other case (single-node hosts, VMs that hide the topology, unreadable sysfs) it changes nothing.
+    Returns a short description of what was done (for logs / the bench line)."""
+    import os
+    try:
+        dev = os.path.join(sysfs_root, pci_bus_id.lower())          # "dddd:bb:dd.f", e.g. 0000:c0:00.0
+        node = int(open(os.path.join(dev, "numa_node")).read().strip())
+        local = _parse_cpulist(open(os.path.join(dev, "local_cpulist")).read())
+    except (OSError, ValueError):
+        return "unchanged (no sysfs topology for %s)" % pci_bus_id
+    allowed = os.sched_getaffinity(0)
+    target = local & allowed
+    if node < 0 or not target or target == allowed:
+        return "unchanged (numa_node %d, %d local of %d allowed cpus)" % (node, len(target), len(allowed))
+    os.sched_setaffinity(0, target)
+    return "bound to numa node %d (%d of %d cpus)" % (node, len(target), len(allowed))
+
+
 def shard(total, rank, world):
     """Contiguous block of global chain ids for `rank`: (offset, count).  Philox counters use global ids, so a chain's
     trajectory does not depend on the sharding."""

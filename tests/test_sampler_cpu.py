@@ -168,3 +168,29 @@ def test_summary_columns_match_reference_tables(tmp_path):
     dg.summary_csv(tmp_path / "s.csv", {"x": x})
     head = open(tmp_path / "s.csv").readline().strip()
     assert head == ",mean,sd,hdi_3%,hdi_97%,mcse_mean,mcse_sd,ess_bulk,ess_tail,r_hat,median"
+
+
+def test_bind_to_gpu_numa_is_conservative(tmp_path):
+    """distributed.bind_to_gpu_numa acts only on a real multi-node topology: strict subset of the allowed CPUs and a
+    NUMA node >= 0; everything else leaves the affinity untouched."""
+    import os
+    from noblegas_rtd_mcmc_b200 import distributed as D
+    before = os.sched_getaffinity(0)
+    try:
+        assert D._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+        assert D.bind_to_gpu_numa("0000:ff:1f.0", sysfs_root=str(tmp_path)).startswith("unchanged")      # no sysfs entry
+        dev = tmp_path / "0000:c0:00.0"
+        dev.mkdir()
+        allcpus = ",".join(str(c) for c in sorted(before))
+        (dev / "numa_node").write_text("-1\n"); (dev / "local_cpulist").write_text(allcpus + "\n")
+        assert D.bind_to_gpu_numa("0000:C0:00.0", sysfs_root=str(tmp_path)).startswith("unchanged")      # VM: node -1
+        (dev / "numa_node").write_text("0\n")
+        assert D.bind_to_gpu_numa("0000:c0:00.0", sysfs_root=str(tmp_path)).startswith("unchanged")      # single node
+        assert os.sched_getaffinity(0) == before
+        if len(before) >= 2:
+            keep = sorted(before)[: len(before) // 2]
+            (dev / "numa_node").write_text("1\n"); (dev / "local_cpulist").write_text(",".join(map(str, keep)) + ",9999\n")
+            msg = D.bind_to_gpu_numa("0000:c0:00.0", sysfs_root=str(tmp_path))
+            assert msg.startswith("bound to numa node 1") and os.sched_getaffinity(0) == set(keep)
+    finally:
+        os.sched_setaffinity(0, before)
