@@ -188,7 +188,9 @@ extern "C" int ngrtd_plan_create(ngrtd_plan** out, int32_t L, int32_t nseries, c
         pv.Kc = Lpad;
         pv.dyn_bg = 0.0;
         for (int c = 0; c < NCOL; c++) pv.ct[c] = ColTail{-1, 0.0, 0.0, 0.0, 0.0};
-        const bool want = getenv("NGRTD_NO_TAIL") == nullptr && c1 != CLS_D && c2 != CLS_D && (c1 == CLS_G || c2 == CLS_G);
+        const bool any_d = c1 == CLS_D || c2 == CLS_D, any_g = c1 == CLS_G || c2 == CLS_G;
+        // dispersion components: only in NGRTD_DM_TAIL builds, and not together with a per-chain decay constant (thalf_cfc)
+        const bool want = getenv("NGRTD_NO_TAIL") == nullptr && (any_d ? (DM_TAIL && !P->dyn) : any_g);
         if (want && L >= 64) {
             int kvar = 0;                                       // first lag from which every used series is constant
             auto scan = [&](int sidx) {
@@ -330,7 +332,7 @@ template <int C1, int C2, bool DYN, int NT, int UA, int MAXW>
 static int launch_forward_t(ngrtd_plan* P, const SlotMap& sm, const double* theta, long long B, double* out,
                             double* logp, const LikPar& lik, cudaStream_t st, int stage, int warps_req) {
     using WT = WarpTiles<C1, C2, DYN, NT, UA>;
-    const int Lloop = (WT::ANY_G && !WT::ANY_D && P->pv.Kc < P->pv.L) ? P->pv.Kc : P->Lpad;
+    const int Lloop = tail_active(P->pv, WT::ANY_G, WT::ANY_D) ? P->pv.Kc : P->Lpad;
     int lc_cap = WT::ANY_LOOP ? std::min(Lloop, LC_MAX) : 0;
     long long nunits = (B + NT * 8 - 1) / (NT * 8);
     int warps = warps_req > 0 ? std::min(warps_req, MAXW) : pick_warps(nunits, P->nsm, MAXW);
@@ -1094,7 +1096,7 @@ static int launch_mcmc_age(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st)
     int warps = pick_warps(nunits, P->nsm, MAXW);
     if (warps > 4) warps &= ~3;
     // shared memory: forward tables + one CH_REC record per resident chain; shrink the lag chunk until it fits
-    const int Lloop = (WT::ANY_G && !WT::ANY_D && P->pv.Kc < P->pv.L) ? P->pv.Kc : P->Lpad;
+    const int Lloop = tail_active(P->pv, WT::ANY_G, WT::ANY_D) ? P->pv.Kc : P->Lpad;
     int lc_cap = WT::ANY_LOOP ? std::min(Lloop, LC_MAX) : 0;
     size_t sh = 0;
     for (;;) {

@@ -106,6 +106,19 @@ struct PlanView {
     double tpl, itpl;               // last lag of the grid, tp[L-1], and its reciprocal (dispersion dead-chain rule)
 };
 
+// Which plans cut the lag loop at Kc and add the tail [Kc, L) analytically in the epilogue: exponential-class components always
+// (closed form); dispersion components only in -DNGRTD_DM_TAIL builds (Gauss-Legendre quadrature of the smooth tail,
+// WarpTiles::dm_tail in ngrtd_forward.cuh; experimental in r1, see profiles/r1_notes.md).  Plan creation leaves Kc = Lpad when
+// the plan does not qualify.
+#ifdef NGRTD_DM_TAIL
+constexpr bool DM_TAIL = true;
+#else
+constexpr bool DM_TAIL = false;
+#endif
+__host__ __device__ __forceinline__ bool tail_active(const PlanView& pv, bool any_g, bool any_d) {
+    return (any_g || any_d) && (!any_d || DM_TAIL) && pv.Kc < pv.L;
+}
+
 struct SlotMap {
     int ndim;
     signed char col_of_slot[NSLOT];   // -1: not in par_names -> p_dict default

@@ -165,6 +165,12 @@ struct Comp<CLS_D> {
     }
 };
 
+// order-16 Gauss-Legendre nodes / weights on [-1, 1] (positive half) for WarpTiles::dm_tail
+__constant__ double DM_GX[8] = {0.095012509837637441, 0.28160355077925892, 0.45801677765722737, 0.61787624440264377,
+                                0.755404408355003, 0.86563120238783176, 0.9445750230732326, 0.98940093499164994};
+__constant__ double DM_GW[8] = {0.18945061045506864, 0.18260341504492364, 0.16915651939500265, 0.14959598881657671,
+                                0.12462897125553407, 0.095158511682492605, 0.062253523938647456, 0.027152459411754176};
+
 // ---------------------------------------------------------------- analytic tail of geometric weights
 // G0(x, n) = sum_{i<n} e^{-i x},  G1(x, n) = sum_{i<n} i e^{-i x}   (x = eta/tau + lambda >= 0)
 __device__ __forceinline__ double geo_sum0(double x, double n) {
@@ -405,6 +411,113 @@ struct WarpTiles {
 
 #undef NGRTD_LOAD_IT
 
+    // ---- dispersion tail (NGRTD_DM_TAIL builds) -------------------------------------------------------------------------
+    // Beyond Kc every folded column is an analytic function of the lag (PlanView::ct), so
+    //   sum_{k=Kc}^{L-1} w(tp_k) col(tp_k),   w(t) = t^-1.5 exp(-(t - tau)^2 / (4 D tau t))   (the loop's weight incl. Xd's t^-1.5)
+    // equals the integral over [tp_Kc - 1/2, tp_{L-1} + 1/2] minus the midpoint Euler-Maclaurin end terms g1/24 - 7 g3/5760
+    // (g1, g3: first and third derivative; the interior error is exponentially small for peaks wider than ~2 lags).
+    // Order-16 Gauss-Legendre panels, 2 per sigma = tau sqrt(2D) near the mode, widening geometrically away from it and
+    // never wider than 0.35 t; the 4 lanes of a chain take every 4th panel and all 8 columns, partial sums are combined by
+    // shuffles.  tools/dm_tail_prototype.py is the float64 prototype (8e-15 against the reference's golden vectors).
+    // Outside the validated domain (D outside [0.01, 2.5], tau < 1, mode more than 12 sigma beyond the last lag) the same
+    // analytic terms are summed lag by lag.
+    __device__ __forceinline__ static void dm_node(const PlanView& pv, double t, double wt, double tau, double c4,
+                                                   double (&acc)[NCOL]) {
+        const double dt = t - tau;
+        const double wgt = wt * exp(-dt * dt * c4 / t) / (t * sqrt(t));
+        acc[0] += wgt;
+        double last = 0.0, d = 1.0;
+#pragma unroll
+        for (int c = 1; c < NCOL; c++) {
+            const ColTail ct = pv.ct[c];
+            if (ct.type < 0) continue;
+            if (ct.lam != last) { d = exp(-ct.lam * t); last = ct.lam; }
+            double v;
+            if (ct.type == 1) v = ct.bg * d;
+            else if (ct.type == 2) v = ct.bg * (1.0 - d);
+            else v = (ct.i0 + ct.s * (t - pv.dtp)) * d;
+            acc[c] = fma(wgt, v, acc[c]);
+        }
+    }
+    // sgn * (g1/24 - 7 g3/5760) of every column at the end point t
+    __device__ __forceinline__ static void dm_end(const PlanView& pv, double t, double sgn, double tau, double a, double c4,
+                                                  double (&acc)[NCOL]) {
+        const double dt = t - tau, it = 1.0 / t;
+        const double w = exp(-dt * dt * c4 * it) * it / sqrt(t);
+        const double p1 = (1.5 - 2.0 * a * it) * it * it, p2 = (-3.0 + 6.0 * a * it) * it * it * it;
+        const double pb = (-1.5 + a * it) * it - c4;                  // log-derivative without the decay constant
+        auto terms = [&](double lam, double& g, double& g1, double& g2, double& g3) {
+            const double p = pb - lam;
+            g = w * exp(-lam * t);
+            g1 = g * p; g2 = g * (p * p + p1); g3 = g * (p * p * p + 3.0 * p * p1 + p2);
+        };
+        double g, g1, g2, g3;
+        terms(0.0, g, g1, g2, g3);
+        const double k1 = sgn / 24.0, k3 = -sgn * 7.0 / 5760.0;
+        acc[0] += k1 * g1 + k3 * g3;
+#pragma unroll
+        for (int c = 1; c < NCOL; c++) {
+            const ColTail ct = pv.ct[c];
+            if (ct.type < 0) continue;
+            double h, h1, h2, h3;
+            terms(ct.lam, h, h1, h2, h3);
+            if (ct.type == 1) acc[c] += ct.bg * (k1 * h1 + k3 * h3);
+            else if (ct.type == 2) acc[c] += ct.bg * (k1 * (g1 - h1) + k3 * (g3 - h3));
+            else {
+                const double q = ct.i0 + ct.s * (t - pv.dtp);
+                acc[c] += k1 * (ct.s * h + q * h1) + k3 * (3.0 * ct.s * h2 + q * h3);
+            }
+        }
+    }
+    __device__ __forceinline__ static void dm_tail(const PlanView& pv, double tau, double D, bool dead, int j, double& o0,
+                                                   double& o1) {
+        double acc[NCOL];
+#pragma unroll
+        for (int c = 0; c < NCOL; c++) acc[c] = 0.0;
+        if (!dead) {
+            const double lo = (double)pv.Kc - 0.5 + pv.dtp, hi = (double)pv.L - 0.5 + pv.dtp;
+            const double c4 = 1.0 / (4.0 * D * tau), a = tau / (4.0 * D);
+            const double sig = fmax(tau * sqrt(2.0 * D), 1.0);
+            const bool quad = D >= 0.01 && D <= 2.5 && tau >= 1.0 && tau - 12.0 * sig <= hi;
+            if (quad) {
+                const double wlo = fmax(lo, tau - 12.0 * sig);
+                const double whi = fmin(hi, fmax(fmax(tau + 60.0 * sig, tau + 200.0 * D * tau), lo + 1.0));
+                if (whi > wlo) {
+                    const double w = 0.5 * sig;
+                    double x = wlo;
+                    for (int pi = 0; x < whi; pi++) {
+                        const double ad = fabs(x - tau);
+                        double step = (ad < 6.0 * sig) ? w : fmax(w, 0.25 * ad);
+                        step = fmin(step, 0.35 * x);
+                        const double x1 = fmin(whi, x + step);
+                        if ((pi & 3) == j) {
+                            const double mid = 0.5 * (x1 + x), half = 0.5 * (x1 - x);
+#pragma unroll 1
+                            for (int q = 0; q < 16; q++) {
+                                const double gx = (q & 1) ? -DM_GX[q >> 1] : DM_GX[q >> 1];
+                                dm_node(pv, fma(half, gx, mid), half * DM_GW[q >> 1], tau, c4, acc);
+                            }
+                        }
+                        x = x1;
+                    }
+                    if (j == 0 && wlo == lo) dm_end(pv, lo, 1.0, tau, a, c4, acc);
+                    if (j == 1 && whi == hi) dm_end(pv, hi, -1.0, tau, a, c4, acc);
+                }
+            } else {
+#pragma unroll 1
+                for (int k = pv.Kc + j; k < pv.L; k += 4) dm_node(pv, (double)k + pv.dtp, 1.0, tau, c4, acc);
+            }
+        }
+        const unsigned full = 0xffffffffu;
+#pragma unroll
+        for (int c = 0; c < NCOL; c++) {
+            acc[c] += __shfl_xor_sync(full, acc[c], 1);
+            acc[c] += __shfl_xor_sync(full, acc[c], 2);
+        }
+        o0 += (j == 0) ? acc[0] : (j == 1) ? acc[2] : (j == 2) ? acc[4] : acc[6];
+        o1 += (j == 0) ? acc[1] : (j == 1) ? acc[3] : (j == 2) ? acc[5] : acc[7];
+    }
+
     // normalise, mix the two components, apply tracer rules; lane (r, j) returns the outputs of tracers
     // j, j+4 of chain r in val[0..1] (NaN-propagating exactly like f1*cout1 + f2*cout2 of the reference)
     __device__ __forceinline__ void end(const ChainPar (&p)[NT], const PlanView& pv, double* scratch_warp, int lane,
@@ -418,7 +531,7 @@ struct WarpTiles {
                 a1[t][0][0] += a1[t][u][0]; a1[t][0][1] += a1[t][u][1];
                 a2[t][0][0] += a2[t][u][0]; a2[t][0][1] += a2[t][u][1];
             }
-            if (ANY_G && !ANY_D && pv.Kc < pv.L) {      // analytic tail [Kc, L) of the exponential-class components
+            if (tail_active(pv, ANY_G, ANY_D)) {         // analytic tail [Kc, L): closed form (G), quadrature (D, NGRTD_DM_TAIL)
                 const double dtp = pv.dtp;
                 if constexpr (C1 == CLS_G) {
                     double a = (double)max(c1[t].k0, pv.Kc), n = (double)pv.L - a;
@@ -440,6 +553,8 @@ struct WarpTiles {
                             ad2[t] += Wa * pv.dyn_bg * exp(-p[t].lam_cfc * (a + dtp)) * geo_sum0(c2[t].er + p[t].lam_cfc, n);
                     }
                 }
+                if constexpr (DM_TAIL && C1 == CLS_D) dm_tail(pv, p[t].tau1, p[t].D1, c1[t].dead(), j, a1[t][0][0], a1[t][0][1]);
+                if constexpr (DM_TAIL && C2 == CLS_D) dm_tail(pv, p[t].tau2, p[t].D2, c2[t].dead(), j, a2[t][0][0], a2[t][0][1]);
             }
             double m[2], md = 0.0;
             double x1[2], x2[2] = {0.0, 0.0}, xd1 = 0.0, xd2 = 0.0;
@@ -624,7 +739,7 @@ struct FwdCta {
         s.xraw = p; if (DYN) p += lc_cap;
         s.xrawd = p; if (DYN && WT::ANY_D) p += lc_cap;
         scratch_off = s.scratch + warp * NT * 8 * NCOL;
-        Lloop = (WT::ANY_G && !WT::ANY_D && pv.Kc < pv.L) ? pv.Kc : pv.Lpad;
+        Lloop = tail_active(pv, WT::ANY_G, WT::ANY_D) ? pv.Kc : pv.Lpad;
         nchunks = WT::ANY_LOOP ? (Lloop + lc_cap - 1) / lc_cap : 1;
         need_J = false;
         for (int t = 0; t < pv.ntracer; t++) need_J |= (pv.tr[t].col_b >= 0);
