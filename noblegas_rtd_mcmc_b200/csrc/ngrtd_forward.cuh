@@ -417,9 +417,9 @@ struct WarpTiles {
     // equals the integral over [tp_Kc - 1/2, tp_{L-1} + 1/2] minus the midpoint Euler-Maclaurin end terms g1/24 - 7 g3/5760
     // (g1, g3: first and third derivative; the interior error is exponentially small for peaks wider than ~2 lags).
     // Order-16 Gauss-Legendre panels, 2 per sigma = tau sqrt(2D) near the mode, widening geometrically away from it and
-    // never wider than 0.35 t; the 4 lanes of a chain take every 4th panel and all 8 columns, partial sums are combined by
+    // never wider than 0.35 t; the 4 lanes of a chain take 4 of the 16 nodes of every panel and all 8 columns, partial sums are combined by
     // shuffles.  tools/dm_tail_prototype.py is the float64 prototype (8e-15 against the reference's golden vectors).
-    // Outside the validated domain (D outside [0.01, 2.5], tau < 1, mode more than 12 sigma beyond the last lag) the same
+    // Outside the validated domain (D outside [0.01, 2.5], mode more than 12 sigma beyond the last lag) the same
     // analytic terms are summed lag by lag.
     __device__ __forceinline__ static void dm_node(const PlanView& pv, double t, double wt, double tau, double c4,
                                                    double (&acc)[NCOL]) {
@@ -478,22 +478,23 @@ struct WarpTiles {
             const double lo = (double)pv.Kc - 0.5 + pv.dtp, hi = (double)pv.L - 0.5 + pv.dtp;
             const double c4 = 1.0 / (4.0 * D * tau), a = tau / (4.0 * D);
             const double sig = fmax(tau * sqrt(2.0 * D), 1.0);
-            const bool quad = D >= 0.01 && D <= 2.5 && tau >= 1.0 && tau - 12.0 * sig <= hi;
+            const bool quad = D >= 0.01 && D <= 2.5 && tau - 12.0 * sig <= hi;
             if (quad) {
                 const double wlo = fmax(lo, tau - 12.0 * sig);
                 const double whi = fmin(hi, fmax(fmax(tau + 60.0 * sig, tau + 200.0 * D * tau), lo + 1.0));
                 if (whi > wlo) {
                     const double w = 0.5 * sig;
                     double x = wlo;
-                    for (int pi = 0; x < whi; pi++) {
+                    while (x < whi) {
                         const double ad = fabs(x - tau);
                         double step = (ad < 6.0 * sig) ? w : fmax(w, 0.25 * ad);
                         step = fmin(step, 0.35 * x);
                         const double x1 = fmin(whi, x + step);
-                        if ((pi & 3) == j) {
+                        {   // the 4 lanes of the chain take 4 of the panel's 16 nodes each (no divergence inside a chain)
                             const double mid = 0.5 * (x1 + x), half = 0.5 * (x1 - x);
 #pragma unroll 1
-                            for (int q = 0; q < 16; q++) {
+                            for (int i = 0; i < 4; i++) {
+                                const int q = 4 * j + i;
                                 const double gx = (q & 1) ? -DM_GX[q >> 1] : DM_GX[q >> 1];
                                 dm_node(pv, fma(half, gx, mid), half * DM_GW[q >> 1], tau, c4, acc);
                             }

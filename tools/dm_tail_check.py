@@ -14,7 +14,7 @@ for name in ("dm", "dm_dm", "epm_dm", "dm_emm"):
     m1, m2, pn = CONFIGS[name]
     if "thalf_cfc" in pn:
         print("%-14s %-8s skipped (per-chain decay constant: plan keeps the full loop)" % (tag, name)); continue
-    plan = real_plan(m1, m2, pn, tracers)
+    plan, _ = real_plan(m1, m2, pn, tracers)
     th = z[name + "/theta"]
     out = plan.forward_host(th, pn)
     worst = 0.0
@@ -39,7 +39,7 @@ for name in ("dm", "dm_dm", "epm_dm", "dm_emm"):
     print("%-14s %-8s golden parity %.2e (%d thetas) | 16,384 chains %.3f ms per launch" % (tag, name, worst, len(th), ms), flush=True)
 # fallback domain: compare with the oracle's full sums
 pn = ["tau1", "D1"]
-plan = real_plan("dispersion", False, pn, tracers)
+plan, _ = real_plan("dispersion", False, pn, tracers)
 th = np.array([[150.0, 0.004], [131.0, 0.002], [9000.0, 0.003], [40000.0, 0.01], [60000.0, 0.02], [0.5, 1.0], [300.0, 3.0], [2000.0, 8.0]])
 out = plan.forward_host(th, pn)
 C = load_c_in()
