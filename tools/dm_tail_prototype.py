@@ -88,45 +88,53 @@ def head_direct(tau, D, Kc, X):
     return (base(tp, a, c)[:, None] * X[:Kc]).sum(0)
 
 
-z = np.load(os.path.join(GOLD, "forward_real.npz"))
-series = load_c_in()
-L, Kc = len(series["H3"]), 128
-lamH = np.log(2) / 12.34
-tracers = ["CFC12", "SF6", "H3", "He4_ter", "He3", "CFC11"]
-# folded columns: ones + one per tracer
-cols = [(0, 0, 0, 0, 0)]
-Xh = [np.ones(Kc)]
-tp = np.arange(Kc, dtype=np.float64); tp[0] += 1e-5
-for tr in tracers:
-    key, th, ra = REAL_TRACERS[tr]
-    if ra == "4He":
-        cols.append((3, 0.0, 0.0, 0.0, 1.0)); Xh.append(np.arange(Kc, dtype=np.float64))          # index * J (:323)
-    elif ra == "3He":
-        cols.append((2, float(series[key][-1]), lamH, 0, 0)); Xh.append(series[key][:Kc] * (1 - np.exp(-lamH * tp)))
-    elif th:
-        cols.append((1, float(series[key][-1]), lamH, 0, 0)); Xh.append(series[key][:Kc] * np.exp(-lamH * tp))
-    else:
-        cols.append((1, float(series[key][-1]), 0.0, 0, 0)); Xh.append(series[key][:Kc])
-Xh = np.stack(Xh, -1)
-for k in ("CFC12", "SF6", "H3", "CFC11"):
-    assert np.all(series[k][Kc:] == series[k][-1]), "series not constant beyond Kc"
-theta = z["dm/theta"]
-worst, nodes, skipped = 0.0, [], 0
-J = 10 ** O.DEFAULT_LOG10_J
-for i, (tau, D) in enumerate(theta):
-    if not (0.01 <= D <= 2.5 and tau >= 1.0):
-        skipped += 1; continue
-    tq, n = tail_quad(tau, D, Kc, L, cols)
-    tot = head_direct(tau, D, Kc, Xh) + tq
-    out = tot[1:] / tot[0]
-    for jx, tr in enumerate(tracers):
-        want = z["dm/" + tr][i]
-        got = out[jx] * (J if tr == "He4_ter" else 1.0)
-        if np.isfinite(want) and want != 0:
-            e = abs(got - want) / abs(want)
-            worst = max(worst, e)
-            if e > 1e-10: print("  tau %.4g D %.4g %s: got %.15g want %.15g rel %.2e" % (tau, D, tr, got, want, e))
-    nodes.append(n)
-print("golden 'dm' (reference output, real series L = %d, Kc = %d): %d parameter pairs (%d outside the validated domain skipped), "
-      "worst relative error %.2e, nodes median %d max %d (order %d, %.0f panels per sigma) vs %d direct tail terms" % (
-          L, Kc, len(nodes), skipped, worst, np.median(nodes), max(nodes), ORDER, PPS, L - Kc))
+def run(verbose=True):
+    global cols, Xh, L, Kc
+    z = np.load(os.path.join(GOLD, "forward_real.npz"))
+    series = load_c_in()
+    L, Kc = len(series["H3"]), 128
+    lamH = np.log(2) / 12.34
+    tracers = ["CFC12", "SF6", "H3", "He4_ter", "He3", "CFC11"]
+    # folded columns: ones + one per tracer
+    cols = [(0, 0, 0, 0, 0)]
+    Xh = [np.ones(Kc)]
+    tp = np.arange(Kc, dtype=np.float64); tp[0] += 1e-5
+    for tr in tracers:
+        key, th, ra = REAL_TRACERS[tr]
+        if ra == "4He":
+            cols.append((3, 0.0, 0.0, 0.0, 1.0)); Xh.append(np.arange(Kc, dtype=np.float64))          # index * J (:323)
+        elif ra == "3He":
+            cols.append((2, float(series[key][-1]), lamH, 0, 0)); Xh.append(series[key][:Kc] * (1 - np.exp(-lamH * tp)))
+        elif th:
+            cols.append((1, float(series[key][-1]), lamH, 0, 0)); Xh.append(series[key][:Kc] * np.exp(-lamH * tp))
+        else:
+            cols.append((1, float(series[key][-1]), 0.0, 0, 0)); Xh.append(series[key][:Kc])
+    Xh = np.stack(Xh, -1)
+    for k in ("CFC12", "SF6", "H3", "CFC11"):
+        assert np.all(series[k][Kc:] == series[k][-1]), "series not constant beyond Kc"
+    theta = z["dm/theta"]
+    worst, nodes, skipped = 0.0, [], 0
+    J = 10 ** O.DEFAULT_LOG10_J
+    for i, (tau, D) in enumerate(theta):
+        if not (0.01 <= D <= 2.5 and tau >= 1.0):
+            skipped += 1; continue
+        tq, n = tail_quad(tau, D, Kc, L, cols)
+        tot = head_direct(tau, D, Kc, Xh) + tq
+        out = tot[1:] / tot[0]
+        for jx, tr in enumerate(tracers):
+            want = z["dm/" + tr][i]
+            got = out[jx] * (J if tr == "He4_ter" else 1.0)
+            if np.isfinite(want) and want != 0:
+                e = abs(got - want) / abs(want)
+                worst = max(worst, e)
+                if e > 1e-10: print("  tau %.4g D %.4g %s: got %.15g want %.15g rel %.2e" % (tau, D, tr, got, want, e))
+        nodes.append(n)
+    if verbose:
+        print("golden 'dm' (reference output, real series L = %d, Kc = %d): %d parameter pairs (%d outside the validated domain skipped), "
+              "worst relative error %.2e, nodes median %d max %d (order %d, %.0f panels per sigma) vs %d direct tail terms" % (
+                  L, Kc, len(nodes), skipped, worst, np.median(nodes), max(nodes), ORDER, PPS, L - Kc))
+    return worst, int(np.median(nodes)), int(max(nodes)), skipped
+
+
+if __name__ == "__main__":
+    run()
