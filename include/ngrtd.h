@@ -79,6 +79,11 @@ typedef struct ngrtd_tracer {
 typedef struct ngrtd_plan ngrtd_plan;   /* opaque: input series + lag tables resident in HBM */
 
 int ngrtd_version(void);
+/* compile-time options of this build (bit mask): experimental kernel variants kept behind macros, see README.md */
+#define NGRTD_FEATURE_DM_TAIL 1     /* -DNGRTD_DM_TAIL: constant tail of dispersion components by quadrature */
+#define NGRTD_FEATURE_XF_SWIZZLE 2  /* -DNGRTD_XF_SWIZZLE: half-warp-contiguous layout of the folded tables */
+#define NGRTD_FEATURE_TP_DADD 4     /* -DNGRTD_TP_DADD: lag value carried in a register */
+int ngrtd_build_features(void);
 const char* ngrtd_last_error(void);
 
 /* ---- plan: replaces tracer_conv_integral.__init__(C_t, t_samp) (conv utils :105-108) and the

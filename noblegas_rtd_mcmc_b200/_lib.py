@@ -59,6 +59,7 @@ lib = ctypes.CDLL(LIB_PATH)
 _vp, _i32, _i64, _dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
 _PROTOS = {
     "ngrtd_version": ([], ctypes.c_int),
+    "ngrtd_build_features": ([], ctypes.c_int),
     "ngrtd_last_error": ([], ctypes.c_char_p),
     "ngrtd_plan_create": ([ctypes.POINTER(_vp), _i32, _i32, _vp, _vp, _dbl, _i32, ctypes.POINTER(Tracer), _i32, _i32, _i32], ctypes.c_int),
     "ngrtd_plan_destroy": ([_vp], ctypes.c_int),

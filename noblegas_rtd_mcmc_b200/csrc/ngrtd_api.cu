@@ -71,6 +71,19 @@ static int cls_of(int mod) {
 }
 
 extern "C" int ngrtd_version(void) { return NGRTD_VERSION; }
+extern "C" int ngrtd_build_features(void) {
+    int f = 0;
+#ifdef NGRTD_DM_TAIL
+    f |= NGRTD_FEATURE_DM_TAIL;
+#endif
+#ifdef NGRTD_XF_SWIZZLE
+    f |= NGRTD_FEATURE_XF_SWIZZLE;
+#endif
+#ifdef NGRTD_TP_DADD
+    f |= NGRTD_FEATURE_TP_DADD;
+#endif
+    return f;
+}
 extern "C" const char* ngrtd_last_error(void) { return g_err.c_str(); }
 
 static double j_flux(double Del, double rho_r, double rho_w, double U, double Th, double phi) {

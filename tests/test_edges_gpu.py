@@ -154,3 +154,25 @@ def test_constant_tail_closed_form_corners():
     w2 = O.forward_mod(th2, ["tau1", "J", "thalf_cfc", "lamsf6"], "He4_ter", np.zeros(L), "exponential", False, rad_accum="4He",
                        index_newest_first=idx2)
     assert rel_err(got[:, 4], w2) < 1e-10
+
+
+def test_dispersion_extreme_parameters_on_the_real_series():
+    """Very narrow / very broad dispersion RTDs and modes far beyond the lag window on the 25,256-lag series against the
+    oracle's full sums.  In -DNGRTD_DM_TAIL builds (ngrtd_build_features() & 1) these parameters lie outside the quadrature's
+    validated domain and exercise its lag-by-lag fallback; in the default build they take the ordinary lag loop."""
+    import np_oracle as O
+    from helpers import REAL_TRACERS, load_c_in, real_plan
+    tracers = ["CFC12", "SF6", "H3", "He4_ter", "He3", "CFC11"]
+    pn = ["tau1", "D1"]
+    plan, C = real_plan("dispersion", False, pn, tracers)
+    th = np.array([[150.0, 0.004], [131.0, 0.002], [9000.0, 0.003], [40000.0, 0.01], [60000.0, 0.02], [0.5, 1.0],
+                   [300.0, 3.0], [2000.0, 8.0]])
+    out = plan.forward_host(th, pn)
+    for i, t in enumerate(tracers):
+        key, thalf, ra = REAL_TRACERS[t]
+        s = C[key] if key is not None else np.zeros(len(C["H3"]))
+        want = O.forward_mod(th, pn, t, s, "dispersion", False, t_half=thalf, rad_accum=ra)
+        assert np.array_equal(np.isnan(out[:, i]), np.isnan(want)), (t, out[:, i], want)
+        ok = np.isfinite(want) & (want != 0)
+        if ok.any():
+            assert np.max(np.abs(out[ok, i] - want[ok]) / np.abs(want[ok])) < 1e-10, t
