@@ -43,7 +43,7 @@ struct ngrtd_plan {
     int cls1 = 0, cls2 = 0;
     bool dyn = false;
     PlanView pv{};
-    double *dXf = nullptr, *dXd = nullptr, *ditp = nullptr, *dxraw = nullptr, *dxrawd = nullptr, *dtbl = nullptr;
+    double *dXf = nullptr, *dXd = nullptr, *ditp = nullptr, *dxraw = nullptr, *dxrawd = nullptr, *dtbl = nullptr, *dtbl11 = nullptr;
     // workspace of the *_host entry points
     double *w_theta = nullptr, *w_out = nullptr, *w_logp = nullptr, *w_nu = nullptr;
     size_t w_theta_n = 0, w_out_n = 0, w_logp_n = 0, w_nu_n = 0;
@@ -241,14 +241,23 @@ extern "C" int ngrtd_plan_create(ngrtd_plan** out, int32_t L, int32_t nseries, c
             }
         }
     }
-    std::vector<double> tbl(TBL_N);     // the kernels replicate it TBL_REP times in shared memory
-    for (int i = 0; i < TBL_N; i++) {
-        double v = std::exp2((double)i / TBL_N);
-        uint64_t b;
-        std::memcpy(&b, &v, 8);
-        b -= (uint64_t)i << (32 + 20 - TBL_BITS);      // exponent insertion becomes one integer add (exp_scaled_bits)
-        std::memcpy(&tbl[i], &b, 8);
-    }
+    // exp tables of exp_scaled_bits<TB>: 2^(i/N) with i << (20 - log2 N) and exp_tbl_fold<TB>() subtracted from the high word,
+    // so that the exponent insertion becomes one integer multiply-add; the kernels copy (and for N = 128 replicate) them
+    // into shared memory
+    auto make_tbl = [](int bits, int sub, unsigned int fold) {
+        const int n = 1 << bits;
+        std::vector<double> tbl(n);
+        for (int i = 0; i < n; i++) {
+            double v = std::exp2((double)i / n);
+            uint64_t b;
+            std::memcpy(&b, &v, 8);
+            uint32_t hi = (uint32_t)(b >> 32) - ((uint32_t)(i >> sub) << (20 - (bits - sub))) - fold;   // modulo 2^32, like the device add
+            b = ((uint64_t)hi << 32) | (b & 0xffffffffull);
+            std::memcpy(&tbl[i], &b, 8);
+        }
+        return tbl;
+    };
+    const std::vector<double> tbl7 = make_tbl(7, ExpCfg<7>::SUB, exp_tbl_fold<7>()), tbl11 = make_tbl(11, ExpCfg<11>::SUB, exp_tbl_fold<11>());
 
     auto up = [&](double** d, const std::vector<double>& h) -> cudaError_t {
         cudaError_t e = cudaMalloc((void**)d, h.size() * sizeof(double));
@@ -258,7 +267,8 @@ extern "C" int ngrtd_plan_create(ngrtd_plan** out, int32_t L, int32_t nseries, c
     cudaError_t e = cudaSuccess;
     if ((e = up(&P->dXf, Xf)) != cudaSuccess || (e = up(&P->dXd, Xd)) != cudaSuccess ||
         (e = up(&P->ditp, itp)) != cudaSuccess || (e = up(&P->dxraw, xraw)) != cudaSuccess ||
-        (e = up(&P->dxrawd, xrawd)) != cudaSuccess || (e = up(&P->dtbl, tbl)) != cudaSuccess ||
+        (e = up(&P->dxrawd, xrawd)) != cudaSuccess || (e = up(&P->dtbl, tbl7)) != cudaSuccess ||
+        (e = up(&P->dtbl11, tbl11)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&P->hstream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&P->hstream2, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&P->hstream3, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -287,7 +297,8 @@ extern "C" int ngrtd_plan_create(ngrtd_plan** out, int32_t L, int32_t nseries, c
     pv.itp = P->ditp;
     pv.xraw = P->dxraw;
     pv.xrawd = P->dxrawd;
-    pv.tbl = P->dtbl;
+    pv.tbl7 = P->dtbl;
+    pv.tbl11 = P->dtbl11;
     pv.ntracer = ntracer;
     pv.eta1_is_one = (mod_type1 == NGRTD_MOD_EXPONENTIAL);
     pv.eta2_is_one = (mod_type2 == NGRTD_MOD_EXPONENTIAL);
@@ -301,7 +312,7 @@ extern "C" int ngrtd_plan_create(ngrtd_plan** out, int32_t L, int32_t nseries, c
 extern "C" int ngrtd_plan_destroy(ngrtd_plan* P) {
     if (!P) return NGRTD_OK;
     cudaFree(P->dXf); cudaFree(P->dXd); cudaFree(P->ditp); cudaFree(P->dxraw); cudaFree(P->dxrawd);
-    cudaFree(P->dtbl);
+    cudaFree(P->dtbl); cudaFree(P->dtbl11);
     cudaFree(P->w_theta); cudaFree(P->w_out); cudaFree(P->w_logp); cudaFree(P->w_nu);
     if (P->hstream) cudaStreamDestroy(P->hstream);
     if (P->hstream2) cudaStreamDestroy(P->hstream2);
@@ -341,34 +352,87 @@ static int pick_warps(long long nunits, int nsm, int maxw) {
     return w;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute of a kernel: remember what was
+// configured for every device ordinal, so that a second plan on another GPU of the same thread configures its own context.
+constexpr int MAX_DEVICES = 64;
+struct SmemConfigured { size_t bytes[MAX_DEVICES] = {}; };
+constexpr size_t SMEM_LIMIT = 227 * 1024;       // opt-in dynamic shared memory per CTA on sm_100
+
+static bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("NGRTD_PDL"); return !(e && atoi(e) == 0); }();
+    return on;
+}
+
+template <int C1, int C2, bool DYN, int NT, int UA, int MAXW, bool TAIL>
+static int launch_forward_tt(ngrtd_plan* P, const SlotMap& sm, const double* theta, long long B, double* out,
+                             double* logp, const LikPar& lik, cudaStream_t st, int stage, int warps_req) {
+    using WT = WarpTiles<C1, C2, DYN, NT, UA, FWD_TB, TAIL ? 1 : 0, true>;
+    const int Lloop = (TAIL && tail_active(P->pv, WT::ANY_G, WT::ANY_D)) ? P->pv.Kc : P->Lpad;
+    long long nunits = (B + NT * 8 - 1) / (NT * 8);
+    if (sm.ndim > NSLOT) stage = 0;                                  // staging slots are sized for <= NSLOT columns
+    int warps = warps_req > 0 ? std::min(warps_req, MAXW) : MAXW;    // tape schedule: every warp takes an equal share
+    if (warps > 4) warps &= ~3;
+    auto total = [&](int w, int lc, bool tape) -> size_t {
+        size_t sh = (size_t)fwd_smem_doubles<WT>(w, lc, tape);
+        if (stage) sh = ((sh + 1) & ~(size_t)1) + (size_t)w * (NT * 8 * sm.ndim + 1) + 1;
+        return sh * sizeof(double);
+    };
+    int lc_cap = WT::ANY_LOOP ? std::min(Lloop, LC_MAX) : 0;
+    bool resident = !WT::ANY_LOOP || Lloop <= lc_cap;               // FwdCta::setup: tape <=> one chunk
+    size_t sh = total(warps, lc_cap, resident);
+    if (resident && sh > SMEM_LIMIT) {          // tables + hand-off slots of the tape do not fit: stream two chunks in lock step
+        lc_cap = (Lloop / 2 + 3) & ~3;
+        resident = false;
+    }
+    int grid;
+    if (resident) {
+        grid = (int)std::min<long long>(nunits, P->nsm);
+        const long long per_cta = (nunits + grid - 1) / std::max(grid, 1);
+        if (per_cta * std::max(1, Lloop / 4) >= (1LL << 31))
+            return fail(NGRTD_EINVAL, "forward: batch too large for one launch (split it)");
+    } else {
+        if (warps_req <= 0) warps = pick_warps(nunits, P->nsm, MAXW);
+        if (warps > 4) warps &= ~3;
+        long long want = (nunits + warps - 1) / warps;
+        grid = (int)std::min<long long>(want, P->nsm);
+    }
+    if (grid < 1) grid = 1;
+    sh = total(warps, lc_cap, resident);
+    if (sh > SMEM_LIMIT) return fail(NGRTD_EINVAL, "forward: shared-memory layout exceeds 227 KB");
+    auto kern = k_forward<C1, C2, DYN, NT, UA, MAXW, TAIL>;
+    static thread_local SmemConfigured configured;
+    const int dev = (P->device >= 0 && P->device < MAX_DEVICES) ? P->device : 0;
+    if (configured.bytes[dev] < sh) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        configured.bytes[dev] = sh;
+    }
+    // Programmatic dependent launch: launch i+1 may begin its set-up (table loads) while launch i drains; the kernel
+    // waits for its predecessor (griddepcontrol.wait) before it reads theta or writes anything.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)(warps * 32));
+    cfg.dynamicSmemBytes = sh;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    static const int tape_min = [] { const char* e = getenv("NGRTD_TAPE_MIN"); return e ? atoi(e) : TAPE_MIN_GROUPS; }();
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, P->pv, sm, theta, B, out, logp, lik, lc_cap, stage, tape_min));
+    return NGRTD_OK;
+}
+
+// two instantiations per model pair: with and without the analytic-tail code (WarpTiles TM)
 template <int C1, int C2, bool DYN, int NT, int UA, int MAXW>
 static int launch_forward_t(ngrtd_plan* P, const SlotMap& sm, const double* theta, long long B, double* out,
                             double* logp, const LikPar& lik, cudaStream_t st, int stage, int warps_req) {
-    using WT = WarpTiles<C1, C2, DYN, NT, UA>;
-    const int Lloop = tail_active(P->pv, WT::ANY_G, WT::ANY_D) ? P->pv.Kc : P->Lpad;
-    int lc_cap = WT::ANY_LOOP ? std::min(Lloop, LC_MAX) : 0;
-    long long nunits = (B + NT * 8 - 1) / (NT * 8);
-    int warps = warps_req > 0 ? std::min(warps_req, MAXW) : pick_warps(nunits, P->nsm, MAXW);
-    if (warps > 4) warps &= ~3;
-    size_t sh = (size_t)TBL_DOUBLES + 2 + (size_t)warps * NT * 8 * NCOL;
-    sh += (size_t)lc_cap * NCOL;
-    if (WT::ANY_D) sh += (size_t)lc_cap * NCOL + 2 * (size_t)lc_cap;
-    if (DYN) sh += lc_cap + (WT::ANY_D ? lc_cap : 0);
-    if (sm.ndim > NSLOT) stage = 0;                                  // staging slots are sized for <= NSLOT columns
-    if (stage) sh = ((sh + 1) & ~(size_t)1) + (size_t)warps * (NT * 8 * sm.ndim + 1) + 1;
-    sh *= sizeof(double);
-    auto kern = k_forward<C1, C2, DYN, NT, UA, MAXW>;
-    static thread_local size_t configured = 0;
-    if (configured < sh) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-        configured = sh;
+    constexpr bool ANY_G = (C1 == CLS_G || C2 == CLS_G), ANY_D = (C1 == CLS_D || C2 == CLS_D);
+    if constexpr (ANY_G || ANY_D) {
+        if (tail_active(P->pv, ANY_G, ANY_D))
+            return launch_forward_tt<C1, C2, DYN, NT, UA, MAXW, true>(P, sm, theta, B, out, logp, lik, st, stage, warps_req);
     }
-    long long want = (nunits + warps - 1) / warps;
-    int grid = (int)std::min<long long>(want, P->nsm);
-    if (grid < 1) grid = 1;
-    kern<<<grid, warps * 32, sh, st>>>(P->pv, sm, theta, B, out, logp, lik, lc_cap, stage);
-    CUDA_TRY(cudaGetLastError());
-    return NGRTD_OK;
+    return launch_forward_tt<C1, C2, DYN, NT, UA, MAXW, false>(P, sm, theta, B, out, logp, lik, st, stage, warps_req);
 }
 
 #ifndef NGRTD_FWD_MAXW
@@ -1102,7 +1166,7 @@ static double lbeta(double a, double b) { return std::lgamma(a) + std::lgamma(b)
 template <int C1, int C2, bool DYN>
 static int launch_mcmc_age(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st) {
     constexpr int NT = FWD_NT, UA = FWD_UA, MAXW = FWD_MAXW;
-    using WT = WarpTiles<C1, C2, DYN, NT, UA>;
+    using WT = WarpTiles<C1, C2, DYN, NT, UA, MCMC_TB>;
     ngrtd_plan* P = S->plan;
     const long long B = S->sv.B;
     long long nunits = (B + NT * 8 - 1) / (NT * 8);
@@ -1113,9 +1177,7 @@ static int launch_mcmc_age(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st)
     int lc_cap = WT::ANY_LOOP ? std::min(Lloop, LC_MAX) : 0;
     size_t sh = 0;
     for (;;) {
-        sh = (size_t)TBL_DOUBLES + 2 + (size_t)warps * NT * 8 * NCOL + (size_t)lc_cap * NCOL;
-        if (WT::ANY_D) sh += (size_t)lc_cap * NCOL + 2 * (size_t)lc_cap;
-        if (DYN) sh += lc_cap + (WT::ANY_D ? lc_cap : 0);
+        sh = (size_t)fwd_smem_doubles<WT>(warps, lc_cap, false);
         sh += (size_t)warps * NT * 8 * CH_REC + (sizeof(PriorDev) * ND_MAX + 7) / 8;
         sh *= sizeof(double);
         if (sh <= 227 * 1024 || lc_cap <= 64) break;
@@ -1123,10 +1185,11 @@ static int launch_mcmc_age(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st)
     }
     if (sh > 227 * 1024) return fail(NGRTD_EINVAL, "sampler: shared-memory budget exceeded");
     auto kern = k_mcmc_age<C1, C2, DYN, NT, UA, MAXW>;
-    static thread_local size_t configured = 0;
-    if (configured < sh) {
+    static thread_local SmemConfigured configured;
+    const int dev = (S->device >= 0 && S->device < MAX_DEVICES) ? S->device : 0;
+    if (configured.bytes[dev] < sh) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-        configured = sh;
+        configured.bytes[dev] = sh;
     }
     long long want = (nunits + warps - 1) / warps;
     int grid = (int)std::max<long long>(1, std::min<long long>(want, P->nsm));

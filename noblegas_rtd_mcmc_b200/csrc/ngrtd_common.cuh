@@ -29,41 +29,54 @@ __host__ __device__ __forceinline__ int xf_index(int k, int c) {
 }
 
 // table-driven exp(): exp(e) = 2^(n/N) * q(g), n = floor(e*N/ln2), g = 1 + frac(e*N/ln2)  (exp_scaled_bits below).
-// The N-entry table of 2^(j/N) lives in shared memory as 8-byte entries, replicated TBL_REP times: lane l gathers from
-// copy l & (TBL_REP-1) at double index j*TBL_REP + copy.  A 64-bit shared load is served per half-warp; with 16 copies
-// every lane of a half-warp owns its own pair of banks and the gather is conflict-free (2 wavefronts per warp).
-// Measured (profiles/r1_notes.md): one copy as two 32-bit word arrays, N = 256: ~6.8 wavefronts per gather pair, LSU data
-// pipe 64 % busy; 16 copies: 46 % -- but the lag loop is held by the shared FP64/DMMA pipe (math-pipe-throttle stalls
-// at 67 % pipe activity), so throughput did not move, and 16 KB more shared memory pushed the sampler kernel into
-// chunked streaming.  Default: 4 copies (4 KB), N = 128.
-#ifndef NGRTD_TBL_BITS
-#define NGRTD_TBL_BITS 7
-#endif
-#ifndef NGRTD_TBL_REP_BITS
-#define NGRTD_TBL_REP_BITS 2
-#endif
-constexpr int TBL_BITS = NGRTD_TBL_BITS;
-constexpr int TBL_N = 1 << TBL_BITS;
-constexpr int TBL_REP_BITS = NGRTD_TBL_REP_BITS;
-constexpr int TBL_REP = 1 << TBL_REP_BITS;
-constexpr int TBL_DOUBLES = TBL_N * TBL_REP;      // shared-memory footprint in doubles
+// The N-entry table of 2^(j/N) lives in shared memory as 8-byte entries, replicated REP times: lane l gathers from
+// copy l & (REP-1) at double index j*REP + copy.  Two configurations (ExpCfg<TB>, TB = log2 N), chosen per kernel:
+//   TB = 7  (k_mcmc_age: the sampler kernel has ~3 KB of shared memory to spare): 128 entries x 4 copies = 4 KB, cubic q,
+//           3 DFMA + 1 DMUL on the shared FP64/DMMA pipe per weight, max rel err of q 2.8e-13;
+//   TB = 11 (k_forward, r2): 2,048 entries x 1 copy = 16 KB, QUADRATIC q -- one DFMA less per dispersion weight on the pipe
+//           that bounds the lag loop -- max rel err of q 2.0e-13.  The exponent is carried in units of 4 table steps
+//           (SUB = 2) so that its integer part still fits the 20 mantissa bits of the high word over the whole double
+//           range (1022 * 2048 / 4 < 2^19); the two missing index bits are the top bits of the low word.
+// tools/exp_poly_g.py prints the constants and error bounds.
+// r1 measurements on the replication (profiles/r1_notes.md): the gather is never the bound (LSU data pipe 46-64 % busy, the
+// loop is held by the shared FP64/DMMA pipe), so the larger table is not replicated (r2: 2 copies measured slower).
 constexpr double LN2 = 0.693147180559945309417232121458;
-constexpr double EXP_K = TBL_N / LN2;
-// exp_scaled_bits: q(g) ~= exp((g - 1) ln2 / N) on g in [1, 2)  (tools/exp_poly_g.py: constants and error bounds)
-#if NGRTD_TBL_BITS == 7
-constexpr double EXQ_C0 = 0.99459942332194162, EXQ_C1 = 0.0053859675366433966, EXQ_C2 = 1.4582602945559778e-05,
-                 EXQ_C3 = 2.6538188920206277e-08;      // max rel err 2.8e-13
-#elif NGRTD_TBL_BITS == 8
-constexpr double EXQ_C0 = 0.99729605607536986, EXQ_C1 = 0.0027002849873872833, EXQ_C2 = 3.6556244405132574e-06,
-                 EXQ_C3 = 3.3127848075725495e-09;      // 1.8e-14
-#elif NGRTD_TBL_BITS == 9
-constexpr double EXQ_C0 = 0.99864711289033903, EXQ_C1 = 0.0013519715460713645, EXQ_C2 = 9.1514977059835842e-07,
-                 EXQ_C3 = 4.1381786370901806e-10;      // 1.2e-15
-#else
-constexpr double EXQ_C0 = 0, EXQ_C1 = 0, EXQ_C2 = 0, EXQ_C3 = 0;
+#ifndef NGRTD_TB11_REP_BITS
+#define NGRTD_TB11_REP_BITS 0
 #endif
+template <int TB>
+struct ExpCfg;
+template <>
+struct ExpCfg<7> {
+    static constexpr int BITS = 7, N = 128, SUB = 0, REP_BITS = 2, REP = 4, DOUBLES = N * REP, DEG = 3;
+    static constexpr double C0 = 0.99459942332194162, C1 = 0.0053859675366433966, C2 = 1.4582602945559778e-05,
+                            C3 = 2.6538188920206277e-08;      // max rel err 2.8e-13
+};
+template <>
+struct ExpCfg<11> {
+    static constexpr int BITS = 11, N = 2048, SUB = 2, REP_BITS = NGRTD_TB11_REP_BITS, REP = 1 << REP_BITS, DOUBLES = N * REP, DEG = 2;
+    static constexpr double C0 = 0.99966160651623492, C1 = 0.00033833619981139687, C2 = 5.7284155667395806e-08,
+                            C3 = 0.0;                         // max rel err 2.0e-13
+};
+// scale of the exponent handed to exp_scaled_bits: t = e * exp_k + FX_MAGIC (units of 2^SUB table steps)
+template <int TB>
+__host__ __device__ constexpr double exp_k() { return (ExpCfg<TB>::N >> ExpCfg<TB>::SUB) / LN2; }
+// below this (in the same units) the result is clamped at ~2^-1022 instead of flushing to zero
+template <int TB>
+__host__ __device__ constexpr int exp_clamp() { return -1022 * (ExpCfg<TB>::N >> ExpCfg<TB>::SUB); }
+// what ngrtd_plan_create subtracts from the high word of every table entry (see exp_scaled_bits)
+template <int TB>
+__host__ __device__ constexpr int exp_ins_shift() { return 20 - (TB - ExpCfg<TB>::SUB); }
+template <int TB>
+__host__ __device__ constexpr unsigned int exp_tbl_fold() {
+    return (unsigned int)(((unsigned long long)0x41380000u << exp_ins_shift<TB>()) & 0xffffffffull);
+}
+#ifndef NGRTD_FWD_TB
+#define NGRTD_FWD_TB 11
+#endif
+constexpr int FWD_TB = NGRTD_FWD_TB;      // k_forward
+constexpr int MCMC_TB = 7;      // k_mcmc_age
 constexpr double FX_MAGIC = 1572864.0;               // 1.5 * 2^20: ulp 2^-32, integer part biased by 2^19
-constexpr int EXP_NMIN = -1022 * TBL_N;             // below 2^-1022: clamp (see DESIGN.md "underflow")
 
 enum Cls : int { CLS_NONE = 0, CLS_P = 1, CLS_G = 2, CLS_D = 3 };
 
@@ -91,7 +104,8 @@ struct PlanView {
     const double* itp;    // [Lpad][2] {1/tp, tp} (pad: 0, 0)
     const double* xraw;   // [Lpad] raw series of the per-chain-lambda tracer
     const double* xrawd;  // [Lpad] xraw * tp^-1.5
-    const double* tbl;    // [TBL_N] 2^(j/TBL_N) with j << (20 - TBL_BITS) subtracted from the high word (see exp_scaled_bits)
+    const double* tbl7;   // [128]  2^(j/N) with j << (20 - log2 N) subtracted from the high word (see exp_scaled_bits)
+    const double* tbl11;  // [2048] same, N = 2048
     int ntracer;
     TracerDev tr[MAX_TRACER];
     int eta1_is_one, eta2_is_one;   // 'exponential' == exp_pist_flow with eta = 1 (bit-identical in the reference)
@@ -153,38 +167,54 @@ __device__ __forceinline__ ChainPar load_chain_par(const double* __restrict__ th
     return p;
 }
 
-// exp(e) for e <= ~0, given t = ep + FX_MAGIC with ep = e*N/ln2.  The addition is folded into the caller's FMA chain
-// (cp + FX_MAGIC is a per-chain constant), so it costs nothing.  With 2^20 <= t < 2^21 the mantissa of t IS ep in fixed
-// point: high word bits 0..19 = floor(ep) + 2^19, low word = the 32-bit fraction F of ep.
-//   * table slot / exponent insertion come from the high word on the integer pipes (the 2^19 bias and the exponent
-//     field of t fold into one immediate; the table stores 2^(j/N) with j << (20 - log2 N) subtracted from its high word);
-//   * g = 1 + F 2^-32 is assembled from the bits of F (two shifts, one OR) and p = q(g) = exp((g-1) ln2/N) is a cubic
-//     in g: no F2I / I2F conversions and no DADD for the reduced argument.
-// Shared FP64/DMMA-pipe cost: 3 DFMA + 1 DMUL.  History (profiles/r1_notes.md): the first version rounded with F2I/I2F
+// exp(e) for e <= ~0, given t = ep + FX_MAGIC with ep = e * exp_k<TB>() (= e N / (2^SUB ln2)).  The addition is folded into
+// the caller's FMA chain (cp + FX_MAGIC is a per-chain constant), so it costs nothing.  With 2^20 <= t < 2^21 the mantissa
+// of t IS ep in fixed point: high word bits 0..19 = floor(ep) + 2^19, low word = the 32-bit fraction of ep, whose top SUB
+// bits are the low bits of the table index and whose remaining bits F are the reduced argument.
+//   * table slot / exponent insertion come from the high word on the integer pipes: the table stores 2^(j/N) with
+//     (j >> SUB) << (20 - (TB - SUB)) and the image of FX_MAGIC's high word (exp_tbl_fold<TB>(): the 2^19 bias and the
+//     exponent field of t) subtracted from its high word, so the insertion is ONE integer multiply-add;
+//   * g = 1 + F 2^-(32-SUB) is assembled from the bits of F (shifts, one OR) and p = q(g) = exp((g-1) ln2/N) is a polynomial
+//     in g (cubic for N = 128, quadratic for N = 2048): no F2I / I2F conversions and no DADD for the reduced argument.
+// Shared FP64/DMMA-pipe cost: DEG DFMA + 1 DMUL.  History (profiles/r1_notes.md): the first version rounded with F2I/I2F
 // (XU pipe) and a centred polynomial; a fully integer polynomial with IMAD.HI / IMAD.WIDE measured SLOWER (wide integer
 // multiplies issue at ~4.5 cycles and contend with the FP64 pipe -- tools/microbench/imad_peak.cu).
-// Error: ep is rounded to 2^-32 table units twice (<= 2^-32 ln2/N relative, unbiased) + the polynomial.
-// Below EXP_NMIN the high word is clamped (result ~2^-1022) instead of flushing to zero: one VIMNMX instead of a compare
-// and two selects.  NaN does NOT propagate through the integer path: chains whose largest weight would be below 2^-1022,
-// or with NaN parameters, are declared dead in Comp<CLS_D>::init and poisoned in the epilogue, which reproduces the
+// Error: ep is rounded to 2^-32 twice (<= 2^-32 2^SUB ln2/N relative, unbiased) + the polynomial.
+// Below exp_clamp<TB>() the high word is clamped (result ~2^-1022) instead of flushing to zero: one VIMNMX instead of a
+// compare and two selects.  NaN does NOT propagate through the integer path: chains whose largest weight would be below
+// 2^-1022, or with NaN parameters, are declared dead in CompD::init_q and poisoned in the epilogue, which reproduces the
 // reference's 0/0 = NaN when every weight underflows.
-__device__ __forceinline__ double exp_scaled_bits(double t, const double* __restrict__ tbl) {
-    constexpr int S = 20 - TBL_BITS;
+template <int TB>
+__device__ __forceinline__ double exp_scaled_bits(double t, const double* __restrict__ tbl0, unsigned int tbl_lane) {
+    using E = ExpCfg<TB>;
+    constexpr int S = exp_ins_shift<TB>();
     constexpr int HI_MAGIC = 0x41380000;                                  // high word of FX_MAGIC
-    constexpr int HI_MIN = HI_MAGIC + EXP_NMIN;                           // high word of EXP_NMIN + FX_MAGIC
-    constexpr unsigned int FOLD = (unsigned int)(((unsigned long long)HI_MAGIC << S) & 0xffffffffull);
+    constexpr int HI_MIN = HI_MAGIC + exp_clamp<TB>();                    // high word of exp_clamp + FX_MAGIC
     const int ht = max(__double2hiint(t), HI_MIN);
-    const unsigned int F = (unsigned int)__double2loint(t);
-    const double g = __hiloint2double((int)(0x3FF00000u | (F >> 12)), (int)(F << 20));
-#ifdef NGRTD_ESTRIN
-    const double p = fma(g * g, fma(g, EXQ_C3, EXQ_C2), fma(g, EXQ_C1, EXQ_C0));      // depth 2 instead of 3, one more FP64 op
+    const unsigned int lo = (unsigned int)__double2loint(t);
+    // g = 1 + F 2^-(32-SUB): mantissa = the low (32 - SUB) bits of lo, left-aligned
+#ifdef NGRTD_EXPV1
+    // right shifts are funnel shifts (SHF) in SASS; (x >> s) + c is one LEA.HI
+    const unsigned int Fm = lo & (0xffffffffu >> E::SUB);
+    const double g = __hiloint2double((int)(0x3FF00000u + (Fm >> (12 - E::SUB))), (int)(lo << (20 + E::SUB)));
 #else
-    const double p = fma(g, fma(g, fma(g, EXQ_C3, EXQ_C2), EXQ_C1), EXQ_C0);
+    const double g = __hiloint2double((int)(0x3FF00000u | ((lo << E::SUB) >> 12)), (int)(lo << (20 + E::SUB)));
 #endif
-    // tbl points at this lane's copy: entry j is at tbl[j * TBL_REP]
-    const int off = (ht << (3 + TBL_REP_BITS)) & ((TBL_N - 1) << (3 + TBL_REP_BITS));
-    const double T = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(tbl) + off);
-    const unsigned int hi = (unsigned int)__double2hiint(T) + ((unsigned int)ht << S) - FOLD;
+    double p;
+    if constexpr (E::DEG == 3) p = fma(g, fma(g, fma(g, E::C3, E::C2), E::C1), E::C0);
+    else p = fma(g, fma(g, E::C2, E::C1), E::C0);
+    // entry j = (low bits of floor(ep)) : (top SUB bits of lo) of this lane's copy.  tbl_lane = byte offset of the lane's
+    // copy from the start of the kernel's dynamic shared memory (the table sits at its very beginning): the masked index
+    // and the copy select merge into one LOP3, and the base is the immediate of the load.
+    constexpr int OSH = 3 + E::REP_BITS + E::SUB;
+#ifdef NGRTD_EXPV1
+    const unsigned int sh = (E::SUB == 0) ? ((unsigned int)ht << OSH) : (((unsigned int)ht << OSH) + (lo >> (32 - OSH)));
+#else
+    const unsigned int sh = (E::SUB == 0) ? ((unsigned int)ht << OSH) : __funnelshift_l(lo, (unsigned int)ht, OSH);
+#endif
+    const unsigned int off = (sh & ((unsigned int)(E::N - 1) << (3 + E::REP_BITS))) | tbl_lane;
+    const double T = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(tbl0) + off);
+    const unsigned int hi = (unsigned int)__double2hiint(T) + ((unsigned int)ht << S);   // the table's high words carry -fold
     return __hiloint2double((int)hi, __double2loint(T)) * p;
 }
 

@@ -38,6 +38,9 @@ struct SmemView {
     int tbl;
     int scratch;   // [warps][NT][8 chains][8 cols]
     int bar;       // mbarrier of the bulk-copy staging (2 doubles reserved)
+    int part;      // tape schedule: [warps][NT * NPART][32 lanes] accumulators of partial lag ranges
+    int flag;      // tape schedule: [warps] int, 1 = the warp's partial is published
+    int park;      // PK: [warps][NT][8 chains][PARK_DOUBLES] epilogue-only values parked across the lag loop
 };
 
 struct LikPar {
@@ -123,47 +126,45 @@ struct Comp<CLS_G> {
     }
 };
 
-template <>
-struct Comp<CLS_D> {
+// Dispersion component.  TB selects the exp table (ExpCfg<TB>).
+// The exponent e(tp) = -(tp - tau)^2 / (4 D tau tp) is evaluated in table units (x exp_k<TB>()) as ap/tp + bp*tp + cp.
+template <int TB>
+struct CompD {
     double ap, bp, cp;
     // exp_scaled_bits() does not propagate NaN -> WarpTiles::end() poisons the sums of dead chains instead
     __device__ __forceinline__ bool dead() const { return ap != ap; }
-    __device__ __forceinline__ void init(double tau, double, double D, double dtp, int L) {
+    // i4D = 1/(4D) and bq = -exp_k/(4 D tau) are supplied by the lane-split prologue of WarpTiles::begin
+    __device__ __forceinline__ void init_q(double tau, double D, double i4D, double bq, const PlanView& pv) {
+        constexpr double K = exp_k<TB>();
         bool ok = (tau > 0.0) && (D > 0.0) && (tau < 1.0e300) && (D < 1.0e300);
-        double i4D = 1.0 / (4.0 * D);
-        // e = -(1-x)^2/(4Dx), x = tp/tau  ==  -(tau/4D)/tp + 1/(2D) - tp/(4D tau); pre-scaled by N/ln2
-        ap = -EXP_K * tau * i4D;
-        bp = -EXP_K * i4D / tau;
-        cp = EXP_K * 2.0 * i4D;
-        // Largest exponent over the lag grid: e(x) peaks (e = 0) at x = 1; if tau lies beyond the last lag the
-        // maximum is at the last lag.  Below 2^-1022 every reference weight is (sub)denormal or exactly zero and
-        // g/g.sum() is NaN or precision-less: the chain is declared dead -> NaN output.
-        double tpl = (double)(L - 1) + dtp + ((L == 1) ? 1e-5 : 0.0);
-        if (ok && tau > tpl) {
-            double emax = fma(ap, 1.0 / tpl, fma(bp, tpl, cp));
-            ok = emax >= (double)EXP_NMIN;
+        ap = -K * tau * i4D;
+        bp = bq;
+        cp = K * 2.0 * i4D;
+        if (ok) {
+            // Largest exponent over the lag grid: e(tp) is unimodal with its maximum (0) at tp = tau, so the discrete
+            // maximum sits at one of the two grid lags around tau (the last lag when tau lies beyond the grid).
+            // tp_k = k + dtp (tp_0 = 1e-5 + dtp); pv.itp holds the same {1/tp, tp} pairs the lag loop reads.
+            const double s = fmin(fmax(floor(tau - pv.dtp), 0.0), (double)(pv.L - 1));
+            const int ka = (int)s, kb = min(ka + 1, pv.L - 1);
+            const double2 ia = *reinterpret_cast<const double2*>(pv.itp + 2 * ka);
+            const double2 ib = *reinterpret_cast<const double2*>(pv.itp + 2 * kb);
+            const double emax = fmax(fma(ap, ia.x, fma(bp, ia.y, cp)), fma(ap, ib.x, fma(bp, ib.y, cp)));
+            // Below 2^-1022 every reference weight is (sub)denormal or exactly zero and g/g.sum() is NaN or
+            // precision-less: the chain is declared dead -> NaN output.
+            ok = emax >= (double)exp_clamp<TB>();
         }
         cp += FX_MAGIC;     // exp_scaled_bits takes ep + FX_MAGIC: folded into the constant term
         if (!ok) ap = __longlong_as_double(0x7ff8000000000000LL);
     }
-    // same, with i4D = 1/(4D) and bq = -(N/ln2)/(4 D tau) supplied by the lane-split prologue of WarpTiles::begin
-    __device__ __forceinline__ void init_q(double tau, double D, double i4D, double bq, const PlanView& pv) {
-        bool ok = (tau > 0.0) && (D > 0.0) && (tau < 1.0e300) && (D < 1.0e300);
-        ap = -EXP_K * tau * i4D;
-        bp = bq;
-        cp = EXP_K * 2.0 * i4D;
-        if (ok && tau > pv.tpl) {
-            double emax = fma(ap, pv.itpl, fma(bp, pv.tpl, cp));
-            ok = emax >= (double)EXP_NMIN;
-        }
-        cp += FX_MAGIC;
-        if (!ok) ap = __longlong_as_double(0x7ff8000000000000LL);
-    }
     // it = {1/tp, tp} of the lag (shared-memory table): two independent FMAs, no carried state
-    __device__ __forceinline__ double weight(double2 it, const double* tbl) const {
-        return exp_scaled_bits(fma(ap, it.x, fma(bp, it.y, cp)), tbl);
+    __device__ __forceinline__ double weight(double2 it, unsigned int tbl_lane) const {
+        return exp_scaled_bits<TB>(fma(ap, it.x, fma(bp, it.y, cp)), ngrtd_smem, tbl_lane);
     }
 };
+template <int CLS, int TB>
+struct CompSel { using type = Comp<CLS>; };
+template <int TB>
+struct CompSel<CLS_D, TB> { using type = CompD<TB>; };
 
 // order-16 Gauss-Legendre nodes / weights on [-1, 1] (positive half) for WarpTiles::dm_tail
 __constant__ double DM_GX[8] = {0.095012509837637441, 0.28160355077925892, 0.45801677765722737, 0.61787624440264377,
@@ -201,16 +202,27 @@ __device__ __forceinline__ double col_tail(const ColTail& ct, double er, double 
 }
 
 // ---------------------------------------------------------------- one warp = NT tiles of 8 chains
-template <int C1, int C2, bool DYN, int NT, int UA>
+// TM: 1 = the analytic constant tail is decided at run time (PlanView::Kc), 0 = compiled out (k_forward instantiates both
+//     and the launcher picks: without the tail code the lag loop keeps fewer values alive and schedules tighter).
+// PK: the values only the epilogue needs (f1, f2, lamsf6, J) are parked in shared memory across the lag loop instead of
+//     occupying 16 registers (k_forward; the sampler kernel has no shared memory to spare and keeps them in registers).
+constexpr int PARK_DOUBLES = 4;
+template <int C1, int C2, bool DYN, int NT, int UA, int TB, int TM = 1, bool PK = false>
 struct WarpTiles {
     static constexpr bool LOOP1 = (C1 == CLS_G || C1 == CLS_D);
     static constexpr bool LOOP2 = (C2 == CLS_G || C2 == CLS_D);
     static constexpr bool ANY_LOOP = LOOP1 || LOOP2;
     static constexpr bool ANY_D = (C1 == CLS_D || C2 == CLS_D);
     static constexpr bool ANY_G = (C1 == CLS_G || C2 == CLS_G);
+    static constexpr int TBITS = TB, NTILES = NT;
+    static constexpr bool DYNAMIC = DYN, PARK = PK;
 
-    Comp<C1> c1[NT];
-    Comp<C2> c2[NT];
+    static constexpr double EXP_K = exp_k<TB>();
+    // doubles per lane and tile that a partial lag range hands to the owner of its unit (tape schedule of k_forward)
+    static constexpr int NPART = (LOOP1 ? 2 : 0) + (LOOP2 ? 2 : 0) + ((DYN && LOOP1) ? 1 : 0) + ((DYN && LOOP2) ? 1 : 0);
+
+    typename CompSel<C1, TB>::type c1[NT];
+    typename CompSel<C2, TB>::type c2[NT];
     double a1[NT][UA][2], a2[NT][UA][2];   // UA independent DMMA accumulator chains per tile and component
     double dv[NT], d4[NT], lam[NT], ad1[NT], ad2[NT];
     double Jl[NT];                          // J = 10**log10J (run_age_mcmc_utils.py:101)
@@ -223,7 +235,8 @@ struct WarpTiles {
     //       dispersion:        0.25/D = 1/(4D) and -(N/ln2)/4 / (D tau)
     //   exp slots: lane 0 J = exp(ln10 * log10 J) (argument product carried in two pieces), lane 1 / 2 the 4-lag decay
     //       factor exp(-4 eta/tau) of component 1 / 2, lane 3 exp(-4 lambda) of a per-chain decay constant.
-    __device__ __forceinline__ void begin(const ChainPar (&p)[NT], const PlanView& pv, int lane, bool need_J) {
+    __device__ __forceinline__ void begin(const ChainPar (&p)[NT], const PlanView& pv, int lane, bool need_J,
+                                          double* park_warp = nullptr) {
         const int j = lane & 3, base = lane & ~3;
         const unsigned full = 0xffffffffu;
 #pragma unroll
@@ -253,6 +266,12 @@ struct WarpTiles {
                 double ee = exp(ea);
                 ee = fma(ee, el, ee);
                 Jl[t] = need_J ? __shfl_sync(full, ee, base) : 0.0;
+                if constexpr (PK) {
+                    if (j == 0) {
+                        double* pk = park_warp + (t * 8 + (lane >> 2)) * PARK_DOUBLES;
+                        pk[0] = p[t].f1; pk[1] = p[t].f2; pk[2] = p[t].lamsf6; pk[3] = Jl[t];
+                    }
+                }
                 if constexpr (C1 == CLS_G) e[1] = __shfl_sync(full, ee, base + 1);
                 if constexpr (C2 == CLS_G) e[2] = __shfl_sync(full, ee, base + 2);
                 if (DYN) e[3] = __shfl_sync(full, ee, base + 3);
@@ -274,17 +293,18 @@ struct WarpTiles {
         }
     }
 
-    // accumulate lags [kc, kc + 4*ngroups); shared memory holds that range at local index 0
-    __device__ __forceinline__ void chunk(const SmemView& s, const PlanView& pv, int kc, int ngroups, int lane) {
+    // accumulate lags [kc, kc + 4*ngroups); shared memory holds lag kc at local lag index kl (a multiple of 4: 0 for a
+    // streamed chunk, kc when the whole table is resident)
+    __device__ __forceinline__ void chunk(const SmemView& s, const PlanView& pv, int kc, int ngroups, int lane, int kl = 0) {
         if (!ANY_LOOP) return;
         const int j = lane & 3, r = lane >> 2;
         int k = kc + j;
-        const double* pf = ngrtd_smem + s.Xf + xf_index(j, r);     // chunks start at multiples of 4 lags
-        const double* pd = ngrtd_smem + s.Xd + xf_index(j, r);
-        const double2* pi = reinterpret_cast<const double2*>(ngrtd_smem + s.itp) + j;
-        const double* px = ngrtd_smem + s.xraw + j;
-        const double* pxd = ngrtd_smem + s.xrawd + j;
-        const double* tbl = ngrtd_smem + s.tbl + (lane & (TBL_REP - 1));   // this lane's copy of the exp table
+        const double* pf = ngrtd_smem + s.Xf + xf_index(kl + j, r);     // chunks start at multiples of 4 lags
+        const double* pd = ngrtd_smem + s.Xd + xf_index(kl + j, r);
+        const double2* pi = reinterpret_cast<const double2*>(ngrtd_smem + s.itp) + kl + j;
+        const double* px = ngrtd_smem + s.xraw + kl + j;
+        const double* pxd = ngrtd_smem + s.xrawd + kl + j;
+        const unsigned int tbl = (unsigned int)(lane & (ExpCfg<TB>::REP - 1)) << 3;   // byte offset of this lane's copy of the exp table
         const double dtp = pv.dtp;
         {   // first group of the chunk: direct evaluation (handles tp_0 = 1e-5 and re-anchors the recurrences)
             double bf = pf[0];
@@ -358,6 +378,7 @@ struct WarpTiles {
             }
         }
 #endif
+#pragma unroll 2
         for (; g + UA <= ngroups; g += UA) {
 #pragma unroll
             for (int u = 0; u < UA; u++) {
@@ -384,6 +405,7 @@ struct WarpTiles {
                 }
             }
         }
+        if constexpr (UA > 1)
         for (; g < ngroups; g++) {   // remainder groups
             k += 4;
             pf += 4 * NCOL;
@@ -410,6 +432,45 @@ struct WarpTiles {
     }
 
 #undef NGRTD_LOAD_IT
+
+    // ---- tape schedule of k_forward: a unit's lag range may be cut between warps.  The warp that holds the range starting
+    // at lag 0 owns the unit (it runs end()); every other range stores its accumulators (NPART doubles per lane and tile,
+    // lane-contiguous: conflict-free) for the owner to add.  All ranges use the same weight scale (geometric weights are
+    // relative to tp_k0, dispersion weights are absolute), so partial sums simply add.
+    __device__ __forceinline__ void store_partial(double* slot, int lane) const {
+        int i = 0;
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+            if constexpr (LOOP1) {
+                double x0 = a1[t][0][0], x1 = a1[t][0][1];
+#pragma unroll
+                for (int u = 1; u < UA; u++) { x0 += a1[t][u][0]; x1 += a1[t][u][1]; }
+                slot[(i++) * 32 + lane] = x0; slot[(i++) * 32 + lane] = x1;
+                if constexpr (DYN) slot[(i++) * 32 + lane] = ad1[t];
+            }
+            if constexpr (LOOP2) {
+                double x0 = a2[t][0][0], x1 = a2[t][0][1];
+#pragma unroll
+                for (int u = 1; u < UA; u++) { x0 += a2[t][u][0]; x1 += a2[t][u][1]; }
+                slot[(i++) * 32 + lane] = x0; slot[(i++) * 32 + lane] = x1;
+                if constexpr (DYN) slot[(i++) * 32 + lane] = ad2[t];
+            }
+        }
+    }
+    __device__ __forceinline__ void add_partial(const double* slot, int lane) {
+        int i = 0;
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+            if constexpr (LOOP1) {
+                a1[t][0][0] += slot[(i++) * 32 + lane]; a1[t][0][1] += slot[(i++) * 32 + lane];
+                if constexpr (DYN) ad1[t] += slot[(i++) * 32 + lane];
+            }
+            if constexpr (LOOP2) {
+                a2[t][0][0] += slot[(i++) * 32 + lane]; a2[t][0][1] += slot[(i++) * 32 + lane];
+                if constexpr (DYN) ad2[t] += slot[(i++) * 32 + lane];
+            }
+        }
+    }
 
     // ---- dispersion tail (NGRTD_DM_TAIL builds) -------------------------------------------------------------------------
     // Beyond Kc every folded column is an analytic function of the lag (PlanView::ct), so
@@ -522,17 +583,25 @@ struct WarpTiles {
     // normalise, mix the two components, apply tracer rules; lane (r, j) returns the outputs of tracers
     // j, j+4 of chain r in val[0..1] (NaN-propagating exactly like f1*cout1 + f2*cout2 of the reference)
     __device__ __forceinline__ void end(const ChainPar (&p)[NT], const PlanView& pv, double* scratch_warp, int lane,
-                                        double (&val)[NT][2]) {
+                                        double (&val)[NT][2], const double* park_warp = nullptr) {
         const int j = lane & 3, r = lane >> 2;
         const unsigned full = 0xffffffffu;
+        if constexpr (PK) __syncwarp();
 #pragma unroll
         for (int t = 0; t < NT; t++) {
+            double pf1, pf2, plam, pJ;
+            if constexpr (PK) {
+                const double* pk = park_warp + (t * 8 + r) * PARK_DOUBLES;
+                pf1 = pk[0]; pf2 = pk[1]; plam = pk[2]; pJ = pk[3];
+            } else {
+                pf1 = p[t].f1; pf2 = p[t].f2; plam = p[t].lamsf6; pJ = Jl[t];
+            }
 #pragma unroll
             for (int u = 1; u < UA; u++) {
                 a1[t][0][0] += a1[t][u][0]; a1[t][0][1] += a1[t][u][1];
                 a2[t][0][0] += a2[t][u][0]; a2[t][0][1] += a2[t][u][1];
             }
-            if (tail_active(pv, ANY_G, ANY_D)) {         // analytic tail [Kc, L): closed form (G), quadrature (D, NGRTD_DM_TAIL)
+            if (TM != 0 && tail_active(pv, ANY_G, ANY_D)) {         // analytic tail [Kc, L): closed form (G), quadrature (D, NGRTD_DM_TAIL)
                 const double dtp = pv.dtp;
                 if constexpr (C1 == CLS_G) {
                     double a = (double)max(c1[t].k0, pv.Kc), n = (double)pv.L - a;
@@ -632,9 +701,9 @@ struct WarpTiles {
                 }
             }
             // cout = f1*cout1 + f2*cout2 (run_age_mcmc_utils.py:154); cout2 = 0.0 without a second component
-            m[0] = p[t].f1 * x1[0] + p[t].f2 * x2[0];
-            m[1] = p[t].f1 * x1[1] + p[t].f2 * x2[1];
-            if (DYN) md = p[t].f1 * xd1 + p[t].f2 * xd2;
+            m[0] = pf1 * x1[0] + pf2 * x2[0];
+            m[1] = pf1 * x1[1] + pf2 * x2[1];
+            if (DYN) md = pf1 * xd1 + pf2 * xd2;
             double* sc = scratch_warp + (t * 8 + r) * NCOL;
             sc[2 * j] = m[0];
             sc[2 * j + 1] = m[1];
@@ -649,9 +718,9 @@ struct WarpTiles {
                         v = md;
                     } else {
                         double va = td.col_a >= 0 ? sc[td.col_a] : 0.0;
-                        v = td.col_b >= 0 ? va + Jl[t] * sc[td.col_b] : va;
+                        v = td.col_b >= 0 ? va + pJ * sc[td.col_b] : va;
                     }
-                    if (td.sf6) v *= (1.0 + p[t].lamsf6);
+                    if (td.sf6) v *= (1.0 + plam);
                 }
                 val[t][q] = v;
             }
@@ -709,29 +778,45 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int 
 // ---------------------------------------------------------------- per-CTA scaffolding shared by the kernels
 // Shared-memory carve-up, chunk streaming of the lag tables and the unit schedule.  k_forward evaluates one
 // parameter vector per chain; k_mcmc_age (ngrtd_mcmc.cuh) runs whole Metropolis steps around eval().
-template <int C1, int C2, bool DYN, int NT, int UA>
+// Shared-memory footprint (doubles) of the forward tables + per-warp scratch (+ the hand-off slots and flags of the tape
+// schedule); the launchers size the dynamic shared memory with the same function FwdCta::setup lays it out with.
+template <class WT>
+__host__ __device__ inline int fwd_smem_doubles(int nwarps, int lc_cap, bool tape) {
+    int p = ExpCfg<WT::TBITS>::DOUBLES + 2 + nwarps * WT::NTILES * 8 * NCOL + lc_cap * NCOL;
+    if (WT::ANY_D) p += lc_cap * NCOL + 2 * lc_cap;
+    if (WT::DYNAMIC) p += lc_cap + (WT::ANY_D ? lc_cap : 0);
+    if (tape) p += nwarps * WT::NTILES * WT::NPART * 32 + ((nwarps + 2) >> 1);
+    if (WT::PARK) p += nwarps * WT::NTILES * 8 * PARK_DOUBLES;
+    return p;
+}
+
+template <int C1, int C2, bool DYN, int NT, int UA, int TB, int TM = 1, bool PK = false>
 struct FwdCta {
-    using WT = WarpTiles<C1, C2, DYN, NT, UA>;
+    using WT = WarpTiles<C1, C2, DYN, NT, UA, TB, TM, PK>;
     SmemView s;
     const PlanView& pv;
     int lc_cap, nchunks, nwarps, nthreads, tid, lane, warp;
     int Lloop;       // lags covered by the lag loop: Lpad, or Kc when the analytic tail applies
-    int scratch_off;
+    int scratch_off, park_off;
     unsigned int phase;
     bool need_J, pending;   // pending: resident tables issued (TMA in flight), not yet waited for
+    bool tape;              // tape schedule active (k_forward, resident tables): hand-off slots are laid out
 
     __device__ __forceinline__ FwdCta(const PlanView& pv_) : pv(pv_) {}
 
-    // returns the offset (in doubles) of the first shared-memory double not used by the forward tables
-    __device__ __forceinline__ int setup(int lc_cap_) {
+    // returns the offset (in doubles) of the first shared-memory double not used by the forward tables.
+    // want_tape: reserve the hand-off slots of the tape schedule (k_forward with resident tables)
+    __device__ __forceinline__ int setup(int lc_cap_, bool want_tape = false) {
         lc_cap = lc_cap_;
         nthreads = blockDim.x;
         nwarps = nthreads >> 5;
         tid = threadIdx.x;
         lane = tid & 31;
-        warp = tid >> 5;
+        // broadcast from lane 0: tells the compiler the warp index is warp-uniform, so everything derived from it (the tape
+        // cuts, loop trip counts) stays on the uniform datapath and mma.sync needs no WARPSYNC in front of it
+        warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
         int p = 0;
-        s.tbl = p; p += TBL_DOUBLES;       // first: 128-byte aligned, so copy c of every entry sits in banks 2c, 2c+1
+        s.tbl = p; p += ExpCfg<TB>::DOUBLES;   // first: 128-byte aligned, so copy c of every entry sits in banks 2c, 2c+1
         s.bar = p; p += 2;
         s.scratch = p; p += nwarps * NT * 8 * NCOL;
         s.Xf = p; p += lc_cap * NCOL;
@@ -740,15 +825,22 @@ struct FwdCta {
         s.xraw = p; if (DYN) p += lc_cap;
         s.xrawd = p; if (DYN && WT::ANY_D) p += lc_cap;
         scratch_off = s.scratch + warp * NT * 8 * NCOL;
-        Lloop = tail_active(pv, WT::ANY_G, WT::ANY_D) ? pv.Kc : pv.Lpad;
+        Lloop = (TM != 0 && tail_active(pv, WT::ANY_G, WT::ANY_D)) ? pv.Kc : pv.Lpad;
         nchunks = WT::ANY_LOOP ? (Lloop + lc_cap - 1) / lc_cap : 1;
+        tape = want_tape && nchunks == 1;
+        s.part = p; if (tape) p += nwarps * NT * WT::NPART * 32;
+        s.flag = p; if (tape) p += (nwarps + 2) >> 1;
+        s.park = p; if (PK) p += nwarps * NT * 8 * PARK_DOUBLES;
+        park_off = s.park + warp * NT * 8 * PARK_DOUBLES;
         need_J = false;
         for (int t = 0; t < pv.ntracer; t++) need_J |= (pv.tr[t].col_b >= 0);
         phase = 0;
         if (tid == 0) mbar_init(reinterpret_cast<unsigned long long*>(ngrtd_smem + s.bar), 1);
         if (WT::ANY_D) {
-            for (int i = tid; i < TBL_DOUBLES; i += nthreads) ngrtd_smem[s.tbl + i] = pv.tbl[i >> TBL_REP_BITS];
+            const double* tg = (TB == 11) ? pv.tbl11 : pv.tbl7;
+            for (int i = tid; i < ExpCfg<TB>::DOUBLES; i += nthreads) ngrtd_smem[s.tbl + i] = tg[i >> ExpCfg<TB>::REP_BITS];
         }
+        if (tape && tid < nwarps) reinterpret_cast<volatile int*>(ngrtd_smem + s.flag)[tid] = 0;
         __syncthreads();
         pending = false;
         if (nchunks == 1 && WT::ANY_LOOP) {           // resident tables: one TMA load per launch, waited for lazily so
@@ -794,7 +886,7 @@ struct FwdCta {
     // take part in the chunk loads and barriers).
     __device__ __forceinline__ void eval(const ChainPar (&par)[NT], bool active, bool lockstep, double (&val)[NT][2]) {
         WT w;
-        w.begin(par, pv, lane, need_J);
+        w.begin(par, pv, lane, need_J, ngrtd_smem + park_off);
         if (!lockstep) {
             if (pending) { wait_chunk(); pending = false; }
             w.chunk(s, pv, 0, Lloop / 4, lane);
@@ -808,7 +900,21 @@ struct FwdCta {
                 if (active) w.chunk(s, pv, kc, len / 4, lane);
             }
         }
-        if (active) w.end(par, pv, ngrtd_smem + scratch_off, lane, val);
+        if (active) w.end(par, pv, ngrtd_smem + scratch_off, lane, val, ngrtd_smem + park_off);
+    }
+    // lock-step rounds only (k_forward with streamed tables; its resident-table path is the tape schedule)
+    __device__ __forceinline__ void eval_lockstep(const ChainPar (&par)[NT], bool active, double (&val)[NT][2]) {
+        WT w;
+        w.begin(par, pv, lane, need_J, ngrtd_smem + park_off);
+        for (int c = 0; c < nchunks; c++) {
+            int kc = c * lc_cap;
+            int len = min(lc_cap, Lloop - kc);
+            __syncthreads();
+            load_chunk(kc, len);
+            __syncthreads();
+            if (active) w.chunk(s, pv, kc, len / 4, lane);
+        }
+        if (active) w.end(par, pv, ngrtd_smem + scratch_off, lane, val, ngrtd_smem + park_off);
     }
 
     // Unit schedule.  Resident tables: static and balanced -- units are dealt round-robin to the 4*gridDim.x SM
@@ -884,21 +990,41 @@ __device__ __forceinline__ double lik_reduce(int kind, int ntracer, int j, const
 // first round of units streams in while the SMs start, the second round is prefetched under the first) instead of a
 // staged cudaMemcpyAsync.  Units whose byte count or source address is not a multiple of 16 (ragged last unit, odd
 // row offsets) are staged with plain lane loads.
-template <int C1, int C2, bool DYN, int NT, int UA, int MAXW>
+//
+// Schedule with resident tables (r2): the TAPE.  A CTA takes a contiguous block of units; their lag loops are laid end to
+// end on a tape of (units x lag groups) and the tape is cut into one equal segment per warp.  A unit whose lag range is cut
+// is finished by the warp that holds its first lags (the owner); the warps holding the other ranges publish their DMMA
+// accumulators through shared memory (WarpTiles::store_partial) -- they do so at the START of their segment, the owner
+// collects at the END of its own, so the flags are practically never waited for and no cycle of waits exists.
+// What it buys over the r1 schedule (units dealt round-robin to warps, every warp whole units):
+//   * every warp carries the same number of lag groups, so the four warps of a sub-partition share the FP64/DMMA pipe
+//     until the last group (r1: 1.73 units per warp at 65,536 chains -> the second round ran 3 of 4 warps);
+//   * the cuts fall at different lags in different warps, so their prologues (parameter loads, divisions, exp) and
+//     epilogues (normalisation, mixing, likelihood, stores) no longer coincide: while one warp is outside its lag loop the
+//     others keep the pipe busy (r1: all four in lock step, ~7 us of idle pipe per round, profiles/r1_notes.md);
+//   * a batch smaller than the grid still uses every warp of the SMs it touches.
+// Results are deterministic for a given (B, grid); they differ from a different cut of the same chain by rounding only
+// (different association of the same sums), which the parity tests bound at 1e-10 against the reference.
+// Tables streamed in chunks (long lag axes): CTA-wide rounds in lock step as in r1.
+//
+// Programmatic dependent launch: the kernel triggers its dependents at once and waits for its own predecessor
+// (griddepcontrol.wait) only after the table loads, so with the launch attribute set by launch_forward_t the set-up of
+// launch i+1 runs under the tail of launch i.  Without the attribute both instructions are no-ops.
+constexpr int TAPE_MIN_GROUPS = 8;     // a cut closer than this to a unit boundary is moved onto the boundary
+
+template <int C1, int C2, bool DYN, int NT, int UA, int MAXW, bool TAIL>
 __global__ void __launch_bounds__(MAXW * 32, 1)
 k_forward(PlanView pv, SlotMap sm, const double* __restrict__ theta, long long B, double* __restrict__ out,
-          double* __restrict__ logp, LikPar lik, int lc_cap, int stage) {
-    FwdCta<C1, C2, DYN, NT, UA> cta(pv);
-    int p_end = cta.setup(lc_cap);
+          double* __restrict__ logp, LikPar lik, int lc_cap, int stage, int tape_min) {
+    using CTA = FwdCta<C1, C2, DYN, NT, UA, FWD_TB, TAIL ? 1 : 0, true>;
+    using WT = typename CTA::WT;
+    asm volatile("griddepcontrol.launch_dependents;");
+    CTA cta(pv);
+    int p_end = cta.setup(lc_cap, true);
     p_end = (p_end + 1) & ~1;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int j = cta.lane & 3, r = cta.lane >> 2;
     const long long nunits = (B + NT * 8 - 1) / (NT * 8);
-    double ob[2], is[2], lc[2];                 // the lane's two tracers (j, j+4)
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-        int tr = min(j + 4 * q, MAX_TRACER - 1);
-        ob[q] = lik.obs[tr]; is[q] = lik.isd[tr]; lc[q] = lik.lc[tr];
-    }
     const int th_unit = NT * 8 * sm.ndim;       // doubles per staged unit
     double* const stg = ngrtd_smem + p_end + cta.warp * th_unit;
     unsigned long long* const tbar = reinterpret_cast<unsigned long long*>(ngrtd_smem + p_end + cta.nwarps * th_unit) + cta.warp;
@@ -920,51 +1046,144 @@ k_forward(PlanView pv, SlotMap sm, const double* __restrict__ theta, long long B
             for (int i_ = cta.lane; i_ < (int)n_; i_ += 32) stg[i_] = src_[i_];                         \
         }                                                                                               \
     } while (0)
-    cta.sched_begin(nunits);
-    if (stage) {
-        if (cta.lane == 0) mbar_init(tbar, 1);
-        __syncwarp();
-        if (cta.sched_valid() && cta.active) NGRTD_STAGE_UNIT(cta.unit);
-    }
-    for (; cta.sched_valid(); cta.sched_next()) {
-        const long long u = cta.unit;
-        const bool active = cta.active, lockstep = cta.lockstep;
-        ChainPar par[NT];
-        long long chain[NT];
-        if (stage && active) {
-            if (staged_tma) { mbar_wait(tbar, tphase); tphase ^= 1u; }
+    // outputs + likelihood of one finished unit (lane (r, j): tracers j, j+4 of chain r of every tile)
+#define NGRTD_EMIT_UNIT()                                                                               \
+    do {                                                                                                \
+        /* the lane's two tracers (j, j+4): read from the kernel parameters here, not held across the lag loop */ \
+        double ob[2], is[2], lc[2];                                                                     \
+        _Pragma("unroll") for (int q = 0; q < 2; q++) {                                                 \
+            int tr = min(j + 4 * q, MAX_TRACER - 1);                                                    \
+            ob[q] = lik.obs[tr]; is[q] = lik.isd[tr]; lc[q] = lik.lc[tr];                               \
+        }                                                                                               \
+        _Pragma("unroll") for (int t = 0; t < NT; t++) {                                                \
+            bool ok = chain[t] < B;                                                                     \
+            if (out != nullptr && ok) {                                                                 \
+                if (j < pv.ntracer) out[chain[t] * pv.ntracer + j] = val[t][0];                         \
+                if (j + 4 < pv.ntracer) out[chain[t] * pv.ntracer + j + 4] = val[t][1];                 \
+            }                                                                                           \
+            if (logp != nullptr) {                                                                      \
+                double nu = (lik.kind == 1) ? lik.nu[ok ? chain[t] : B - 1] : 0.0;                      \
+                double acc = lik_reduce(lik.kind, pv.ntracer, j, val[t], ob, is, lc, nu);               \
+                if (j == 0 && ok) logp[chain[t]] = acc;                                                 \
+            }                                                                                           \
+        }                                                                                               \
+    } while (0)
+
+    if (cta.tape) {
+        // ---- tape schedule: this CTA's units [ub0, ub1), ng lag groups each, cut into nwarps segments
+        // (tape positions are 32-bit: the launcher keeps units-per-CTA x lag groups below 2^31)
+        const int ng = WT::ANY_LOOP ? cta.Lloop / 4 : 1;
+        const long long ub0 = nunits * blockIdx.x / gridDim.x, ub1 = nunits * (blockIdx.x + 1) / gridDim.x;
+        const int G = (int)(ub1 - ub0) * ng;
+        const int nw = cta.nwarps;
+        auto cut = [&](int w) -> int {
+            int c = (int)((long long)G * w / nw);
+            const int rem = c % ng;
+            if (rem < tape_min) c -= rem;
+            else if (ng - rem < tape_min) c += ng - rem;
+            return c;
+        };
+        int pos = cut(cta.warp);
+        const int s1 = cut(cta.warp + 1);
+        volatile int* const flags = reinterpret_cast<volatile int*>(ngrtd_smem + cta.s.flag);
+        const int part_sz = NT * WT::NPART * 32;
+        if (stage) {
+            if (cta.lane == 0) mbar_init(tbar, 1);
             __syncwarp();
+            if (pos < s1) NGRTD_STAGE_UNIT(ub0 + pos / ng);
         }
-#pragma unroll
-        for (int t = 0; t < NT; t++) {
-            chain[t] = (u * NT + t) * 8 + r;
-            long long cl = chain[t] < B ? chain[t] : B - 1;
-            if (stage && active) par[t] = load_chain_par(stg, sm, cl - u * (NT * 8), pv, cta.need_J);
-            else par[t] = load_chain_par(theta, sm, active ? cl : 0, pv, cta.need_J);
-        }
-        if (stage && active) {
-            __syncwarp();                                   // every lane holds its rows: the slot is free again
-            const long long un = cta.sched_peek();
-            if (un < nunits) NGRTD_STAGE_UNIT(un);
-        }
-        double val[NT][2];
-        cta.eval(par, active, lockstep, val);
-        if (!active) continue;
-#pragma unroll
-        for (int t = 0; t < NT; t++) {
-            bool ok = chain[t] < B;
-            if (out != nullptr && ok) {
-                if (j < pv.ntracer) out[chain[t] * pv.ntracer + j] = val[t][0];
-                if (j + 4 < pv.ntracer) out[chain[t] * pv.ntracer + j + 4] = val[t][1];
+        while (pos < s1) {
+            const int ul = pos / ng;
+            const int g0 = pos - ul * ng;
+            const int g1 = min(ng, g0 + (s1 - pos));
+            const long long u = ub0 + ul;
+            ChainPar par[NT];
+            if (stage) {
+                if (staged_tma) { mbar_wait(tbar, tphase); tphase ^= 1u; }
+                __syncwarp();
             }
-            if (logp != nullptr) {
-                double nu = (lik.kind == 1) ? lik.nu[ok ? chain[t] : B - 1] : 0.0;
-                double acc = lik_reduce(lik.kind, pv.ntracer, j, val[t], ob, is, lc, nu);
-                if (j == 0 && ok) logp[chain[t]] = acc;
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+                const long long ch = (u * NT + t) * 8 + r;
+                long long cl = ch < B ? ch : B - 1;
+                if (stage) par[t] = load_chain_par(stg, sm, cl - u * (NT * 8), pv, cta.need_J);
+                else par[t] = load_chain_par(theta, sm, cl, pv, cta.need_J);
             }
+            pos += g1 - g0;
+            if (stage) {
+                __syncwarp();                                   // every lane holds its rows: the slot is free again
+                if (pos < s1) NGRTD_STAGE_UNIT(ub0 + pos / ng);
+            }
+            WT w;
+            w.begin(par, pv, cta.lane, cta.need_J, ngrtd_smem + cta.park_off);
+            if (cta.pending) { cta.wait_chunk(); cta.pending = false; }
+            w.chunk(cta.s, pv, 4 * g0, g1 - g0, cta.lane, 4 * g0);
+            if (g0 != 0) {
+                // a later range of a unit owned by a lower warp: publish the accumulators
+                w.store_partial(ngrtd_smem + cta.s.part + cta.warp * part_sz, cta.lane);
+                __threadfence_block();
+                __syncwarp();
+                if (cta.lane == 0) flags[cta.warp] = 1;
+            } else {
+                if (g1 < ng) {
+                    // owner of a cut unit: the remaining ranges belong to the next warps (each publishes at most one partial)
+                    const int uend = (ul + 1) * ng;
+                    int c2 = s1;                                // = cut(warp + 1): start of the next warp's segment
+                    for (int w2 = cta.warp + 1; w2 < nw && c2 < uend; w2++) {
+                        const int c3 = cut(w2 + 1);
+                        if (c3 > c2) {                          // non-empty segment: its first range continues this unit
+                            while (flags[w2] == 0) {}
+                            __threadfence_block();
+                            w.add_partial(ngrtd_smem + cta.s.part + w2 * part_sz, cta.lane);
+                        }
+                        c2 = c3;
+                    }
+                }
+                double val[NT][2];
+                w.end(par, pv, ngrtd_smem + cta.scratch_off, cta.lane, val, ngrtd_smem + cta.park_off);
+                long long chain[NT];
+#pragma unroll
+                for (int t = 0; t < NT; t++) chain[t] = ((ub0 + ul) * NT + t) * 8 + r;
+                NGRTD_EMIT_UNIT();
+            }
+        }
+    } else {
+        // ---- tables streamed in chunks: CTA-wide rounds in lock step
+        cta.sched_begin(nunits);
+        if (stage) {
+            if (cta.lane == 0) mbar_init(tbar, 1);
+            __syncwarp();
+            if (cta.sched_valid() && cta.active) NGRTD_STAGE_UNIT(cta.unit);
+        }
+        for (; cta.sched_valid(); cta.sched_next()) {
+            const long long u = cta.unit;
+            const bool active = cta.active;
+            ChainPar par[NT];
+            long long chain[NT];
+            if (stage && active) {
+                if (staged_tma) { mbar_wait(tbar, tphase); tphase ^= 1u; }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+                chain[t] = (u * NT + t) * 8 + r;
+                long long cl = chain[t] < B ? chain[t] : B - 1;
+                if (stage && active) par[t] = load_chain_par(stg, sm, cl - u * (NT * 8), pv, cta.need_J);
+                else par[t] = load_chain_par(theta, sm, active ? cl : 0, pv, cta.need_J);
+            }
+            if (stage && active) {
+                __syncwarp();                                   // every lane holds its rows: the slot is free again
+                const long long un = cta.sched_peek();
+                if (un < nunits) NGRTD_STAGE_UNIT(un);
+            }
+            double val[NT][2];
+            cta.eval_lockstep(par, active, val);
+            if (!active) continue;
+            NGRTD_EMIT_UNIT();
         }
     }
 #undef NGRTD_STAGE_UNIT
+#undef NGRTD_EMIT_UNIT
     if (cta.pending) cta.wait_chunk();      // warps without work must not exit under an in-flight bulk copy
 }
 
