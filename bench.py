@@ -10,10 +10,17 @@ column, computed but not counted: SURVEY.md section 8d) on each GPU (weak scalin
 the data path).  Prints ONE JSON line (rank 0).
 
 metric  : likelihood evals/s = chains x steps x tracers / seconds (whole job, all GPUs)
-value   : inputs resident in HBM, CUDA events on the launching stream, max over ranks
-e2e     : the same metric through the host-buffer C-ABI call (pinned host theta -> H2D -> kernel -> D2H logp)
-roofline: algorithmic FP64 flops (F_step = 2*L*(T+1)*n_comp per chain) / mean kernel time vs the measured FP64 peak
+value   : inputs resident in HBM; a timed region = K launches back to back between two CUDA events on the launching
+          stream; the region is repeated (>= 20 times, >= 50 ms in total) and the MEDIAN region is reported, max over ranks;
+          nvidia-smi clocks are sampled while the regions run
+e2e     : the same metric through the host-buffer C-ABI call (pinned host theta -> H2D -> kernel -> D2H logp), median of
+          repeated K-step runs; `host_link` = a plain cudaMemcpyAsync probe of the same pinned buffers on every rank
+roofline: algorithmic FP64 flops (F_step = 2*L*(T+1)*n_comp per chain) / average launch duration over the timed region
+          vs the measured FP64 peak; `kernel_ms_isolated` = the same launches bracketed one by one
 cpu_baseline / --impl reference: the plain-C oracle port of the reference arithmetic on the host cores
+Informational blocks: `informative` (cfg-3 shapes, theta inside the data range: no NaN outputs), `cfg2` (real 25,256-lag
+series, EPM joint inversion of CFC-12 / SF6 / 3H / 4He), `cfg5` (10,000-lag axis, EPM + dispersion with 4He), `sampler`
+(fused Metropolis steps), `ess` (config-1 ESS/s).
 """
 import argparse
 import json
@@ -26,9 +33,8 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "tests")):
-    if p not in sys.path:
-        sys.path.insert(0, p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 CHAINS_PER_GPU = 65536
 L = 840
@@ -39,21 +45,19 @@ F_STEP = 2.0 * L * (T_COUNTED + 1) * N_COMP          # 23,520 algorithmic flops 
 # DFMA 36.2-36.5 TFLOP/s burst and sustained, DMMA.8x8x4 36.96; MEASURED_PEAKS.json carries no FP64 entry.
 FP64_PEAK_TFLOPS = 36.45
 # dram__bytes_read.sum + dram__bytes_write.sum of k_forward at this workload, one `ncu --set full` capture
-# (profiles/r1_ncu_forward_summary_final.txt: dram__bytes_read.sum 4.17 MB, dram__bytes_write.sum 0); per launch.
-NCU_DRAM_BYTES_PER_LAUNCH = 4.17e6
+# (profiles/r2_ncu_forward_summary.txt: dram__bytes_read.sum 3.88 MB, dram__bytes_write.sum 0); per launch.
+NCU_DRAM_BYTES_PER_LAUNCH = 3.88e6
 METRIC = "likelihood evals/sec (chains x draws x tracers)"
 UNIT = "tracer-likelihood evals/s"
+OBS = np.array([8.0, 40.0, 150.0, 300.0, 50.0, 5.0, 1e-8])
 
 
-def workload_config(n_gpus, extra=None):
-    cfg = {"workload": "cfg3: synthetic batch, 65,536 chains/GPU x EPM+dispersion RTDs x 840-month input x 6 tracers "
-                       "(+He4_ter column computed, not counted)",
-           "chains_per_gpu": CHAINS_PER_GPU, "lags": L, "tracers_counted": T_COUNTED, "tracers_computed": 7,
-           "n_comp": N_COMP, "likelihood": "normal", "parallelism": "chains sharded x%d, no data-path collective" % n_gpus,
-           "l2": "inputs larger than L2: 40 rotating theta batches (147 MB) per GPU"}
-    if extra:
-        cfg.update(extra)
-    return cfg
+def workload_config(n_gpus):
+    return {"workload": "cfg3: synthetic batch, 65,536 chains/GPU x EPM+dispersion RTDs x 840-month input x 6 tracers "
+                        "(+He4_ter column computed, not counted)",
+            "chains_per_gpu": CHAINS_PER_GPU, "lags": L, "tracers_counted": T_COUNTED, "tracers_computed": 7,
+            "n_comp": N_COMP, "likelihood": "normal", "parallelism": "chains sharded x%d, no data-path collective" % n_gpus,
+            "l2": "inputs larger than L2: 40 rotating theta batches (147 MB) per GPU"}
 
 
 class ClockSampler:
@@ -111,13 +115,13 @@ class ClockSampler:
 
 
 def cpu_port_rate(seconds_target, nthreads=0):
-    """Time the plain-C oracle port (oracle/ngrtd_oracle.c) on a bounded sample of the cfg-3 workload."""
+    """Time the plain-C oracle port (oracle/ngrtd_oracle.c) on a bounded sample of the cfg-3 workload.
+    A step = forward model of every chain of the sample AND its Gaussian log-likelihood, both inside the clock."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import c_oracle
-    from helpers import synth_descs
     from noblegas_rtd_mcmc_b200 import synthetic
     pn = list(synthetic.PAR_NAMES_CFG3)
-    X, descs = synth_descs(pn)
+    X, descs = synthetic.series_matrix_and_descs(pn)
     cores = nthreads or c_oracle.max_threads()
     probe = synthetic.theta_cfg3(32 * cores, 0)
     t0 = time.perf_counter()
@@ -125,19 +129,20 @@ def cpu_port_rate(seconds_target, nthreads=0):
     dt = max(time.perf_counter() - t0, 1e-4)
     n = int(min(CHAINS_PER_GPU, max(64 * cores, probe.shape[0] * seconds_target / dt)))
     theta = synthetic.theta_cfg3(n, 0)
+    sd = 0.05 * OBS
 
     def step():
         t0 = time.perf_counter()
         out = c_oracle.forward(X, descs, "exp_pist_flow", "dispersion", theta, pn, nthreads=cores)
-        dt = time.perf_counter() - t0
-        # the likelihood itself is O(T) per chain and is included for completeness
-        c_oracle.loglik("normal", out, np.ones(7), np.ones(7) * 0.05)
-        return dt
+        c_oracle.loglik("normal", out, OBS, sd)
+        return time.perf_counter() - t0
     return step, n, cores
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the CPU implementation of the same path (C oracle port), all host threads, rank 0 only."""
+    """--impl reference: the CPU implementation of the same path (C oracle port), all host threads, rank 0 only.
+    The reference itself is pure Python (it cannot travel to the GPU box); the timed arm is the plain-C port of its
+    arithmetic, oracle/ngrtd_oracle.c (cpu_baseline.kind = "port")."""
     if rank != 0:
         return
     step, n, cores = cpu_port_rate(seconds_target=max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup))))
@@ -147,16 +152,16 @@ def run_reference(args, rank, world):
     for _ in range(args.steps):
         t += step()
     value = n * T_COUNTED * args.steps / t
-    sample = "%d of %d chains per step (same theta prior, L=840, 7 tracers computed / 6 counted), %d threads" % (
+    sample = "%d of %d chains per step (same theta prior, L=840, 7 tracers computed / 6 counted, forward + log-likelihood), %d threads" % (
         n, CHAINS_PER_GPU, cores)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.gpus, {"note": "reference is pure Python (cannot travel to the GPU box); timed "
-                                                           "arm is the plain-C port of its arithmetic, oracle/ngrtd_oracle.c"}),
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0,
+            "note": "reference is pure Python (cannot travel to the GPU box); timed arm is the plain-C port of its "
+                    "arithmetic, oracle/ngrtd_oracle.c"}
     emit(line)
 
 
@@ -192,6 +197,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the informational blocks (development)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -203,8 +209,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from helpers import synth_plan
-    from noblegas_rtd_mcmc_b200 import _lib, synthetic
+    from noblegas_rtd_mcmc_b200 import _lib, datasets, synthetic
 
     assert torch.cuda.is_available(), "bench.py (impl=ours) needs a CUDA device; there is no CPU fallback"
     torch.cuda.set_device(local)
@@ -223,23 +228,45 @@ def main():
             numa = "unchanged (%s)" % type(exc).__name__
         print("rank %d: cpu placement %s" % (rank, numa), file=sys.stderr, flush=True)
     pn = list(synthetic.PAR_NAMES_CFG3)
-    plan, _, _ = synth_plan("exp_pist_flow", "dispersion", pn, device=local)
+    X3, descs3 = synthetic.series_matrix_and_descs(pn)
+    plan = _lib.Plan(X3, descs3, "exp_pist_flow", "dispersion", device=local)
     B = CHAINS_PER_GPU
     NBUF = 40
+    K = args.steps
     # chains are sharded by global chain id: rank r owns ids [r*B, (r+1)*B) of every rotating batch
     thetas = [torch.from_numpy(synthetic.theta_cfg3(B, seed=1000 * i + rank)).to(dev) for i in range(NBUF)]
-    obs = np.array([8.0, 40.0, 150.0, 300.0, 50.0, 5.0, 1e-8])
-    sd = 0.05 * obs
+    sd = 0.05 * OBS
     logp = torch.empty(B, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream()
-
-    def step(i):
-        plan.forward_loglik_dev(thetas[i % NBUF], pn, obs, sd, "normal", logp_t=logp, stream=stream)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0])
+        return float(x)
+
+    def timed_regions(step, nrep, k):
+        """nrep regions of k back-to-back launches, each between two CUDA events on the launching stream; barrier +
+        synchronize on both sides of the whole measurement.  Returns the per-region times in ms."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nrep)]
+        barrier()
+        i = 0
+        for a, b in evs:
+            a.record(stream)
+            for _ in range(k):
+                step(i); i += 1
+            b.record(stream)
+        barrier()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    def step(i):
+        plan.forward_loglik_dev(thetas[i % NBUF], pn, OBS, sd, "normal", logp_t=logp, stream=stream)
 
     sampler = ClockSampler(",".join(str(i) for i in range(world)) if world > 1 else local) if rank == 0 else None
     for i in range(args.warmup):
@@ -250,61 +277,74 @@ def main():
         barrier()
         for i in range(args.warmup):
             step(i)
-    barrier()
-    # ---- timed region: K steps, per-launch CUDA events on the launching stream ----
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(args.steps):
-        ev[i][0].record(stream)
-        step(i)
-        ev[i][1].record(stream)
-    e1.record(stream)
-    barrier()
-    total_ms = e0.elapsed_time(e1)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    # ---- timed regions: K steps each, repeated so that >= 50 ms are measured with the clocks sampled across them ----
+    approx_ms = 0.12
+    nrep = int(max(20, np.ceil(50.0 / (K * approx_ms))))
+    regions = timed_regions(step, nrep, K)
+    total_ms = max_over_ranks(float(np.median(regions)))
     checksum = float(torch.nansum(logp))
-    # keep the GPU under the same load long enough for nvidia-smi to see the clocks of this kernel
+    nan_frac = float(torch.isnan(logp).double().mean())
+    # the same launches bracketed one by one: the isolated duration of a launch (events between launches also switch off
+    # the programmatic overlap of launch i+1's set-up with launch i's tail)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(max(K, 20))]
+    barrier()
+    for i, (a, b) in enumerate(ev):
+        a.record(stream); step(i); b.record(stream)
+    barrier()
+    kern_iso_ms = max_over_ranks(float(np.median([a.elapsed_time(b) for a, b in ev])))
+    # keep the GPU under the same load long enough for nvidia-smi to see the clocks of this kernel in every case
     t_probe = time.perf_counter()
     i = 0
-    while time.perf_counter() - t_probe < 1.0:          # every rank: rank 0's nvidia-smi samples all GPUs of the job
+    while time.perf_counter() - t_probe < 0.6:          # every rank: rank 0's nvidia-smi samples all GPUs of the job
         for _ in range(50):
             step(i); i += 1
         torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     per_rank = None
     if world > 1:
-        t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([float(np.median(regions))], dtype=torch.float64, device=dev)
         allt = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(allt, t)
-        per_rank = [round(float(x[0]) / args.steps, 5) for x in allt]       # ms per step of every rank (the max is reported)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, kern_ms = float(t[0]), float(t[1])
-    value = world * B * T_COUNTED * args.steps / (total_ms * 1e-3)
+        per_rank = [round(float(x[0]) / K, 5) for x in allt]       # ms per step of every rank (the max is reported)
+    value = world * B * T_COUNTED * K / (total_ms * 1e-3)
+    kern_ms = total_ms / K
+
+    # ---- informational: the same shapes with theta inside the data range (no NaN outputs): same kernel, same time ----
+    thetas_inf = [torch.from_numpy(synthetic.theta_cfg3_informative(B, seed=500 + 10 * i + rank)).to(dev) for i in range(8)]
+    logp_inf = torch.empty(B, dtype=torch.float64, device=dev)
+
+    def step_inf(i):
+        plan.forward_loglik_dev(thetas_inf[i % 8], pn, OBS, sd, "normal", logp_t=logp_inf, stream=stream)
+    for i in range(5):
+        step_inf(i)
+    inf_ms = max_over_ranks(float(np.median(timed_regions(step_inf, 10, K)))) / K
+    informative = {"workload": "cfg3 shapes, theta_cfg3_informative (tau1 12-600, tau2 100-3000 steps)", "ms_per_step": inf_ms,
+                   "value": world * B * T_COUNTED / (inf_ms * 1e-3), "nan_frac": float(torch.isnan(logp_inf).double().mean()),
+                   "frac": F_STEP * B / (inf_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS}
+    del thetas_inf
 
     # ---- e2e: host buffers through the C-ABI host entry point (H2D + kernel + D2H inside the timed region) ----
-    host_thetas = [torch.from_numpy(synthetic.theta_cfg3(B, seed=77 + 1000 * i + rank)).pin_memory() for i in range(8)]
+    # theta crosses the host link without its redundant f2 = 1 - f1 column (48 instead of 56 bytes per chain): the
+    # "f1_f2c" column alias (NGRTD_P_F1_COMPLEMENT) forms f2 on the device, bit-identical to the column theta_cfg3 carries
+    pn_h = ["tau1", "tau2", "f1_f2c", "eta1", "D2", "J"]
+    host_thetas = [torch.from_numpy(np.ascontiguousarray(np.delete(synthetic.theta_cfg3(B, seed=77 + 1000 * i + rank), 3, axis=1))).pin_memory()
+                   for i in range(8)]
     host_logp = torch.empty(B, dtype=torch.float64).pin_memory()
     hl = host_logp.numpy()
 
     def e2e_step(i):
-        plan.forward_loglik_host(host_thetas[i % 8].numpy(), pn, obs, sd, "normal", logp_out=hl)
+        plan.forward_loglik_host(host_thetas[i % 8].numpy(), pn_h, OBS, sd, "normal", logp_out=hl)
 
     def timed(run):
         barrier()
         t0 = time.perf_counter()
         run()
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t[0])
-        return dt
+        return max_over_ranks(time.perf_counter() - t0)
 
     for i in range(3):
         e2e_step(i)
-    e2e_sync_s = timed(lambda: [e2e_step(i) for i in range(args.steps)])
+    e2e_sync_s = float(np.median([timed(lambda: [e2e_step(i) for i in range(K)]) for _ in range(5)]))
 
     # the same K batches through the submit / wait form of the call: DEPTH independent batches in flight, so the copy-in of
     # batch i+1 and the copy-out of batch i-1 run under the kernel of batch i.  Every step still moves its own theta from
@@ -318,20 +358,171 @@ def main():
             if i >= DEPTH:
                 plan.host_wait((i - DEPTH) % DEPTH)
             if i < n:
-                plan.forward_loglik_host_submit(host_thetas[i % 8].numpy(), pn, obs, sd, "normal", logp_out=hls[i % DEPTH],
+                plan.forward_loglik_host_submit(host_thetas[i % 8].numpy(), pn_h, OBS, sd, "normal", logp_out=hls[i % DEPTH],
                                                 slot=i % DEPTH)
 
     # Warm-up of this call path: every (host buffer, slot) pair once (8 buffers x DEPTH slots) and long enough (>= 10 ms of
-    # back-to-back batches) that the timed run does not start behind the idle gap of the pinned allocations above -- with
-    # 4 warm-up batches the first timed run of a process sometimes measured 0.15-0.18 ms/step while every later run of
-    # the same process measured 0.114 (profiles/r1_notes.md, "e2e warm-up").
+    # back-to-back batches) that the timed runs do not start behind the idle gap of the pinned allocations above
+    # (profiles/r1_notes.md, "e2e warm-up").  The K-step run is repeated and the median reported.
     e2e_warm = max(args.warmup, 100)
     e2e_pipelined(e2e_warm)
-    e2e_s = timed(lambda: e2e_pipelined(args.steps))
-    e2e_value = world * B * T_COUNTED * args.steps / e2e_s
+    e2e_runs = [timed(lambda: e2e_pipelined(K)) for _ in range(max(7, int(np.ceil(50.0 / (K * approx_ms)))))]
+    e2e_s = float(np.median(e2e_runs))
+    e2e_value = world * B * T_COUNTED * K / e2e_s
+    # host-link probe: the H2D copies of the e2e path alone (same pinned buffers, one cudaMemcpyAsync per batch), all ranks
+    # at once -- the ceiling of any host-buffer path on this box
+    dth = torch.empty(host_thetas[0].shape, dtype=torch.float64, device=dev)
+    for i in range(5):
+        dth.copy_(host_thetas[i % 8], non_blocking=True)
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    pe0.record(stream)
+    for i in range(50):
+        dth.copy_(host_thetas[i % 8], non_blocking=True)
+    pe1.record(stream)
+    barrier()
+    h2d_ms = max_over_ranks(pe0.elapsed_time(pe1) / 50)
+    h2d_bytes = B * len(pn_h) * 8
+    host_link = {"h2d_ms_per_batch": h2d_ms, "gbps_per_rank": h2d_bytes / h2d_ms / 1e6,
+                 "gbps_aggregate": world * h2d_bytes / h2d_ms / 1e6,
+                 "e2e_ceiling_evals_per_s": world * B * T_COUNTED / (h2d_ms * 1e-3),
+                 "note": "max over ranks of 50 back-to-back cudaMemcpyAsync(H2D) of one theta batch, all ranks concurrently; "
+                         "a host-buffer step cannot be faster than max(this, the kernel)"}
+    del dth
 
-    # ---- informational: the same workload as fused Metropolis steps (propose -> forward -> Student-T -> accept) inside
-    #      the persistent sampler kernel, 100 steps per launch, chains started inside the informative region ----
+    extras = {}
+    if not args.no_extras:
+        extras = run_extras(args, plan, pn, rank, world, local, dev, stream, barrier, max_over_ranks, timed_regions)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cstep, n, cores = cpu_port_rate(seconds_target=12.0)
+        cstep()
+        dt, passes = 0.0, 0
+        while dt < 10.0 and passes < 1000:          # bounded sample: about 10 s of CPU work
+            dt += cstep()
+            passes += 1
+        cpu = {"value": passes * n * T_COUNTED / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d passes over %d of %d chains (forward + log-likelihood), oracle/ngrtd_oracle.c (pthreads), %.1f s" % (passes, n, B, dt)}
+    if rank == 0:
+        achieved = F_STEP * B / (kern_ms * 1e-3) / 1e12
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+                "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+                "timing": {"regions": nrep, "steps_per_region": K, "statistic": "median region", "span_ms": float(np.sum(regions)),
+                           "region_ms_min": float(np.min(regions)), "region_ms_max": float(np.max(regions))},
+                "nan_frac": nan_frac,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * len(pn_h) * 8, "d2h_bytes_per_step": B * 8,
+                        "ms_per_step": 1e3 * e2e_s / K, "warmup_steps": e2e_warm, "runs": len(e2e_runs), "statistic": "median run",
+                        "note": "theta of a step was just written by the copy engine (L2-warm); `value` rotates 40 batches so "
+                                "that its theta comes from HBM.  Host theta has 6 columns: f2 = 1 - f1 is formed on the device "
+                                "(column alias f1_f2c), as the reference's model does (run_age_mcmc_utils.py:304)",
+                        "call": "ngrtd_forward_loglik_host_submit / ngrtd_host_wait, %d independent batches in flight: pinned "
+                                "host theta -> cudaMemcpyAsync -> kernel -> cudaMemcpyAsync -> pinned host logp, every step" % DEPTH,
+                        "host_link": host_link,
+                        "sync_call": {"value": world * B * T_COUNTED * K / e2e_sync_s, "ms_per_step": 1e3 * e2e_sync_s / K,
+                                      "call": "ngrtd_forward_loglik_host (one blocking call per batch): the kernel reads pinned host "
+                                              "theta over PCIe (one TMA bulk copy per 16-chain unit, next unit prefetched) and stores "
+                                              "logp straight into the pinned host buffer"}},
+                "gpu_launches": K,
+                "clocks": clocks, "per_rank_ms_per_step": per_rank, "cpu_placement": numa,
+                "roofline": {"bound": "tensor", "pipe": "fp64: DMMA.8x8x4 (tensor sub-pipe) shares the FP64 pipe with DFMA",
+                             "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                             "frac": achieved / FP64_PEAK_TFLOPS, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                             "peak_source": "measured FP64 DFMA peak on this pool (tools/microbench/fp64_peak.cu); "
+                                            "MEASURED_PEAKS.json has no FP64 entry",
+                             "kernel": "k_forward<G,D>", "kernel_ms": kern_ms, "kernel_ms_isolated": kern_iso_ms,
+                             "frac_isolated": F_STEP * B / (kern_iso_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+                             "flops_per_chain": F_STEP,
+                             "note": "kernel_ms = average launch duration over the timed region (launches back to back: "
+                                     "programmatic dependent launch lets launch i+1 set up under the tail of launch i); "
+                                     "kernel_ms_isolated = median of launches bracketed one by one"},
+                "informative": informative, "cpu_baseline": cpu, "checksum_logp": checksum}
+        line.update(extras)
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_extras(args, plan, pn, rank, world, local, dev, stream, barrier, max_over_ranks, timed_regions):
+    """Informational blocks: BASELINE configs 2 and 5 as forward + likelihood launches, the fused sampler, ESS/s."""
+    import torch
+    import torch.distributed as dist
+    from noblegas_rtd_mcmc_b200 import _lib, datasets, synthetic
+    B = CHAINS_PER_GPU
+    out = {}
+    # ---- cfg 2: the reference's own inversion (run_age_mcmc.py): exp_pist_flow joint fit `.123` of CFC-12, SF6, 3H, 4He on
+    #      the real yearly series (L = 25,256; constant beyond lag 128 -> exact closed-form tail, L_eff = 128) ----
+    pn2 = ["tau1", "eta1", "J", "thalf_cfc", "lamsf6"]
+    tr2 = ["CFC12", "SF6", "H3", "He4_ter"]
+    X2, d2, _ = datasets.real_series_matrix_and_descs(pn2, tr2)
+    plan2 = _lib.Plan(X2, d2, "exp_pist_flow", False, device=local)
+    rng = np.random.default_rng(11 + rank)
+    th2 = np.stack([rng.uniform(1, 1000, B), rng.uniform(1, 5, B), rng.normal(-10.42, 0.33, B), rng.uniform(5, 35, B),
+                    np.abs(rng.normal(0, 0.17, B))], axis=1)
+    th2_d = torch.from_numpy(th2).to(dev)
+    lp2 = torch.empty(B, dtype=torch.float64, device=dev)
+    obs2 = np.array([300.0, 5.0, 8.0, 1e-8]); sd2 = 0.05 * obs2
+
+    def step2(i):
+        plan2.forward_loglik_dev(th2_d, pn2, obs2, sd2, "normal", logp_t=lp2, stream=stream)
+    for i in range(5):
+        step2(i)
+    ms2 = max_over_ranks(float(np.median(timed_regions(step2, 10, 20)))) / 20
+    Leff2 = 128
+    out["cfg2"] = {"workload": "cfg2: exp_pist_flow joint inversion (CFC-12 [thalf_cfc], SF6 [lamsf6], 3H, 4He) on the reference's "
+                               "yearly series, 65,536 chains/GPU", "L": int(X2.shape[0]), "L_eff": Leff2, "tracers": 4,
+                   "kernel_ms": ms2, "value": world * B * 4 / (ms2 * 1e-3), "unit": UNIT,
+                   "frac": 2.0 * Leff2 * 5 * 1 * B / (ms2 * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+                   "nan_frac": float(torch.isnan(lp2).double().mean()),
+                   "note": "the constant tail [128, 25256) is summed in closed form (exact); frac counts only the L_eff lags looped"}
+    # the same series with a dispersion RTD (dispersion tail by quadrature, L_eff = 128)
+    pn2d = ["tau1", "D1", "J", "lamsf6"]
+    X2d, d2d, _ = datasets.real_series_matrix_and_descs(pn2d, tr2)
+    plan2d = _lib.Plan(X2d, d2d, "dispersion", False, device=local)
+    th2d = np.stack([rng.uniform(1, 1000, B), rng.uniform(0.01, 2.0, B), rng.normal(-10.42, 0.33, B), np.abs(rng.normal(0, 0.17, B))], axis=1)
+    th2d_d = torch.from_numpy(th2d).to(dev)
+
+    def step2d(i):
+        plan2d.forward_loglik_dev(th2d_d, pn2d, obs2, sd2, "normal", logp_t=lp2, stream=stream)
+    for i in range(3):
+        step2d(i)
+    ms2d = max_over_ranks(float(np.median(timed_regions(step2d, 5, 5)))) / 5
+    feat = _lib.lib.ngrtd_build_features()
+    Leff2d = 128 if (feat & 1) else int(X2d.shape[0])
+    out["cfg2_dispersion"] = {"workload": "dispersion RTD, same series and tracers, 65,536 chains/GPU", "L": int(X2d.shape[0]),
+                              "L_eff": Leff2d, "kernel_ms": ms2d, "value": world * B * 4 / (ms2d * 1e-3), "unit": UNIT,
+                              "tail": "Gauss-Legendre quadrature of the smooth constant tail" if (feat & 1) else "full lag loop",
+                              "nan_frac": float(torch.isnan(lp2).double().mean())}
+    del plan2, plan2d, th2_d, th2d_d
+    # ---- cfg 5: long lag axis, L = 10,000, exp_pist_flow + dispersion mixture with 4He accumulation, tracers
+    #      {CFC-12, SF6, 3H, 4He}; tables streamed through shared memory in 1,024-lag chunks ----
+    L5 = 10000
+    pn5 = list(synthetic.PAR_NAMES_CFG3)
+    tr5 = ["CFC12", "SF6", "H3", "He4_ter"]
+    X5, d5 = synthetic.series_matrix_and_descs(pn5, tr5, L=L5)
+    plan5 = _lib.Plan(X5, d5, "exp_pist_flow", "dispersion", device=local)
+    th5 = synthetic.theta_cfg3(B, seed=5 + rank)
+    th5[:, 0] *= L5 / 840.0
+    th5[:, 1] = np.random.default_rng(55 + rank).uniform(600.0, 15000.0 * 12, B)
+    th5_d = torch.from_numpy(th5).to(dev)
+    lp5 = torch.empty(B, dtype=torch.float64, device=dev)
+    obs5 = np.array([300.0, 5.0, 8.0, 1e-8]); sd5 = 0.05 * obs5
+
+    def step5(i):
+        plan5.forward_loglik_dev(th5_d, pn5, obs5, sd5, "normal", logp_t=lp5, stream=stream)
+    for i in range(3):
+        step5(i)
+    ms5 = max_over_ranks(float(np.median(timed_regions(step5, 5, 5)))) / 5
+    out["cfg5"] = {"workload": "cfg5: long lag axis, exp_pist_flow + dispersion mixture, CFC-12 / SF6 / 3H / 4He, 65,536 chains/GPU",
+                   "L": L5, "L_eff": L5, "tracers": 4, "kernel_ms": ms5, "value": world * B * 4 / (ms5 * 1e-3), "unit": UNIT,
+                   "frac": 2.0 * L5 * 5 * 2 * B / (ms5 * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+                   "frac_8_mma_columns": 2.0 * L5 * 8 * 2 * B / (ms5 * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+                   "nan_frac": float(torch.isnan(lp5).double().mean())}
+    del plan5, th5_d
+
+    # ---- the cfg-3 workload as fused Metropolis steps (propose -> forward -> Student-T -> accept) inside the persistent
+    #      sampler kernel, 100 steps per launch, chains started inside the informative region ----
     from noblegas_rtd_mcmc_b200.sampler import Sampler, prior
     truth = np.array([[180.0, 1500.0, 0.6, 0.4, 1.8, 0.4, synthetic.LOG10_J_MONTHLY]])
     sobs = plan.forward_host(truth, pn)[0]
@@ -348,30 +539,25 @@ def main():
     smp.run(100, tune=True, stream=stream)
     s1.record(stream)
     barrier()
-    smp_ms = s0.elapsed_time(s1) / 100.0
-    if world > 1:
-        t = torch.tensor([smp_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        smp_ms = float(t[0])
-    sampler_info = {"value": world * B * T_COUNTED / (smp_ms * 1e-3), "unit": UNIT, "ms_per_step": smp_ms,
-                    "steps_per_launch": 100, "kernel": "k_mcmc_age<G,D>", "proposal": "DE-MC-Z", "likelihood": "studentt",
-                    "accept_rate": float(smp.get("accepted").mean()) / 200.0}
+    smp_ms = max_over_ranks(s0.elapsed_time(s1) / 100.0)
+    out["sampler"] = {"value": world * B * T_COUNTED / (smp_ms * 1e-3), "unit": UNIT, "ms_per_step": smp_ms,
+                      "steps_per_launch": 100, "kernel": "k_mcmc_age<G,D>", "proposal": "DE-MC-Z", "likelihood": "studentt",
+                      "accept_rate": float(smp.get("accepted").mean()) / 200.0}
     smp.close()
-    # ---- informational: ESS/s (BASELINE.json's secondary metric) on config 1, the noble-gas closed-equilibrium fit of
-    #      well PLM1 with the reference's sampler settings (DEMetropolisZ, tune 10,000 / tune_interval 5,000), whose
-    #      posterior is validated against the reference's own summaries (tests/test_sampler_gpu.py).  262,144 chains per
-    #      GPU x 5,000 recorded draws, 2,048-slot history ring; per-chain Welford moments all-gathered over NCCL; many-chain ESS estimate. ----
-    import json as _json
+    # ---- ESS/s (BASELINE.json's secondary metric) on config 1, the noble-gas closed-equilibrium fit of well PLM1 with the
+    #      reference's sampler settings (DEMetropolisZ, tune 10,000 / tune_interval 5,000), whose posterior is validated
+    #      against the reference's own summaries (tests/test_sampler_gpu.py).  262,144 chains per GPU x 5,000 recorded draws,
+    #      2,048-slot history ring; pooled moments reduced on the device and all-reduced over NCCL; many-chain ESS estimate ----
     from noblegas_rtd_mcmc_b200 import distributed as ngdist
     from noblegas_rtd_mcmc_b200.noble_gas_mcmc import mcmc_model
-    fx = _json.load(open(os.path.join(ROOT, "tests", "golden", "ng_posterior.json")))["wells"]["PLM1"]
+    fx = json.load(open(os.path.join(ROOT, "noblegas_rtd_mcmc_b200", "data", "ng_obs_plm.json")))["wells"]["PLM1"]
     mdl = mcmc_model(fx["obs"], mcmc_model.well_elev["PLM1"])
     NGC = 262144       # one chain per thread, 92 registers: 5 warps per sub-partition need >= 242k chains (32,768 chains: 1.7)
     warm = Sampler(mdl.build_priors(), mdl.obs_mu, mdl.obs_sd, 64, plan=None, gases=mdl.gases, lik="studentt",
                    nu_range=(1.0, 30.0), tune_interval=5000, hist_cap=8, seed=1, device=local)
     warm.run(4, tune=True, stream=stream)          # first launch of k_mcmc_ng: module load, outside the timed region
     with np.errstate(all="ignore"):
-        ngdist.global_summary(4, warm.get("mean"), warm.get("m2"))     # first use imports the diagnostics module (scipy): 0.6 s
+        ngdist.pooled_summary(warm, 4)                                  # first use: module imports outside the timed region
     warm.close()
     ngs = Sampler(mdl.build_priors(), mdl.obs_mu, mdl.obs_sd, NGC, plan=None, gases=mdl.gases, lik="studentt",
                   nu_range=(1.0, 30.0), tune_interval=5000, hist_cap=2048, seed=123423, chain_offset=rank * NGC, device=local)
@@ -380,57 +566,17 @@ def main():
     ngs.run(10000, tune=True, stream=stream)
     ngs.stop_tuning()
     ngs.run(5000, tune=False, record=True, stream=stream)
+    summ = ngdist.pooled_summary(ngs, 5000)
     torch.cuda.synchronize()
-    summ = ngdist.global_summary(5000, ngs.get("mean"), ngs.get("m2"))
-    ess_s = time.perf_counter() - t_ess
-    if world > 1:
-        t = torch.tensor([ess_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ess_s = float(t[0])
-    ess_info = {"workload": "cfg1: noble-gas CE fit, well PLM1, DE-MC-Z, Student-T", "min_ess": float(np.min(summ["ess"])),
-                "max_r_hat": float(np.max(summ["r_hat"])), "seconds": ess_s, "ess_per_sec": float(np.min(summ["ess"])) / ess_s,
-                "chains": int(summ["chains"]), "steps_per_chain": 15000, "params": ngs.names,
-                "estimator": "M n var+/B over all chains (per-chain Welford moments all-gathered)",
-                "reference": "ess_bulk 1,304-4,049 per 200,000 draws (ng_interp/ng_optPLM1.csv), wall time not recoverable"}
+    ess_s = max_over_ranks(time.perf_counter() - t_ess)
+    out["ess"] = {"workload": "cfg1: noble-gas CE fit, well PLM1, DE-MC-Z, Student-T", "min_ess": float(np.min(summ["ess"])),
+                  "max_r_hat": float(np.max(summ["r_hat"])), "seconds": ess_s, "ess_per_sec": float(np.min(summ["ess"])) / ess_s,
+                  "chains": int(summ["chains"]), "steps_per_chain": 15000, "params": ngs.names,
+                  "estimator": "M n var+/B over all chains; pooled (sum mean, sum mean^2, sum M2) reduced on the device, "
+                               "one all_reduce of 3*nd+1 doubles",
+                  "reference": "ess_bulk 1,304-4,049 per 200,000 draws (ng_interp/ng_optPLM1.csv), wall time not recoverable"}
     ngs.close()
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cstep, n, cores = cpu_port_rate(seconds_target=12.0)
-        cstep()
-        dt, passes = 0.0, 0
-        while dt < 10.0 and passes < 1000:          # bounded sample: about 10 s of CPU work
-            dt += cstep()
-            passes += 1
-        cpu = {"value": passes * n * T_COUNTED / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d passes over %d of %d chains, oracle/ngrtd_oracle.c (pthreads), %.1f s" % (passes, n, B, dt)}
-    if rank == 0:
-        achieved = F_STEP * B / (kern_ms * 1e-3) / 1e12
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": workload_config(world),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * len(pn) * 8, "d2h_bytes_per_step": B * 8,
-                        "ms_per_step": 1e3 * e2e_s / args.steps, "warmup_steps": e2e_warm,
-                        "note": "theta of a step was just written by the copy engine (L2-warm); `value` rotates 40 batches so "
-                                "that its theta comes from HBM",
-                        "call": "ngrtd_forward_loglik_host_submit / ngrtd_host_wait, %d independent batches in flight: pinned "
-                                "host theta -> cudaMemcpyAsync -> kernel -> cudaMemcpyAsync -> pinned host logp, every step" % DEPTH,
-                        "sync_call": {"value": world * B * T_COUNTED * args.steps / e2e_sync_s, "ms_per_step": 1e3 * e2e_sync_s / args.steps,
-                                      "call": "ngrtd_forward_loglik_host (one blocking call per batch): the kernel reads pinned host "
-                                              "theta over PCIe (one TMA bulk copy per 16-chain unit, next unit prefetched) and stores "
-                                              "logp straight into the pinned host buffer"}},
-                "gpu_launches": args.steps,
-                "clocks": clocks, "per_rank_ms_per_step": per_rank, "cpu_placement": numa,
-                "roofline": {"bound": "tensor", "pipe": "fp64: DMMA.8x8x4 (tensor sub-pipe) shares the FP64 pipe with DFMA",
-                             "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                             "frac": achieved / FP64_PEAK_TFLOPS, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                             "peak_source": "measured FP64 DFMA peak on this pool (tools/microbench/fp64_peak.cu); "
-                                            "MEASURED_PEAKS.json has no FP64 entry",
-                             "kernel": "k_forward<G,D>", "kernel_ms": kern_ms, "flops_per_chain": F_STEP},
-                "cpu_baseline": cpu, "sampler": sampler_info, "ess": ess_info, "checksum_logp": checksum}
-        emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    return out
 
 
 if __name__ == "__main__":

@@ -56,6 +56,10 @@ extern "C" {
 #define NGRTD_P_THALF_CFC 9    /* CFC-12 first-order decay half life (:107-109) */
 #define NGRTD_P_LAMSF6 10      /* SF6 contamination factor (:160-161) */
 #define NGRTD_NSLOT 11
+/* column alias: this column is f1 AND f2 = 1 - f1 is formed on the device -- the reference's model makes f2 a deterministic
+ * 1 - f1 (run_age_mcmc_utils.py:304) and still hands both to the Op; a batched caller that owns theta can leave the
+ * redundant column out (one eighth fewer bytes over the host link).  Not allowed together with NGRTD_P_F1 / NGRTD_P_F2. */
+#define NGRTD_P_F1_COMPLEMENT 11
 
 /* rad_accum modes of tracer_conv_integral.update_pars (utils/convolution_integral_utils.py:123,313-333) */
 #define NGRTD_ACC_NONE 0
@@ -252,6 +256,12 @@ int ngrtd_sampler_stop_tuning(ngrtd_sampler* s);   /* DEMetropolisZ.stop_tuning:
 int ngrtd_sampler_get(ngrtd_sampler* s, int32_t what, double* out_d, void* stream);
 /* restore: same selectors; setting q (0) re-evaluates logp unless logp (1) is set afterwards */
 int ngrtd_sampler_set(ngrtd_sampler* s, int32_t what, const double* in_d, void* stream);
+/* K6 on the device ("ncclAllReduce of pooled moments"): sums over the sampler's chains of the per-chain
+ * Welford statistics -- out_d[0..nd) = sum_c mean, [nd..2nd) = sum_c mean^2, [2nd..3nd) = sum_c M2, out_d[3nd] = chains --
+ * 3*ndim + 1 doubles on the device (deterministic two-stage reduction, same bits for the same chains).  Ranks add these
+ * vectors with ONE all-reduce and derive the pooled mean / R-hat / ESS that ArviZ's az.summary reports in the reference
+ * (run_age_mcmc.py:234, noble_gas_mcmc.py:450) -- see noblegas_rtd_mcmc_b200/distributed.py:pooled_summary. */
+int ngrtd_sampler_pooled_moments(ngrtd_sampler* s, double* out_d, void* stream);
 int ngrtd_sampler_set_counters(ngrtd_sampler* s, int64_t step, int64_t ndraws, int64_t hist_start);
 int ngrtd_sampler_info(const ngrtd_sampler* s, int64_t* step, int64_t* ndraws, int64_t* hist_start);
 int ngrtd_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);   /* known-answer hook */

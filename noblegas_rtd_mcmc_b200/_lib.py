@@ -13,8 +13,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NGRTD_LIB", os.path.join(_HERE, "libngrtd.so"))
 
 MOD = {"piston": 1, "exponential": 2, "exp_pist_flow": 3, "dispersion": 4}
+# "f1_f2c": one column that is f1 and makes f2 = 1 - f1 on the device (NGRTD_P_F1_COMPLEMENT; the reference's model has
+# f2 = Deterministic(1 - f1), run_age_mcmc_utils.py:304) -- for batched callers that want to drop the redundant column
 SLOT = {"tau1": 0, "tau2": 1, "f1": 2, "f2": 3, "eta1": 4, "eta2": 5, "D1": 6, "D2": 7, "J": 8,
-        "thalf_cfc": 9, "lamsf6": 10}
+        "thalf_cfc": 9, "lamsf6": 10, "f1_f2c": 11}
 ACC = {False: 0, None: 0, "3He": 1, "4He": 2}
 GAS = {"He": 0, "Ne": 1, "Ar": 2, "Kr": 3, "Xe": 4}
 LIK = {"normal": 0, "studentt": 1}
@@ -88,6 +90,7 @@ _PROTOS = {
     "ngrtd_sampler_get": ([_vp, _i32, _vp, _vp], ctypes.c_int),
     "ngrtd_sampler_set": ([_vp, _i32, _vp, _vp], ctypes.c_int),
     "ngrtd_sampler_set_counters": ([_vp, _i64, _i64, _i64], ctypes.c_int),
+    "ngrtd_sampler_pooled_moments": ([_vp, _vp, _vp], ctypes.c_int),
     "ngrtd_sampler_info": ([_vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64), ctypes.POINTER(_i64)], ctypes.c_int),
     "ngrtd_philox4x32_10": ([_vp, _vp, _vp], ctypes.c_int),
 }

@@ -29,6 +29,31 @@ static int fail(int code, const std::string& msg) {
         if (e__ != cudaSuccess)                                                                       \
             return fail(NGRTD_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e__));               \
     } while (0)
+// same, releasing a half-built object first (create paths)
+#define CUDA_TRY_OR(x, cleanup)                                                                       \
+    do {                                                                                              \
+        cudaError_t e__ = (x);                                                                        \
+        if (e__ != cudaSuccess) {                                                                     \
+            cleanup;                                                                                  \
+            return fail(NGRTD_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e__));               \
+        }                                                                                             \
+    } while (0)
+
+// Entry points that launch or copy run on the device their plan / sampler lives on and leave the caller's current
+// device as they found it (one thread may drive objects on several GPUs).
+struct DeviceGuard {
+    int prev = -1;
+    bool good = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; good = false; return; }
+        if (prev != dev) good = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+    bool ok() const { return good; }
+};
 
 constexpr int HOST_PARTS_MAX = 8;
 #ifndef NGRTD_STAGE_DEFAULT
@@ -73,9 +98,7 @@ static int cls_of(int mod) {
 extern "C" int ngrtd_version(void) { return NGRTD_VERSION; }
 extern "C" int ngrtd_build_features(void) {
     int f = 0;
-#ifdef NGRTD_DM_TAIL
-    f |= NGRTD_FEATURE_DM_TAIL;
-#endif
+    if (DM_TAIL) f |= NGRTD_FEATURE_DM_TAIL;
 #ifdef NGRTD_XF_SWIZZLE
     f |= NGRTD_FEATURE_XF_SWIZZLE;
 #endif
@@ -104,13 +127,14 @@ extern "C" int ngrtd_plan_create(ngrtd_plan** out, int32_t L, int32_t nseries, c
     if (c1 <= 0) return fail(NGRTD_EINVAL, "plan: unknown mod_type1 " + std::to_string(mod_type1));
     if (c2 < 0) return fail(NGRTD_EINVAL, "plan: unknown mod_type2 " + std::to_string(mod_type2));
     if (dtp != std::floor(dtp)) return fail(NGRTD_EINVAL, "plan: dtp must be integer valued (np.floor in the reference)");
-    if (device >= 0) CUDA_TRY(cudaSetDevice(device));
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
+    int dev = device;
+    if (dev < 0) CUDA_TRY(cudaGetDevice(&dev));
+    DeviceGuard guard(dev);                 // the caller's current device is restored on return
+    if (!guard.ok()) return fail(NGRTD_ECUDA, "plan: cudaSetDevice(" + std::to_string(dev) + ") failed");
 
     auto* P = new ngrtd_plan();
     P->device = dev;
-    CUDA_TRY(cudaDeviceGetAttribute(&P->nsm, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY_OR(cudaDeviceGetAttribute(&P->nsm, cudaDevAttrMultiProcessorCount, dev), delete P);
     P->L = L;
     P->Lpad = (L + 3) & ~3;
     P->mod1 = mod_type1;
@@ -202,8 +226,8 @@ extern "C" int ngrtd_plan_create(ngrtd_plan** out, int32_t L, int32_t nseries, c
         pv.dyn_bg = 0.0;
         for (int c = 0; c < NCOL; c++) pv.ct[c] = ColTail{-1, 0.0, 0.0, 0.0, 0.0};
         const bool any_d = c1 == CLS_D || c2 == CLS_D, any_g = c1 == CLS_G || c2 == CLS_G;
-        // dispersion components: only in NGRTD_DM_TAIL builds, and not together with a per-chain decay constant (thalf_cfc)
-        const bool want = getenv("NGRTD_NO_TAIL") == nullptr && (any_d ? (DM_TAIL && !P->dyn) : any_g);
+        // dispersion components: by quadrature (DM_TAIL builds, the default)
+        const bool want = getenv("NGRTD_NO_TAIL") == nullptr && (any_d ? DM_TAIL : any_g);
         if (want && L >= 64) {
             int kvar = 0;                                       // first lag from which every used series is constant
             auto scan = [&](int sidx) {
@@ -229,6 +253,10 @@ extern "C" int ngrtd_plan_create(ngrtd_plan** out, int32_t L, int32_t nseries, c
             }
             if (P->dyn && dyn_series >= 0) scan(dyn_series);
             int Kc = std::max(4, (kvar + 3) & ~3);
+            // dispersion tails are integrated by quadrature with Euler-Maclaurin end terms, validated (profiles/
+            // r1_dm_tail_quadrature_study.txt) for a cut at lag >= 128: closer to lag 0 the weight t^-1.5 exp(-a/t - c t)
+            // varies too fast across one lag for the end correction (2e-8 at Kc = 4, tau = 37.5, D = 0.3)
+            if (any_d) Kc = std::max(Kc, 128);
             if (ok && Kc + 32 <= L) {                           // a tail worth cutting
                 pv.Kc = Kc;
                 pv.ct[0] = ColTail{0, 1.0, 0.0, 0.0, 0.0};
@@ -496,8 +524,17 @@ static int make_slotmap(SlotMap& sm, int ndim, const int32_t* slot_of_col, bool 
     if (ndim < 1 || ndim > 32 || !slot_of_col) return fail(NGRTD_EINVAL, "theta: ndim must be in 1..32 with a slot map");
     sm.ndim = ndim;
     for (int s = 0; s < NSLOT; s++) sm.col_of_slot[s] = -1;
+    sm.f2_complement = 0;
     for (int i = 0; i < ndim; i++) {
         int s = slot_of_col[i];
+        if (s == NGRTD_P_F1_COMPLEMENT) {           // f1 column that also defines f2 = 1 - f1
+            if (sm.col_of_slot[NGRTD_P_F1] >= 0 || sm.col_of_slot[NGRTD_P_F2] >= 0 || sm.f2_complement)
+                return fail(NGRTD_EINVAL, "theta: the f1-complement column excludes f1 / f2 columns");
+            sm.f2_complement = 1;
+            s = NGRTD_P_F1;
+        } else if (s == NGRTD_P_F1 || s == NGRTD_P_F2) {
+            if (sm.f2_complement) return fail(NGRTD_EINVAL, "theta: the f1-complement column excludes f1 / f2 columns");
+        }
         if (s < 0 || s >= NSLOT) return fail(NGRTD_EINVAL, "theta: unknown parameter slot " + std::to_string(s));
         sm.col_of_slot[s] = (signed char)i;
     }
@@ -512,6 +549,8 @@ static int forward_common(ngrtd_plan* P, const double* theta, long long B, int n
     if (B < 0) return fail(NGRTD_EINVAL, "B < 0");
     if (B == 0) return NGRTD_OK;
     if (!theta) return fail(NGRTD_EINVAL, "theta is null");
+    DeviceGuard guard(P->device);          // launch on the plan's device whatever the caller's current device is
+    if (!guard.ok()) return fail(NGRTD_ECUDA, "forward: cudaSetDevice(plan device) failed");
     SlotMap sm;
     int rc = make_slotmap(sm, ndim, slot_of_col, P->dyn);
     if (rc) return rc;
@@ -609,7 +648,8 @@ static int forward_host_common(ngrtd_plan* P, const double* theta_h, int64_t B, 
     if (!P) return fail(NGRTD_EINVAL, "null plan");
     if (!theta_h) return fail(NGRTD_EINVAL, "null host buffer");
     if (B <= 0) return B == 0 ? NGRTD_OK : fail(NGRTD_EINVAL, "B < 0");
-    CUDA_TRY(cudaSetDevice(P->device));
+    DeviceGuard guard(P->device);
+    if (!guard.ok()) return fail(NGRTD_ECUDA, "cudaSetDevice(plan device) failed");
     const int nt = P->pv.ntracer;
     int rc;
     const bool need_nu = want_lik && lik_kind == NGRTD_LIK_STUDENTT;
@@ -704,7 +744,8 @@ extern "C" int ngrtd_forward_loglik_host_submit(ngrtd_plan* P, const double* the
     if (B == 0) return NGRTD_OK;
     const bool need_nu = lik_kind == NGRTD_LIK_STUDENTT;
     if (need_nu && !nu_h) return fail(NGRTD_EINVAL, "student-t needs nu");
-    CUDA_TRY(cudaSetDevice(P->device));
+    DeviceGuard guard(P->device);
+    if (!guard.ok()) return fail(NGRTD_ECUDA, "cudaSetDevice(plan device) failed");
     const int nt = P->pv.ntracer;
     int rc;
     if ((rc = grow(&sl.theta, &sl.theta_n, (size_t)B * ndim))) return rc;
@@ -718,7 +759,10 @@ extern "C" int ngrtd_forward_loglik_host_submit(ngrtd_plan* P, const double* the
     CUDA_TRY(cudaStreamWaitEvent(s_k, sl.ev_in, 0));
     rc = ngrtd_forward_loglik_dev(P, sl.theta, B, ndim, slot_of_col, lik_kind, obs_mu, obs_sd, need_nu ? sl.nu : nullptr,
                                   sl.logp, model_out_h ? sl.out : nullptr, s_k);
-    if (rc) return rc;
+    if (rc) {                                   // the copy-in is already enqueued on the caller's buffers: drain it
+        cudaStreamSynchronize(s_in);
+        return rc;
+    }
     CUDA_TRY(cudaEventRecord(sl.ev_k, s_k));
     CUDA_TRY(cudaStreamWaitEvent(s_out, sl.ev_k, 0));
     CUDA_TRY(cudaMemcpyAsync(logp_h, sl.logp, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, s_out));
@@ -734,6 +778,7 @@ extern "C" int ngrtd_host_wait(ngrtd_plan* P, int32_t slot) {
     if (slot < 0 || slot >= NGRTD_HOST_SLOTS) return fail(NGRTD_EINVAL, "wait: slot out of range");
     auto& sl = P->slots[slot];
     if (!sl.busy) return NGRTD_OK;
+    DeviceGuard guard(P->device);
     sl.busy = false;
     CUDA_TRY(cudaEventSynchronize(sl.ev_done));
     return NGRTD_OK;
@@ -1159,6 +1204,7 @@ struct ngrtd_sampler {
     long long step = 0, ndraws = 0, hist_start = 0;
     size_t n_q = 0;
     double* d_groups = nullptr;     // [3, G, ntr]: obs, 1/sd, likelihood constant
+    double* d_pool = nullptr;       // workspace of ngrtd_sampler_pooled_moments
 };
 
 static double lbeta(double a, double b) { return std::lgamma(a) + std::lgamma(b) - std::lgamma(a + b); }
@@ -1244,7 +1290,7 @@ extern "C" int ngrtd_sampler_destroy(ngrtd_sampler* S) {
     if (!S) return NGRTD_OK;
     SamplerView& v = S->sv;
     cudaFree(v.q); cudaFree(v.logp); cudaFree(v.lamb); cudaFree(v.scal); cudaFree(v.acc_win); cudaFree(v.acc_tot);
-    cudaFree(v.hist); cudaFree(v.wf_mean); cudaFree(v.wf_m2); cudaFree(S->d_groups);
+    cudaFree(v.hist); cudaFree(v.wf_mean); cudaFree(v.wf_m2); cudaFree(S->d_groups); cudaFree(S->d_pool);
     delete S;
     return NGRTD_OK;
 }
@@ -1261,10 +1307,12 @@ extern "C" int ngrtd_sampler_create(ngrtd_sampler** out, const ngrtd_sampler_cfg
     if (cfg->nobs < 1 || cfg->nobs > MAX_TRACER) return fail(NGRTD_EINVAL, "sampler: nobs must be in 1..8");
     if (plan && cfg->nobs != plan->pv.ntracer) return fail(NGRTD_EINVAL, "sampler: nobs must equal the plan's tracer count");
     if (!plan && (cfg->ngas < 1 || cfg->ngas > 5 || cfg->ngas != cfg->nobs)) return fail(NGRTD_EINVAL, "sampler: noble-gas model needs 1..5 gases = nobs");
-    if (plan) CUDA_TRY(cudaSetDevice(plan->device));
-    else if (device >= 0) CUDA_TRY(cudaSetDevice(device));
+    int sdev = plan ? plan->device : device;
+    if (sdev < 0) CUDA_TRY(cudaGetDevice(&sdev));
+    DeviceGuard guard(sdev);                // the caller's current device is restored on return
+    if (!guard.ok()) return fail(NGRTD_ECUDA, "sampler: cudaSetDevice(" + std::to_string(sdev) + ") failed");
     auto* S = new ngrtd_sampler();
-    CUDA_TRY(cudaGetDevice(&S->device));
+    S->device = sdev;
     S->plan = plan;
     S->tune_drop_fraction = cfg->tune_drop_fraction;
     SamplerView& v = S->sv;
@@ -1342,7 +1390,7 @@ extern "C" int ngrtd_sampler_create(ngrtd_sampler** out, const ngrtd_sampler_cfg
     S->n_q = B * nd;
     size_t hist_bytes = (size_t)cfg->hist_cap * B * nd * sizeof(double);
     size_t free_b = 0, total_b = 0;
-    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    CUDA_TRY_OR(cudaMemGetInfo(&free_b, &total_b), delete S);
     if (hist_bytes > free_b / 2) {
         delete S;
         return fail(NGRTD_ENOMEM, "sampler: history ring (" + std::to_string(hist_bytes >> 20) + " MiB) exceeds half of free device memory; lower hist_cap");
@@ -1359,14 +1407,14 @@ extern "C" int ngrtd_sampler_create(ngrtd_sampler** out, const ngrtd_sampler_cfg
     {
         std::vector<double> hq(B * nd), hl(B, cfg->lamb > 0 ? cfg->lamb : 2.38 / std::sqrt(2.0 * cfg->ndim)), hs(B, cfg->scaling);
         for (size_t b = 0; b < B; b++) for (size_t d = 0; d < nd; d++) hq[b * nd + d] = start[d];
-        CUDA_TRY(cudaMemcpy(v.q, hq.data(), B * nd * 8, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(v.lamb, hl.data(), B * 8, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(v.scal, hs.data(), B * 8, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemset(v.logp, 0, B * 8));
-        CUDA_TRY(cudaMemset(v.acc_win, 0, B * 4));
-        CUDA_TRY(cudaMemset(v.acc_tot, 0, B * 8));
-        CUDA_TRY(cudaMemset(v.wf_mean, 0, B * nd * 8));
-        CUDA_TRY(cudaMemset(v.wf_m2, 0, B * nd * 8));
+        CUDA_TRY_OR(cudaMemcpy(v.q, hq.data(), B * nd * 8, cudaMemcpyHostToDevice), ngrtd_sampler_destroy(S));
+        CUDA_TRY_OR(cudaMemcpy(v.lamb, hl.data(), B * 8, cudaMemcpyHostToDevice), ngrtd_sampler_destroy(S));
+        CUDA_TRY_OR(cudaMemcpy(v.scal, hs.data(), B * 8, cudaMemcpyHostToDevice), ngrtd_sampler_destroy(S));
+        CUDA_TRY_OR(cudaMemset(v.logp, 0, B * 8), ngrtd_sampler_destroy(S));
+        CUDA_TRY_OR(cudaMemset(v.acc_win, 0, B * 4), ngrtd_sampler_destroy(S));
+        CUDA_TRY_OR(cudaMemset(v.acc_tot, 0, B * 8), ngrtd_sampler_destroy(S));
+        CUDA_TRY_OR(cudaMemset(v.wf_mean, 0, B * nd * 8), ngrtd_sampler_destroy(S));
+        CUDA_TRY_OR(cudaMemset(v.wf_m2, 0, B * nd * 8), ngrtd_sampler_destroy(S));
     }
     RunArgs ra{};
     ra.mode = 1;                    // logp of the starting point
@@ -1386,6 +1434,8 @@ extern "C" int ngrtd_sampler_create(ngrtd_sampler** out, const ngrtd_sampler_cfg
 extern "C" int ngrtd_sampler_set_obs_groups(ngrtd_sampler* S, const double* obs_mu, const double* obs_sd, int64_t ngroups,
                                             int64_t chains_per_group) {
     if (!S || !obs_mu || !obs_sd) return fail(NGRTD_EINVAL, "obs_groups: null pointer");
+    DeviceGuard guard(S->device);
+    if (!guard.ok()) return fail(NGRTD_ECUDA, "ngrtd_sampler_set_obs_groups: cudaSetDevice(sampler device) failed");
     if (ngroups < 1 || chains_per_group < 1) return fail(NGRTD_EINVAL, "obs_groups: need ngroups, chains_per_group >= 1");
     SamplerView& v = S->sv;
     if ((v.chain_offset + v.B + chains_per_group - 1) / chains_per_group > ngroups)
@@ -1398,7 +1448,6 @@ extern "C" int ngrtd_sampler_set_obs_groups(ngrtd_sampler* S, const double* obs_
         h[n + i] = 1.0 / sd;
         h[2 * n + i] = v.lik_kind == NGRTD_LIK_NORMAL ? -0.5 * std::log(2.0 * M_PI * sd * sd) : -std::log(sd);
     }
-    CUDA_TRY(cudaSetDevice(S->device));
     cudaFree(S->d_groups);
     S->d_groups = nullptr;
     CUDA_TRY(cudaMalloc((void**)&S->d_groups, 3 * n * sizeof(double)));
@@ -1418,6 +1467,8 @@ extern "C" int ngrtd_sampler_set_obs_groups(ngrtd_sampler* S, const double* obs_
 extern "C" int ngrtd_sampler_run(ngrtd_sampler* S, int64_t nsteps, int32_t tune, int32_t record, int32_t thin,
                                  double* trace_d, void* stream) {
     if (!S) return fail(NGRTD_EINVAL, "null sampler");
+    DeviceGuard guard(S->device);
+    if (!guard.ok()) return fail(NGRTD_ECUDA, "ngrtd_sampler_run: cudaSetDevice(sampler device) failed");
     if (nsteps < 0 || nsteps > 2000000000LL) return fail(NGRTD_EINVAL, "sampler: bad nsteps");
     if (nsteps == 0) return NGRTD_OK;
     if (thin < 1) return fail(NGRTD_EINVAL, "sampler: thin must be >= 1");
@@ -1440,6 +1491,8 @@ extern "C" int ngrtd_sampler_run(ngrtd_sampler* S, int64_t nsteps, int32_t tune,
 
 extern "C" int ngrtd_sampler_stop_tuning(ngrtd_sampler* S) {
     if (!S) return fail(NGRTD_EINVAL, "null sampler");
+    DeviceGuard guard(S->device);
+    if (!guard.ok()) return fail(NGRTD_ECUDA, "ngrtd_sampler_stop_tuning: cudaSetDevice(sampler device) failed");
     long long it = S->step - S->hist_start;              // len(self._history)
     long long n_drop = (long long)(S->tune_drop_fraction * (double)it);
     S->hist_start += n_drop;
@@ -1456,6 +1509,8 @@ extern "C" int ngrtd_sampler_info(const ngrtd_sampler* S, int64_t* step, int64_t
 
 extern "C" int ngrtd_sampler_set_counters(ngrtd_sampler* S, int64_t step, int64_t ndraws, int64_t hist_start) {
     if (!S) return fail(NGRTD_EINVAL, "null sampler");
+    DeviceGuard guard(S->device);
+    if (!guard.ok()) return fail(NGRTD_ECUDA, "ngrtd_sampler_set_counters: cudaSetDevice(sampler device) failed");
     if (step < 0 || ndraws < 0 || hist_start < 0 || hist_start > step) return fail(NGRTD_EINVAL, "sampler_set_counters: bad counters");
     S->step = step;
     S->ndraws = ndraws;
@@ -1475,6 +1530,8 @@ __global__ void k_int_to_double(const int* a, const long long* b, long long n, d
 
 extern "C" int ngrtd_sampler_get(ngrtd_sampler* S, int32_t what, double* out_d, void* stream) {
     if (!S || !out_d) return fail(NGRTD_EINVAL, "sampler_get: null pointer");
+    DeviceGuard guard(S->device);
+    if (!guard.ok()) return fail(NGRTD_ECUDA, "ngrtd_sampler_get: cudaSetDevice(sampler device) failed");
     cudaStream_t st = (cudaStream_t)stream;
     const SamplerView& v = S->sv;
     size_t B = (size_t)v.B;
@@ -1500,8 +1557,70 @@ extern "C" int ngrtd_sampler_get(ngrtd_sampler* S, int32_t what, double* out_d, 
     return NGRTD_OK;
 }
 
+// ---- K6: pooled moments on the device.  Stage 1: every block sums its slice of chains for the 3*nd quantities (fixed
+// chain -> block -> thread assignment and a fixed tree, so the result is deterministic); stage 2: one block folds the
+// block partials.  POOL_BLOCKS * 3 * ND_MAX doubles of workspace live in the sampler object.
+constexpr int POOL_BLOCKS = 296, POOL_THREADS = 256;
+__global__ void __launch_bounds__(POOL_THREADS) k_pool_stage1(const double* __restrict__ mean, const double* __restrict__ m2,
+                                                              long long B, int nd, double* __restrict__ part) {
+    __shared__ double red[POOL_THREADS / 32][3 * ND_MAX];
+    double acc[3 * ND_MAX];
+#pragma unroll
+    for (int i = 0; i < 3 * ND_MAX; i++) acc[i] = 0.0;
+    const long long per = (B + gridDim.x - 1) / gridDim.x;
+    const long long c0 = (long long)blockIdx.x * per, c1 = min(B, c0 + per);
+    for (long long c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
+#pragma unroll
+        for (int d = 0; d < ND_MAX; d++) {
+            if (d < nd) {
+                const double m = mean[c * nd + d];
+                acc[d] += m;
+                acc[ND_MAX + d] = fma(m, m, acc[ND_MAX + d]);
+                acc[2 * ND_MAX + d] += m2[c * nd + d];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3 * ND_MAX; i++) {
+        double v = acc[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * ND_MAX) {
+        double v = 0.0;
+        for (int w = 0; w < POOL_THREADS / 32; w++) v += red[w][threadIdx.x];
+        part[(size_t)blockIdx.x * 3 * ND_MAX + threadIdx.x] = v;
+    }
+}
+__global__ void k_pool_stage2(const double* __restrict__ part, int nblocks, int nd, long long B, double* __restrict__ out) {
+    const int i = threadIdx.x;           // one thread per (quantity, dimension)
+    if (i < 3 * ND_MAX) {
+        double v = 0.0;
+        for (int b = 0; b < nblocks; b++) v += part[(size_t)b * 3 * ND_MAX + i];
+        const int q = i / ND_MAX, d = i % ND_MAX;
+        if (d < nd) out[q * nd + d] = v;
+    }
+    if (i == 0) out[3 * nd] = (double)B;
+}
+
+extern "C" int ngrtd_sampler_pooled_moments(ngrtd_sampler* S, double* out_d, void* stream) {
+    if (!S || !out_d) return fail(NGRTD_EINVAL, "pooled_moments: null pointer");
+    DeviceGuard guard(S->device);
+    if (!guard.ok()) return fail(NGRTD_ECUDA, "pooled_moments: cudaSetDevice failed");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!S->d_pool) CUDA_TRY(cudaMalloc((void**)&S->d_pool, sizeof(double) * POOL_BLOCKS * 3 * ND_MAX));
+    const SamplerView& v = S->sv;
+    k_pool_stage1<<<POOL_BLOCKS, POOL_THREADS, 0, st>>>(v.wf_mean, v.wf_m2, v.B, v.nd, S->d_pool);
+    k_pool_stage2<<<1, 32, 0, st>>>(S->d_pool, POOL_BLOCKS, v.nd, v.B, out_d);
+    CUDA_TRY(cudaGetLastError());
+    return NGRTD_OK;
+}
+
 extern "C" int ngrtd_sampler_set(ngrtd_sampler* S, int32_t what, const double* in_d, void* stream) {
     if (!S || !in_d) return fail(NGRTD_EINVAL, "sampler_set: null pointer");
+    DeviceGuard guard(S->device);
+    if (!guard.ok()) return fail(NGRTD_ECUDA, "ngrtd_sampler_set: cudaSetDevice(sampler device) failed");
     cudaStream_t st = (cudaStream_t)stream;
     SamplerView& v = S->sv;
     double* dst = nullptr;

@@ -120,14 +120,14 @@ struct PlanView {
     double tpl, itpl;               // last lag of the grid, tp[L-1], and its reciprocal (dispersion dead-chain rule)
 };
 
-// Which plans cut the lag loop at Kc and add the tail [Kc, L) analytically in the epilogue: exponential-class components always
-// (closed form); dispersion components only in -DNGRTD_DM_TAIL builds (Gauss-Legendre quadrature of the smooth tail,
-// WarpTiles::dm_tail in ngrtd_forward.cuh; experimental in r1, see profiles/r1_notes.md).  Plan creation leaves Kc = Lpad when
-// the plan does not qualify.
-#ifdef NGRTD_DM_TAIL
-constexpr bool DM_TAIL = true;
-#else
+// Which plans cut the lag loop at Kc and add the tail [Kc, L) analytically in the epilogue: exponential-class components by
+// closed form, dispersion components by Gauss-Legendre quadrature of the smooth tail (WarpTiles::dm_tail in
+// ngrtd_forward.cuh; opt-in experiment in r1, the default since r2 -- -DNGRTD_NO_DM_TAIL builds keep the full lag loop for
+// dispersion plans, for A/B measurements).  Plan creation leaves Kc = Lpad when the plan does not qualify.
+#ifdef NGRTD_NO_DM_TAIL
 constexpr bool DM_TAIL = false;
+#else
+constexpr bool DM_TAIL = true;
 #endif
 __host__ __device__ __forceinline__ bool tail_active(const PlanView& pv, bool any_g, bool any_d) {
     return (any_g || any_d) && (!any_d || DM_TAIL) && pv.Kc < pv.L;
@@ -136,6 +136,7 @@ __host__ __device__ __forceinline__ bool tail_active(const PlanView& pv, bool an
 struct SlotMap {
     int ndim;
     signed char col_of_slot[NSLOT];   // -1: not in par_names -> p_dict default
+    signed char f2_complement;        // 1: f2 = 1 - f1 (NGRTD_P_F1_COMPLEMENT column)
 };
 
 struct ChainPar {
@@ -153,7 +154,7 @@ __device__ __forceinline__ ChainPar load_chain_par(const double* __restrict__ th
     p.tau1 = get(0, 0.0);
     p.tau2 = get(1, 0.0);     // p_dict default 0.0
     p.f1 = get(2, 1.0);       // default 1.0
-    p.f2 = get(3, 0.0);       // default 0.0
+    p.f2 = sm.f2_complement ? 1.0 - p.f1 : get(3, 0.0);       // default 0.0
     p.eta1 = pv.eta1_is_one ? 1.0 : get(4, 0.0);
     p.eta2 = pv.eta2_is_one ? 1.0 : get(5, 0.0);
     p.D1 = get(6, 0.0);

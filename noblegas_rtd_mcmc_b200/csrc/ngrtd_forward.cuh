@@ -41,6 +41,7 @@ struct SmemView {
     int part;      // tape schedule: [warps][NT * NPART][32 lanes] accumulators of partial lag ranges
     int flag;      // tape schedule: [warps] int, 1 = the warp's partial is published
     int park;      // PK: [warps][NT][8 chains][PARK_DOUBLES] epilogue-only values parked across the lag loop
+    int ctab;      // CT_DOUBLES column descriptors of the analytic tail (dm_tail)
 };
 
 struct LikPar {
@@ -140,17 +141,19 @@ struct CompD {
         ap = -K * tau * i4D;
         bp = bq;
         cp = K * 2.0 * i4D;
-        if (ok) {
-            // Largest exponent over the lag grid: e(tp) is unimodal with its maximum (0) at tp = tau, so the discrete
-            // maximum sits at one of the two grid lags around tau (the last lag when tau lies beyond the grid).
-            // tp_k = k + dtp (tp_0 = 1e-5 + dtp); pv.itp holds the same {1/tp, tp} pairs the lag loop reads.
+        // Dead-chain rule: below 2^-1022 every reference weight is (sub)denormal or exactly zero and g/g.sum() is NaN or
+        // precision-less -> the chain is declared dead (NaN output) when the LARGEST exponent over the lag grid is below the
+        // clamp.  e(tp) is unimodal with its maximum (0) at tp = tau, so the discrete maximum sits at one of the two grid
+        // lags around tau (the last lag when tau lies beyond the grid).  Fast path: for 1 <= tau <= tp[L-1] a grid lag lies
+        // within 1/2 of tau, where e >= -(1/4D) * 0.25 / (tau (tau - 1/2)); only chains that fail this bound (or lie
+        // outside the grid) evaluate the two candidate lags (pv.itp holds the {1/tp, tp} pairs the lag loop reads).
+        if (ok && !(tau >= 1.0 + pv.dtp && tau <= pv.tpl &&
+                    K * i4D * 0.25 < -(double)exp_clamp<TB>() * (tau * (tau - 0.5)))) {
             const double s = fmin(fmax(floor(tau - pv.dtp), 0.0), (double)(pv.L - 1));
             const int ka = (int)s, kb = min(ka + 1, pv.L - 1);
             const double2 ia = *reinterpret_cast<const double2*>(pv.itp + 2 * ka);
             const double2 ib = *reinterpret_cast<const double2*>(pv.itp + 2 * kb);
             const double emax = fmax(fma(ap, ia.x, fma(bp, ia.y, cp)), fma(ap, ib.x, fma(bp, ib.y, cp)));
-            // Below 2^-1022 every reference weight is (sub)denormal or exactly zero and g/g.sum() is NaN or
-            // precision-less: the chain is declared dead -> NaN output.
             ok = emax >= (double)exp_clamp<TB>();
         }
         cp += FX_MAGIC;     // exp_scaled_bits takes ep + FX_MAGIC: folded into the constant term
@@ -166,7 +169,7 @@ struct CompSel { using type = Comp<CLS>; };
 template <int TB>
 struct CompSel<CLS_D, TB> { using type = CompD<TB>; };
 
-// order-16 Gauss-Legendre nodes / weights on [-1, 1] (positive half) for WarpTiles::dm_tail
+// order-16 Gauss-Legendre nodes / weights on [-1, 1] (positive half) for dm_tail
 __constant__ double DM_GX[8] = {0.095012509837637441, 0.28160355077925892, 0.45801677765722737, 0.61787624440264377,
                                 0.755404408355003, 0.86563120238783176, 0.9445750230732326, 0.98940093499164994};
 __constant__ double DM_GW[8] = {0.18945061045506864, 0.18260341504492364, 0.16915651939500265, 0.14959598881657671,
@@ -201,6 +204,162 @@ __device__ __forceinline__ double col_tail(const ColTail& ct, double er, double 
     return Wa * Da * ((ct.i0 + ct.s * a) * g0l + ct.s * geo_sum1(er + ct.lam, n));
 }
 
+// ---------------------------------------------------------------- dispersion tail by quadrature (out of line)
+// Beyond Kc every folded column is an analytic function of the lag (PlanView::ct), so
+//   sum_{k=Kc}^{L-1} w(tp_k) col(tp_k),   w(t) = t^-1.5 exp(-(t - tau)^2 / (4 D tau t))   (the loop's weight incl. Xd's t^-1.5)
+// equals the integral over [tp_Kc - 1/2, tp_{L-1} + 1/2] minus the midpoint Euler-Maclaurin end terms g1/24 - 7 g3/5760
+// (g1, g3: first and third derivative; the interior error is exponentially small for peaks wider than ~2 lags).
+// Order-16 Gauss-Legendre panels, 2 per sigma = tau sqrt(2D) near the mode, widening geometrically away from it and never
+// wider than 0.35 t; the 4 lanes of a chain take 4 of the 16 nodes of every panel and all 8 columns, partial sums are
+// combined by shuffles.  tools/dm_tail_prototype.py is the float64 prototype (8e-15 against the reference's golden vectors).
+// Outside the validated domain (D outside [0.01, 2.5], mode more than 12 sigma beyond the last lag) the same analytic
+// terms are summed lag by lag.
+// r2: a __noinline__ function shared by every kernel (r1 inlined it per tile and component: 3x the code of the headline
+// kernel and extra register pressure around the lag loop).  It reads the column descriptors from a 48-double table that
+// FwdCta::setup copies into shared memory (a reference to the kernel-parameter struct would force a local-memory copy).
+constexpr int CT_DOUBLES = 48;      // [8 columns][type, bg, lam, i0, s] + {Kc, L, dtp, dyn_bg}
+struct CtView {
+    const double* t;
+    __device__ __forceinline__ int type(int c) const { return (int)t[c * 5]; }
+    __device__ __forceinline__ double bg(int c) const { return t[c * 5 + 1]; }
+    __device__ __forceinline__ double lam(int c) const { return t[c * 5 + 2]; }
+    __device__ __forceinline__ double i0(int c) const { return t[c * 5 + 3]; }
+    __device__ __forceinline__ double s(int c) const { return t[c * 5 + 4]; }
+    __device__ __forceinline__ double Kc() const { return t[40]; }
+    __device__ __forceinline__ double L() const { return t[41]; }
+    __device__ __forceinline__ double dtp() const { return t[42]; }
+    __device__ __forceinline__ double dyn_bg() const { return t[43]; }
+};
+__device__ __forceinline__ void ct_fill(double* tab, const PlanView& pv, int tid) {
+    if (tid < NCOL) {
+        const ColTail c = pv.ct[tid];
+        tab[tid * 5] = (double)c.type; tab[tid * 5 + 1] = c.bg; tab[tid * 5 + 2] = c.lam; tab[tid * 5 + 3] = c.i0; tab[tid * 5 + 4] = c.s;
+    }
+    if (tid == NCOL) { tab[40] = (double)pv.Kc; tab[41] = (double)pv.L; tab[42] = pv.dtp; tab[43] = pv.dyn_bg; }
+}
+// lam_dyn / accd: per-chain decay constant (thalf_cfc) and the sum of its column dyn_bg * exp(-lam_dyn t) (DYN plans)
+template <bool DYN>
+__device__ __forceinline__ void dm_node(const CtView& cv, double t, double wt, double tau, double c4, double (&acc)[NCOL],
+                                        double lam_dyn, double& accd) {
+    const double dt = t - tau;
+    const double wgt = wt * exp(-dt * dt * c4 / t) / (t * sqrt(t));
+    acc[0] += wgt;
+    if constexpr (DYN) accd = fma(wgt, cv.dyn_bg() * exp(-lam_dyn * t), accd);
+    double last = 0.0, d = 1.0;
+#pragma unroll
+    for (int c = 1; c < NCOL; c++) {
+        const int ty = cv.type(c);
+        if (ty < 0) continue;
+        const double lam = cv.lam(c);
+        if (lam != last) { d = exp(-lam * t); last = lam; }
+        double v;
+        if (ty == 1) v = cv.bg(c) * d;
+        else if (ty == 2) v = cv.bg(c) * (1.0 - d);
+        else v = (cv.i0(c) + cv.s(c) * (t - cv.dtp())) * d;
+        acc[c] = fma(wgt, v, acc[c]);
+    }
+}
+// sgn * (g1/24 - 7 g3/5760) of every column at the end point t
+template <bool DYN>
+__device__ __forceinline__ void dm_end(const CtView& cv, double t, double sgn, double tau, double a, double c4,
+                                       double (&acc)[NCOL], double lam_dyn, double& accd) {
+    const double dt = t - tau, it = 1.0 / t;
+    const double w = exp(-dt * dt * c4 * it) * it / sqrt(t);
+    const double p1 = (1.5 - 2.0 * a * it) * it * it, p2 = (-3.0 + 6.0 * a * it) * it * it * it;
+    const double pb = (-1.5 + a * it) * it - c4;                  // log-derivative without the decay constant
+    auto terms = [&](double lam, double& g, double& g1, double& g2, double& g3) {
+        const double p = pb - lam;
+        g = w * exp(-lam * t);
+        g1 = g * p; g2 = g * (p * p + p1); g3 = g * (p * p * p + 3.0 * p * p1 + p2);
+    };
+    double g, g1, g2, g3;
+    terms(0.0, g, g1, g2, g3);
+    const double k1 = sgn / 24.0, k3 = -sgn * 7.0 / 5760.0;
+    acc[0] += k1 * g1 + k3 * g3;
+    if constexpr (DYN) {
+        double h, h1, h2, h3;
+        terms(lam_dyn, h, h1, h2, h3);
+        accd += cv.dyn_bg() * (k1 * h1 + k3 * h3);
+    }
+#pragma unroll 1
+    for (int c = 1; c < NCOL; c++) {
+        const int ty = cv.type(c);
+        if (ty < 0) continue;
+        double h, h1, h2, h3;
+        terms(cv.lam(c), h, h1, h2, h3);
+        if (ty == 1) acc[c] += cv.bg(c) * (k1 * h1 + k3 * h3);
+        else if (ty == 2) acc[c] += cv.bg(c) * (k1 * (g1 - h1) + k3 * (g3 - h3));
+        else {
+            const double q = cv.i0(c) + cv.s(c) * (t - cv.dtp());
+            acc[c] += k1 * (cv.s(c) * h + q * h1) + k3 * (3.0 * cv.s(c) * h2 + q * h3);
+        }
+    }
+}
+// Tail sums of one dispersion component of one chain, computed by the chain's 4 lanes (j = lane & 3; every lane of the warp
+// calls).  res[0], res[1]: the tail of the lane's two output columns (2j, 2j+1); res[2]: the per-chain-decay column
+// (lane 0 of the chain carries the total, the others 0).  ct_off: offset of the CT_DOUBLES table in ngrtd_smem.
+template <bool DYN>
+__device__ __noinline__ void dm_tail(int ct_off, double tau, double D, int dead_j, double lam_dyn, double* res) {
+    const CtView cv{ngrtd_smem + ct_off};
+    const int j = dead_j & 3;
+    const bool dead = (dead_j >> 2) != 0;
+    double acc[NCOL];
+    double accd = 0.0;
+#pragma unroll
+    for (int c = 0; c < NCOL; c++) acc[c] = 0.0;
+    if (!dead) {
+        const double Kc = cv.Kc(), Ld = cv.L(), dtp = cv.dtp();
+        const double lo = Kc - 0.5 + dtp, hi = Ld - 0.5 + dtp;
+        const double c4 = 1.0 / (4.0 * D * tau), a = tau / (4.0 * D);
+        const double sig = fmax(tau * sqrt(2.0 * D), 1.0);
+        const bool quad = D >= 0.01 && D <= 2.5 && tau - 12.0 * sig <= hi;
+        if (quad) {
+            const double wlo = fmax(lo, tau - 12.0 * sig);
+            const double whi = fmin(hi, fmax(fmax(tau + 60.0 * sig, tau + 200.0 * D * tau), lo + 1.0));
+            if (whi > wlo) {
+                const double w = 0.5 * sig;
+                double x = wlo;
+                while (x < whi) {
+                    const double ad = fabs(x - tau);
+                    double step = (ad < 6.0 * sig) ? w : fmax(w, 0.25 * ad);
+                    step = fmin(step, 0.35 * x);
+                    const double x1 = fmin(whi, x + step);
+                    {   // the 4 lanes of the chain take 4 of the panel's 16 nodes each (no divergence inside a chain)
+                        const double mid = 0.5 * (x1 + x), half = 0.5 * (x1 - x);
+#pragma unroll 1
+                        for (int i = 0; i < 4; i++) {
+                            const int q = 4 * j + i;
+                            const double gx = (q & 1) ? -DM_GX[q >> 1] : DM_GX[q >> 1];
+                            dm_node<DYN>(cv, fma(half, gx, mid), half * DM_GW[q >> 1], tau, c4, acc, lam_dyn, accd);
+                        }
+                    }
+                    x = x1;
+                }
+                if (j == 0 && wlo == lo) dm_end<DYN>(cv, lo, 1.0, tau, a, c4, acc, lam_dyn, accd);
+                if (j == 1 && whi == hi) dm_end<DYN>(cv, hi, -1.0, tau, a, c4, acc, lam_dyn, accd);
+            }
+        } else {
+            const int k0 = (int)Kc, k1 = (int)Ld;
+#pragma unroll 1
+            for (int k = k0 + j; k < k1; k += 4) dm_node<DYN>(cv, (double)k + dtp, 1.0, tau, c4, acc, lam_dyn, accd);
+        }
+    }
+    const unsigned full = 0xffffffffu;
+#pragma unroll
+    for (int c = 0; c < NCOL; c++) {
+        acc[c] += __shfl_xor_sync(full, acc[c], 1);
+        acc[c] += __shfl_xor_sync(full, acc[c], 2);
+    }
+    res[0] = (j == 0) ? acc[0] : (j == 1) ? acc[2] : (j == 2) ? acc[4] : acc[6];
+    res[1] = (j == 0) ? acc[1] : (j == 1) ? acc[3] : (j == 2) ? acc[5] : acc[7];
+    res[2] = 0.0;
+    if constexpr (DYN) {          // the chain's 4 lanes are summed again in end(): hand the total to lane 0 only
+        accd += __shfl_xor_sync(full, accd, 1);
+        accd += __shfl_xor_sync(full, accd, 2);
+        if (j == 0) res[2] = accd;
+    }
+}
+
 // ---------------------------------------------------------------- one warp = NT tiles of 8 chains
 // TM: 1 = the analytic constant tail is decided at run time (PlanView::Kc), 0 = compiled out (k_forward instantiates both
 //     and the launcher picks: without the tail code the lag loop keeps fewer values alive and schedules tighter).
@@ -216,6 +375,7 @@ struct WarpTiles {
     static constexpr bool ANY_G = (C1 == CLS_G || C2 == CLS_G);
     static constexpr int TBITS = TB, NTILES = NT;
     static constexpr bool DYNAMIC = DYN, PARK = PK;
+    static constexpr int TAILMODE = TM;
 
     static constexpr double EXP_K = exp_k<TB>();
     // doubles per lane and tile that a partial lag range hands to the owner of its unit (tape schedule of k_forward)
@@ -472,118 +632,10 @@ struct WarpTiles {
         }
     }
 
-    // ---- dispersion tail (NGRTD_DM_TAIL builds) -------------------------------------------------------------------------
-    // Beyond Kc every folded column is an analytic function of the lag (PlanView::ct), so
-    //   sum_{k=Kc}^{L-1} w(tp_k) col(tp_k),   w(t) = t^-1.5 exp(-(t - tau)^2 / (4 D tau t))   (the loop's weight incl. Xd's t^-1.5)
-    // equals the integral over [tp_Kc - 1/2, tp_{L-1} + 1/2] minus the midpoint Euler-Maclaurin end terms g1/24 - 7 g3/5760
-    // (g1, g3: first and third derivative; the interior error is exponentially small for peaks wider than ~2 lags).
-    // Order-16 Gauss-Legendre panels, 2 per sigma = tau sqrt(2D) near the mode, widening geometrically away from it and
-    // never wider than 0.35 t; the 4 lanes of a chain take 4 of the 16 nodes of every panel and all 8 columns, partial sums are combined by
-    // shuffles.  tools/dm_tail_prototype.py is the float64 prototype (8e-15 against the reference's golden vectors).
-    // Outside the validated domain (D outside [0.01, 2.5], mode more than 12 sigma beyond the last lag) the same
-    // analytic terms are summed lag by lag.
-    __device__ __forceinline__ static void dm_node(const PlanView& pv, double t, double wt, double tau, double c4,
-                                                   double (&acc)[NCOL]) {
-        const double dt = t - tau;
-        const double wgt = wt * exp(-dt * dt * c4 / t) / (t * sqrt(t));
-        acc[0] += wgt;
-        double last = 0.0, d = 1.0;
-#pragma unroll
-        for (int c = 1; c < NCOL; c++) {
-            const ColTail ct = pv.ct[c];
-            if (ct.type < 0) continue;
-            if (ct.lam != last) { d = exp(-ct.lam * t); last = ct.lam; }
-            double v;
-            if (ct.type == 1) v = ct.bg * d;
-            else if (ct.type == 2) v = ct.bg * (1.0 - d);
-            else v = (ct.i0 + ct.s * (t - pv.dtp)) * d;
-            acc[c] = fma(wgt, v, acc[c]);
-        }
-    }
-    // sgn * (g1/24 - 7 g3/5760) of every column at the end point t
-    __device__ __forceinline__ static void dm_end(const PlanView& pv, double t, double sgn, double tau, double a, double c4,
-                                                  double (&acc)[NCOL]) {
-        const double dt = t - tau, it = 1.0 / t;
-        const double w = exp(-dt * dt * c4 * it) * it / sqrt(t);
-        const double p1 = (1.5 - 2.0 * a * it) * it * it, p2 = (-3.0 + 6.0 * a * it) * it * it * it;
-        const double pb = (-1.5 + a * it) * it - c4;                  // log-derivative without the decay constant
-        auto terms = [&](double lam, double& g, double& g1, double& g2, double& g3) {
-            const double p = pb - lam;
-            g = w * exp(-lam * t);
-            g1 = g * p; g2 = g * (p * p + p1); g3 = g * (p * p * p + 3.0 * p * p1 + p2);
-        };
-        double g, g1, g2, g3;
-        terms(0.0, g, g1, g2, g3);
-        const double k1 = sgn / 24.0, k3 = -sgn * 7.0 / 5760.0;
-        acc[0] += k1 * g1 + k3 * g3;
-#pragma unroll
-        for (int c = 1; c < NCOL; c++) {
-            const ColTail ct = pv.ct[c];
-            if (ct.type < 0) continue;
-            double h, h1, h2, h3;
-            terms(ct.lam, h, h1, h2, h3);
-            if (ct.type == 1) acc[c] += ct.bg * (k1 * h1 + k3 * h3);
-            else if (ct.type == 2) acc[c] += ct.bg * (k1 * (g1 - h1) + k3 * (g3 - h3));
-            else {
-                const double q = ct.i0 + ct.s * (t - pv.dtp);
-                acc[c] += k1 * (ct.s * h + q * h1) + k3 * (3.0 * ct.s * h2 + q * h3);
-            }
-        }
-    }
-    __device__ __forceinline__ static void dm_tail(const PlanView& pv, double tau, double D, bool dead, int j, double& o0,
-                                                   double& o1) {
-        double acc[NCOL];
-#pragma unroll
-        for (int c = 0; c < NCOL; c++) acc[c] = 0.0;
-        if (!dead) {
-            const double lo = (double)pv.Kc - 0.5 + pv.dtp, hi = (double)pv.L - 0.5 + pv.dtp;
-            const double c4 = 1.0 / (4.0 * D * tau), a = tau / (4.0 * D);
-            const double sig = fmax(tau * sqrt(2.0 * D), 1.0);
-            const bool quad = D >= 0.01 && D <= 2.5 && tau - 12.0 * sig <= hi;
-            if (quad) {
-                const double wlo = fmax(lo, tau - 12.0 * sig);
-                const double whi = fmin(hi, fmax(fmax(tau + 60.0 * sig, tau + 200.0 * D * tau), lo + 1.0));
-                if (whi > wlo) {
-                    const double w = 0.5 * sig;
-                    double x = wlo;
-                    while (x < whi) {
-                        const double ad = fabs(x - tau);
-                        double step = (ad < 6.0 * sig) ? w : fmax(w, 0.25 * ad);
-                        step = fmin(step, 0.35 * x);
-                        const double x1 = fmin(whi, x + step);
-                        {   // the 4 lanes of the chain take 4 of the panel's 16 nodes each (no divergence inside a chain)
-                            const double mid = 0.5 * (x1 + x), half = 0.5 * (x1 - x);
-#pragma unroll 1
-                            for (int i = 0; i < 4; i++) {
-                                const int q = 4 * j + i;
-                                const double gx = (q & 1) ? -DM_GX[q >> 1] : DM_GX[q >> 1];
-                                dm_node(pv, fma(half, gx, mid), half * DM_GW[q >> 1], tau, c4, acc);
-                            }
-                        }
-                        x = x1;
-                    }
-                    if (j == 0 && wlo == lo) dm_end(pv, lo, 1.0, tau, a, c4, acc);
-                    if (j == 1 && whi == hi) dm_end(pv, hi, -1.0, tau, a, c4, acc);
-                }
-            } else {
-#pragma unroll 1
-                for (int k = pv.Kc + j; k < pv.L; k += 4) dm_node(pv, (double)k + pv.dtp, 1.0, tau, c4, acc);
-            }
-        }
-        const unsigned full = 0xffffffffu;
-#pragma unroll
-        for (int c = 0; c < NCOL; c++) {
-            acc[c] += __shfl_xor_sync(full, acc[c], 1);
-            acc[c] += __shfl_xor_sync(full, acc[c], 2);
-        }
-        o0 += (j == 0) ? acc[0] : (j == 1) ? acc[2] : (j == 2) ? acc[4] : acc[6];
-        o1 += (j == 0) ? acc[1] : (j == 1) ? acc[3] : (j == 2) ? acc[5] : acc[7];
-    }
-
     // normalise, mix the two components, apply tracer rules; lane (r, j) returns the outputs of tracers
     // j, j+4 of chain r in val[0..1] (NaN-propagating exactly like f1*cout1 + f2*cout2 of the reference)
     __device__ __forceinline__ void end(const ChainPar (&p)[NT], const PlanView& pv, double* scratch_warp, int lane,
-                                        double (&val)[NT][2], const double* park_warp = nullptr) {
+                                        double (&val)[NT][2], const double* park_warp = nullptr, int ct_off = 0) {
         const int j = lane & 3, r = lane >> 2;
         const unsigned full = 0xffffffffu;
         if constexpr (PK) __syncwarp();
@@ -623,8 +675,18 @@ struct WarpTiles {
                             ad2[t] += Wa * pv.dyn_bg * exp(-p[t].lam_cfc * (a + dtp)) * geo_sum0(c2[t].er + p[t].lam_cfc, n);
                     }
                 }
-                if constexpr (DM_TAIL && C1 == CLS_D) dm_tail(pv, p[t].tau1, p[t].D1, c1[t].dead(), j, a1[t][0][0], a1[t][0][1]);
-                if constexpr (DM_TAIL && C2 == CLS_D) dm_tail(pv, p[t].tau2, p[t].D2, c2[t].dead(), j, a2[t][0][0], a2[t][0][1]);
+                if constexpr (DM_TAIL && C1 == CLS_D) {
+                    double res[3];
+                    dm_tail<DYN>(ct_off, p[t].tau1, p[t].D1, j | (c1[t].dead() ? 4 : 0), p[t].lam_cfc, res);
+                    a1[t][0][0] += res[0]; a1[t][0][1] += res[1];
+                    if (DYN) ad1[t] += res[2];
+                }
+                if constexpr (DM_TAIL && C2 == CLS_D) {
+                    double res[3];
+                    dm_tail<DYN>(ct_off, p[t].tau2, p[t].D2, j | (c2[t].dead() ? 4 : 0), p[t].lam_cfc, res);
+                    a2[t][0][0] += res[0]; a2[t][0][1] += res[1];
+                    if (DYN) ad2[t] += res[2];
+                }
             }
             double m[2], md = 0.0;
             double x1[2], x2[2] = {0.0, 0.0}, xd1 = 0.0, xd2 = 0.0;
@@ -787,6 +849,7 @@ __host__ __device__ inline int fwd_smem_doubles(int nwarps, int lc_cap, bool tap
     if (WT::DYNAMIC) p += lc_cap + (WT::ANY_D ? lc_cap : 0);
     if (tape) p += nwarps * WT::NTILES * WT::NPART * 32 + ((nwarps + 2) >> 1);
     if (WT::PARK) p += nwarps * WT::NTILES * 8 * PARK_DOUBLES;
+    if (WT::TAILMODE != 0 && WT::ANY_D && DM_TAIL) p += CT_DOUBLES;
     return p;
 }
 
@@ -832,6 +895,8 @@ struct FwdCta {
         s.flag = p; if (tape) p += (nwarps + 2) >> 1;
         s.park = p; if (PK) p += nwarps * NT * 8 * PARK_DOUBLES;
         park_off = s.park + warp * NT * 8 * PARK_DOUBLES;
+        s.ctab = p;
+        if (TM != 0 && WT::ANY_D && DM_TAIL) { p += CT_DOUBLES; ct_fill(ngrtd_smem + s.ctab, pv, tid); }
         need_J = false;
         for (int t = 0; t < pv.ntracer; t++) need_J |= (pv.tr[t].col_b >= 0);
         phase = 0;
@@ -900,7 +965,7 @@ struct FwdCta {
                 if (active) w.chunk(s, pv, kc, len / 4, lane);
             }
         }
-        if (active) w.end(par, pv, ngrtd_smem + scratch_off, lane, val, ngrtd_smem + park_off);
+        if (active) w.end(par, pv, ngrtd_smem + scratch_off, lane, val, ngrtd_smem + park_off, s.ctab);
     }
     // lock-step rounds only (k_forward with streamed tables; its resident-table path is the tape schedule)
     __device__ __forceinline__ void eval_lockstep(const ChainPar (&par)[NT], bool active, double (&val)[NT][2]) {
@@ -914,7 +979,7 @@ struct FwdCta {
             __syncthreads();
             if (active) w.chunk(s, pv, kc, len / 4, lane);
         }
-        if (active) w.end(par, pv, ngrtd_smem + scratch_off, lane, val, ngrtd_smem + park_off);
+        if (active) w.end(par, pv, ngrtd_smem + scratch_off, lane, val, ngrtd_smem + park_off, s.ctab);
     }
 
     // Unit schedule.  Resident tables: static and balanced -- units are dealt round-robin to the 4*gridDim.x SM
@@ -1140,7 +1205,7 @@ k_forward(PlanView pv, SlotMap sm, const double* __restrict__ theta, long long B
                     }
                 }
                 double val[NT][2];
-                w.end(par, pv, ngrtd_smem + cta.scratch_off, cta.lane, val, ngrtd_smem + cta.park_off);
+                w.end(par, pv, ngrtd_smem + cta.scratch_off, cta.lane, val, ngrtd_smem + cta.park_off, cta.s.ctab);
                 long long chain[NT];
 #pragma unroll
                 for (int t = 0; t < NT; t++) chain[t] = ((ub0 + ul) * NT + t) * 8 + r;

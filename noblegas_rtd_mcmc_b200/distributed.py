@@ -1,6 +1,7 @@
 """Multi-GPU plumbing: chains shard over ranks (one process per GPU, torch.distributed over NCCL/NVLink); the only
-collective is the all-gather of per-chain statistics for R-hat / ESS.  On CPU test runs the same code
-goes through the gloo backend."""
+collective is the reduction of chain statistics for R-hat / ESS: ONE all-reduce of 3*ndim + 1 pooled
+moments that every rank reduced on its own device (`pooled_summary`), or -- when per-chain moments are wanted -- an
+all-gather of them (`global_summary`).  On CPU test runs the same code goes through the gloo backend."""
 import numpy as np
 
 
@@ -73,3 +74,35 @@ def global_summary(n_draws, mean_t, m2_t):
     from . import diagnostics
     mean_all, m2_all = gather_chain_stats(mean_t, m2_t)
     return diagnostics.moments_summary(float(n_draws), mean_all.cpu().numpy(), m2_all.cpu().numpy())
+
+
+def allreduce_pooled(vec_t):
+    """Sum the pooled-moment vectors [3*nd + 1] of all ranks (in place; no-op without a process group)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(vec_t, op=dist.ReduceOp.SUM)
+    return vec_t
+
+
+def summary_from_pooled(n_draws, vec):
+    """Pooled mean / sd, classic R-hat and the many-chain ESS estimate from [sum mean, sum mean^2, sum M2, chains]
+    (the same quantities diagnostics.moments_summary derives from per-chain moments)."""
+    vec = np.asarray(vec, dtype=np.float64)
+    nd = (len(vec) - 1) // 3
+    M = float(vec[3 * nd])
+    n = float(n_draws)
+    s1, s2, sm2 = vec[:nd], vec[nd:2 * nd], vec[2 * nd:3 * nd]
+    mean = s1 / M
+    Bn = np.maximum(s2 - s1 * s1 / M, 0.0) / (M - 1.0)         # B / n: variance of the chain means
+    W = sm2 / (M * (n - 1.0))
+    var_plus = (n - 1.0) / n * W + Bn
+    with np.errstate(all="ignore"):
+        return {"mean": mean, "sd": np.sqrt(var_plus), "r_hat": np.sqrt(var_plus / W), "ess": M * var_plus / Bn,
+                "mcse_mean": np.sqrt(Bn / M), "chains": int(M), "draws_per_chain": n}
+
+
+def pooled_summary(sampler, n_draws, stream=None):
+    """R-hat / ESS / pooled moments over the chains of ALL ranks without moving per-chain data: every rank reduces its
+    chains on the device (Sampler.pooled_moments), one all-reduce adds the 3*ndim + 1 numbers (identical on every rank)."""
+    vec = allreduce_pooled(sampler.pooled_moments(stream))
+    return summary_from_pooled(n_draws, vec.cpu().numpy())

@@ -29,7 +29,7 @@ class Sampler(object):
         cfg.ndim = len(priors)
         if not 1 <= cfg.ndim <= 10:
             raise ValueError("1..10 sampler dimensions are supported")
-        tmap = _lib.NG_TARGET if plan is None else dict(_lib.SLOT, nu_=_lib.VAL_NU)
+        tmap = _lib.NG_TARGET if plan is None else dict({k: v for k, v in _lib.SLOT.items() if k != "f1_f2c"}, nu_=_lib.VAL_NU)
         self.names = []
         nu_sampled = False
         for i, p in enumerate(priors):
@@ -71,6 +71,7 @@ class Sampler(object):
             for i, g in enumerate(gases):
                 cfg.gases[i] = _lib.GAS[g[0:2]]
         self.plan = plan
+        self.nobs = len(obs_mu)
         self.hist_cap = int(hist_cap)
         self.nchains = int(nchains)
         self.ndim = cfg.ndim
@@ -110,6 +111,8 @@ class Sampler(object):
         sd = _lib.f64(np.atleast_2d(obs_sd))
         if mu.shape != sd.shape:
             raise ValueError("obs_mu and obs_sd must have the same shape [ngroups, nobs]")
+        if mu.shape[1] != self.nobs:
+            raise ValueError("obs_mu / obs_sd need %d columns (one per observation of the sampler), got %d" % (self.nobs, mu.shape[1]))
         _lib.check(_lib.lib.ngrtd_sampler_set_obs_groups(self.handle, _lib.hptr(mu), _lib.hptr(sd), mu.shape[0],
                                                          int(chains_per_group)))
 
@@ -126,6 +129,15 @@ class Sampler(object):
             shape = (self.hist_cap, self.nchains, self.ndim)
         out = torch.empty(shape, dtype=torch.float64, device=self.device)
         _lib.check(_lib.lib.ngrtd_sampler_get(self.handle, w, _lib.dptr(out), _lib.stream_ptr(stream)))
+        return out
+
+    def pooled_moments(self, stream=None):
+        """K6 on the device: [sum_c mean (nd), sum_c mean^2 (nd), sum_c M2 (nd), chains] over this shard's chains as a CUDA
+        tensor of 3*ndim + 1 doubles (ngrtd_sampler_pooled_moments); ranks add these with one all-reduce
+        (distributed.pooled_summary)."""
+        import torch
+        out = torch.empty(3 * self.ndim + 1, dtype=torch.float64, device=self.device)
+        _lib.check(_lib.lib.ngrtd_sampler_pooled_moments(self.handle, _lib.dptr(out), _lib.stream_ptr(stream)))
         return out
 
     def set(self, what, tensor, stream=None):

@@ -20,30 +20,7 @@ MODEL_CFGS = {
     "pfm_epm": ("piston", "exp_pist_flow", ["tau1", "tau2", "f1", "f2", "eta2", "thalf_cfc"]),
 }
 
-# tracer -> (series key, t_half, rad_accum) on the real yearly data (reference run_age_mcmc.py:200-224)
-REAL_TRACERS = {
-    "CFC11": ("CFC11", False, False),
-    "CFC12": ("CFC12", False, False),
-    "CFC113": ("CFC113", False, False),
-    "SF6": ("SF6", False, False),
-    "He4_ter": (None, False, "4He"),
-    "He3": ("H3", 12.34, "3He"),
-    "H3": ("H3", 12.34, False),
-}
-
-
-def load_c_in(L=None):
-    """Rebuild the reference's C_in_dict series (newest-first float64[L]) from the committed head."""
-    z = np.load(os.path.join(GOLD, "c_in_head.npz"))
-    Lfull = int(z["L"])
-    L = Lfull if L is None else L
-    out = {}
-    for k in ("CFC11", "CFC12", "CFC113", "SF6", "He4_ter", "H3"):
-        v = np.full(L, float(z[k + "_bg"]))
-        n = min(L, 128)
-        v[:n] = z[k + "_head"][:n]
-        out[k] = v
-    return out
+from noblegas_rtd_mcmc_b200.datasets import REAL_TRACERS, load_c_in  # noqa: E402,F401  (the series live in the package)
 
 
 def rel_err(a, b):
@@ -76,16 +53,7 @@ def synth_plan(mod1, mod2, par_names, tracers=None, L=840, seed=0, device=-1):
 
 
 def real_plan(mod1, mod2, par_names, tracers, L=None):
-    """Plan over the reference's yearly series (rebuilt from the committed head + constant background)."""
-    from noblegas_rtd_mcmc_b200 import _lib
-    C = load_c_in(L)
-    names = ["CFC11", "CFC12", "CFC113", "SF6", "H3"]
-    X = np.stack([C[n] for n in names], axis=1)
-    descs = []
-    for t in tracers:
-        s, th, ra = REAL_TRACERS[t]
-        descs.append(dict(series=names.index(s) if s is not None else -1, rad_accum=ra,
-                          lam=float(-1.0 * np.log(0.5) / th) if th else 0.0,
-                          use_thalf_cfc=(t == "CFC12" and "thalf_cfc" in par_names),
-                          use_lamsf6=(t == "SF6")))
+    """Plan over the reference's yearly series (rebuilt from the packaged head + constant background)."""
+    from noblegas_rtd_mcmc_b200 import _lib, datasets
+    X, descs, C = datasets.real_series_matrix_and_descs(par_names, tracers, L)
     return _lib.Plan(X, descs, mod1, mod2), C
