@@ -155,9 +155,21 @@ struct CompD {
             const double2 ib = *reinterpret_cast<const double2*>(pv.itp + 2 * kb);
             const double emax = fmax(fma(ap, ia.x, fma(bp, ia.y, cp)), fma(ap, ib.x, fma(bp, ib.y, cp)));
             ok = emax >= (double)exp_clamp<TB>();
+            // Such chains are evaluated RELATIVE to their largest weight (the normalisation g / g.sum() cancels the factor):
+            // exp_scaled_bits clamps at ~2^-1022 instead of flushing to zero, and when the largest weight itself is within
+            // a few hundred e-folds of that floor (mode far beyond the lag window: e^-680 at the last lag, the floor
+            // hundreds of times across the window) the clamped weights would no longer be negligible.  After the shift the
+            // floor sits 708 e-folds below the largest weight.
+            if (ok) cp -= emax;
         }
         cp += FX_MAGIC;     // exp_scaled_bits takes ep + FX_MAGIC: folded into the constant term
         if (!ok) ap = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    // natural-log scale of the loop's weights relative to the unshifted RTD weight: w_loop = w * exp(-shift()) (the analytic
+    // tail is summed in absolute terms and rescaled with it); i4D as in init_q.  0 on the fast path.
+    __device__ __forceinline__ double shift(double i4D) const {
+        constexpr double K = exp_k<TB>();
+        return (K * 2.0 * i4D - (cp - FX_MAGIC)) * (1.0 / K);           // cp - FX_MAGIC is exact
     }
     // it = {1/tp, tp} of the lag (shared-memory table): two independent FMAs, no carried state
     __device__ __forceinline__ double weight(double2 it, unsigned int tbl_lane) const {
@@ -238,11 +250,12 @@ __device__ __forceinline__ void ct_fill(double* tab, const PlanView& pv, int tid
     if (tid == NCOL) { tab[40] = (double)pv.Kc; tab[41] = (double)pv.L; tab[42] = pv.dtp; tab[43] = pv.dyn_bg; }
 }
 // lam_dyn / accd: per-chain decay constant (thalf_cfc) and the sum of its column dyn_bg * exp(-lam_dyn t) (DYN plans)
+// sh: natural-log scale of the lag loop's weights (CompD::shift), so that loop and tail sums share one scale
 template <bool DYN>
-__device__ __forceinline__ void dm_node(const CtView& cv, double t, double wt, double tau, double c4, double (&acc)[NCOL],
-                                        double lam_dyn, double& accd) {
+__device__ __forceinline__ void dm_node(const CtView& cv, double t, double wt, double tau, double c4, double sh,
+                                        double (&acc)[NCOL], double lam_dyn, double& accd) {
     const double dt = t - tau;
-    const double wgt = wt * exp(-dt * dt * c4 / t) / (t * sqrt(t));
+    const double wgt = wt * exp(-dt * dt * c4 / t - sh) / (t * sqrt(t));
     acc[0] += wgt;
     if constexpr (DYN) accd = fma(wgt, cv.dyn_bg() * exp(-lam_dyn * t), accd);
     double last = 0.0, d = 1.0;
@@ -261,10 +274,10 @@ __device__ __forceinline__ void dm_node(const CtView& cv, double t, double wt, d
 }
 // sgn * (g1/24 - 7 g3/5760) of every column at the end point t
 template <bool DYN>
-__device__ __forceinline__ void dm_end(const CtView& cv, double t, double sgn, double tau, double a, double c4,
+__device__ __forceinline__ void dm_end(const CtView& cv, double t, double sgn, double tau, double a, double c4, double sh,
                                        double (&acc)[NCOL], double lam_dyn, double& accd) {
     const double dt = t - tau, it = 1.0 / t;
-    const double w = exp(-dt * dt * c4 * it) * it / sqrt(t);
+    const double w = exp(-dt * dt * c4 * it - sh) * it / sqrt(t);
     const double p1 = (1.5 - 2.0 * a * it) * it * it, p2 = (-3.0 + 6.0 * a * it) * it * it * it;
     const double pb = (-1.5 + a * it) * it - c4;                  // log-derivative without the decay constant
     auto terms = [&](double lam, double& g, double& g1, double& g2, double& g3) {
@@ -299,7 +312,7 @@ __device__ __forceinline__ void dm_end(const CtView& cv, double t, double sgn, d
 // calls).  res[0], res[1]: the tail of the lane's two output columns (2j, 2j+1); res[2]: the per-chain-decay column
 // (lane 0 of the chain carries the total, the others 0).  ct_off: offset of the CT_DOUBLES table in ngrtd_smem.
 template <bool DYN>
-__device__ __noinline__ void dm_tail(int ct_off, double tau, double D, int dead_j, double lam_dyn, double* res) {
+__device__ __noinline__ void dm_tail(int ct_off, double tau, double D, int dead_j, double sh, double lam_dyn, double* res) {
     const CtView cv{ngrtd_smem + ct_off};
     const int j = dead_j & 3;
     const bool dead = (dead_j >> 2) != 0;
@@ -330,18 +343,18 @@ __device__ __noinline__ void dm_tail(int ct_off, double tau, double D, int dead_
                         for (int i = 0; i < 4; i++) {
                             const int q = 4 * j + i;
                             const double gx = (q & 1) ? -DM_GX[q >> 1] : DM_GX[q >> 1];
-                            dm_node<DYN>(cv, fma(half, gx, mid), half * DM_GW[q >> 1], tau, c4, acc, lam_dyn, accd);
+                            dm_node<DYN>(cv, fma(half, gx, mid), half * DM_GW[q >> 1], tau, c4, sh, acc, lam_dyn, accd);
                         }
                     }
                     x = x1;
                 }
-                if (j == 0 && wlo == lo) dm_end<DYN>(cv, lo, 1.0, tau, a, c4, acc, lam_dyn, accd);
-                if (j == 1 && whi == hi) dm_end<DYN>(cv, hi, -1.0, tau, a, c4, acc, lam_dyn, accd);
+                if (j == 0 && wlo == lo) dm_end<DYN>(cv, lo, 1.0, tau, a, c4, sh, acc, lam_dyn, accd);
+                if (j == 1 && whi == hi) dm_end<DYN>(cv, hi, -1.0, tau, a, c4, sh, acc, lam_dyn, accd);
             }
         } else {
             const int k0 = (int)Kc, k1 = (int)Ld;
 #pragma unroll 1
-            for (int k = k0 + j; k < k1; k += 4) dm_node<DYN>(cv, (double)k + dtp, 1.0, tau, c4, acc, lam_dyn, accd);
+            for (int k = k0 + j; k < k1; k += 4) dm_node<DYN>(cv, (double)k + dtp, 1.0, tau, c4, sh, acc, lam_dyn, accd);
         }
     }
     const unsigned full = 0xffffffffu;
@@ -677,13 +690,15 @@ struct WarpTiles {
                 }
                 if constexpr (DM_TAIL && C1 == CLS_D) {
                     double res[3];
-                    dm_tail<DYN>(ct_off, p[t].tau1, p[t].D1, j | (c1[t].dead() ? 4 : 0), p[t].lam_cfc, res);
+                    dm_tail<DYN>(ct_off, p[t].tau1, p[t].D1, j | (c1[t].dead() ? 4 : 0), c1[t].shift(__ddiv_rn(0.25, p[t].D1)),
+                                 p[t].lam_cfc, res);
                     a1[t][0][0] += res[0]; a1[t][0][1] += res[1];
                     if (DYN) ad1[t] += res[2];
                 }
                 if constexpr (DM_TAIL && C2 == CLS_D) {
                     double res[3];
-                    dm_tail<DYN>(ct_off, p[t].tau2, p[t].D2, j | (c2[t].dead() ? 4 : 0), p[t].lam_cfc, res);
+                    dm_tail<DYN>(ct_off, p[t].tau2, p[t].D2, j | (c2[t].dead() ? 4 : 0), c2[t].shift(__ddiv_rn(0.25, p[t].D2)),
+                                 p[t].lam_cfc, res);
                     a2[t][0][0] += res[0]; a2[t][0][1] += res[1];
                     if (DYN) ad2[t] += res[2];
                 }
