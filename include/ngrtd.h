@@ -159,7 +159,8 @@ int ngrtd_convolve_g_dev(int32_t L, double dtp, const double* g_d, int64_t B, co
 /* ---- closed-equilibrium noble-gas model: noble_gas_fun(...).ce_exc / equil_conc[_dry]
  *      (utils/noble_gas_utils.py:103-253).  gases: HOST int32[ngas] with 0=He 1=Ne 2=Ar 3=Kr 4=Xe.
  *  what: 0 = ce_exc(add_eq_conc=True), 1 = ce_exc(False), 2 = equil_conc_dry(), 3 = equil_conc(),
- *        4 = solubility K
+ *        4 = solubility K, 5 = total pressure as used (lapse_rate(), :103-113, when P is NULL),
+ *        6 = vapor_pressure() (:184-199) -- 5 and 6 do not depend on the gas (one column per listed gas all the same)
  *  E, T, Ae, F, P: [B]; P may be NULL = 'lapse_rate' (:97-98, :112);  S = salinity            */
 int ngrtd_ce_dev(int32_t what, int32_t ngas, const int32_t* gases, const double* E_d, const double* T_d,
                  const double* Ae_d, const double* F_d, const double* P_d, double S, int64_t B,

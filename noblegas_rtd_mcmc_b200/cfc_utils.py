@@ -49,16 +49,13 @@ class cfc_ce_corr():
         out, scalar = _run(what, self.cfc, self.E, self.T, Ae_g, self.F, self.S, X)
         return out[0] if scalar else out
 
-    def vapor_pressure_atm(self):                        # :35-52
-        T = np.asarray(self.T, dtype=np.float64)
-        lo = T <= 99.0
-        P = 10 ** (np.where(lo, 8.07131, 8.14019) - (np.where(lo, 1730.63, 1810.94) / (np.where(lo, 233.426, 244.485) + T)))
-        P = P / 760. * 101325 / 1.0e9 / 0.000101325
-        return float(P) if np.ndim(self.T) == 0 else P
+    def vapor_pressure_atm(self):                        # :35-52: the CE kernel's Antoine pressure [GPa] in atmospheres
+        from .noble_gas_utils import _ce_pressure
+        return _ce_pressure("P_vapor", self.T) / 0.000101325
 
-    def lapse_rate_atm(self):                            # :54-60
-        P = ((1 - .0065 * np.asarray(self.E, dtype=np.float64) / 288.15) ** 5.2561)
-        self.P = float(P) if np.ndim(self.E) == 0 else P
+    def lapse_rate_atm(self):                            # :54-60: the CE kernel's lapse-rate pressure [GPa] in atmospheres
+        from .noble_gas_utils import _ce_pressure
+        self.P = _ce_pressure("P_lapse", self.E) / 0.000101325
         return self.P
 
     def solubility_cfc(self):                            # :62-83

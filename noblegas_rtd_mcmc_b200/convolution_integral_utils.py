@@ -3,12 +3,16 @@ B200 through libngrtd.so.  Same names, kwargs and mutating-attribute behaviour a
 (utils/convolution_integral_utils.py:105-340); additive behaviour: array-valued tau/eta/D/J/lamba of shape [B]
 give batched results of shape [B].
 
-'frac_inf_diff' (fracture / matrix diffusion with a dispersion advective RTD, :36-63,238-266) is evaluated by a
-dedicated quadrature kernel (dispersion or caller-supplied advective RTD `f_tadv_ext`, :66-97) and convolved through the
-external-weights path.  Not provided: 'frac_inf_diff.mint'
-(an older pure-Python duplicate that prints on every call, :199-235), the external advective RTD `f_tadv_ext`
-(:66-97) and the dead 'SF6' accumulation branch (:330-331, J_sf6 is never set by any caller).
+'frac_inf_diff' (fracture / matrix diffusion, :36-63,238-266) is evaluated by a dedicated quadrature kernel -- with the
+dispersion advective RTD or with a caller-supplied one, `update_pars(f_tadv_ext=...)` (:66-97) -- and convolved through the
+external-weights path.  Not provided: 'frac_inf_diff.mint' (an older pure-Python duplicate that prints on every call,
+:199-235) and the dead 'SF6' accumulation branch (:330-331, J_sf6 is never set by any caller).
+
+`.g_tp` after convolve() holds what the reference stores there (:300-316): the normalised weights AFTER the decay /
+ingrowth factor.  The fused kernel never materialises weights, so the attribute is filled lazily on first access.
 """
+import hashlib
+
 import numpy as np
 
 from . import _lib
@@ -36,6 +40,24 @@ class tracer_conv_integral():
         self.C_t = C_t            # input series; DataFrame indexed by lag (descending to the sampling date)
         self.t_samp = t_samp      # sample date
         self._plans = {}
+        self._g_tp = None         # decayed weights of the last convolve(): ndarray, or a thunk that materialises them
+
+    # ---- .g_tp (reference :300-316: normalised weights times exp(-lam tp), or times 1 - exp(-lam tp) for '3He')
+    @property
+    def g_tp(self):
+        if callable(self._g_tp):
+            self._g_tp = self._g_tp()
+        return self._g_tp
+
+    @g_tp.setter
+    def g_tp(self, value):
+        self._g_tp = value
+
+    def _decay(self, g, lam, tp):
+        """g * exp(-lam tp), or g * (1 - exp(-lam tp)) for 3He ingrowth (:313-316); lam scalar or [B]."""
+        lam = np.asarray(lam, dtype=np.float64)
+        e = np.exp(-lam[..., None] * tp) if lam.ndim else np.exp(-lam * tp)
+        return g * (1.0 - e) if self.rad_accum == '3He' else g * e
 
     # ---- utils/convolution_integral_utils.py:111-142
     def update_pars(self, **kwargs):
@@ -161,7 +183,9 @@ class tracer_conv_integral():
         ra = self.rad_accum if self.rad_accum else False
         if lam_batched and ra:
             raise ValueError("array-valued lamba together with rad_accum is not supported")
-        key = (self.mod_type, ra, None if lam_batched else float(lam), id(self.C_t), L, dtp)
+        # the reference re-reads C_t on every convolve(): key the plan cache on the CONTENT of the series and its index
+        digest = hashlib.blake2b(vals.tobytes() + idx.tobytes(), digest_size=16).digest()
+        key = (self.mod_type, ra, None if lam_batched else float(lam), digest, L, dtp)
         plan = self._plans.get(key)
         if plan is None:
             desc = dict(series=0, rad_accum=ra, lam=0.0 if lam_batched else float(lam), use_thalf_cfc=lam_batched)
@@ -182,7 +206,22 @@ class tracer_conv_integral():
                 names.append("thalf_cfc"); cols.append(np.log(2.0) / self._col(lam, B))
         theta = np.ascontiguousarray(np.stack(cols, axis=1))
         out = plan.forward_host(theta, names)[:, 0]
-        self.g_tp = None           # weights are generated in registers; call gen_g_tp() to materialise them
+        # weights are generated in registers by the fused kernel; .g_tp materialises them (decay applied) on first access
+        state = (self.mod_type, self.tau, self.eta, self.D, lam, self.rad_accum)
+
+        def materialise():
+            keep = (self.mod_type, self.tau, self.eta, self.D)
+            self.mod_type, self.tau, self.eta, self.D = state[:4]
+            try:
+                g = self.gen_g_tp()
+            finally:
+                self.mod_type, self.tau, self.eta, self.D = keep
+            keep_ra, self.rad_accum = self.rad_accum, state[5]
+            try:
+                return self._decay(g, state[4], self.tau_list)
+            finally:
+                self.rad_accum = keep_ra
+        self._g_tp = materialise
         C_i = float(out[0]) if scalar else out
         self.C_i = C_i
         return C_i
@@ -206,6 +245,9 @@ class tracer_conv_integral():
         _lib.check(_lib.lib.ngrtd_convolve_g_dev(L, dtp, _lib.dptr(gt), B, _lib.dptr(st), _lib.dptr(it), _lib.dptr(lt), ra,
                                                  _lib.dptr(jt), _lib.dptr(out), _lib.stream_ptr()))
         res = out.cpu().numpy()
-        self.g_tp = g
+        tp = np.arange(0, L).astype(float)
+        tp[0] += 1e-5
+        tp += dtp
+        self._g_tp = self._decay(g, lam if np.ndim(lam) else float(lam), tp)      # decayed, as the reference stores it
         self.C_i = float(res[0]) if scalar else res
         return self.C_i

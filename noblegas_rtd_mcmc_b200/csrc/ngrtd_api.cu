@@ -1050,9 +1050,9 @@ extern "C" int ngrtd_ce_dev(int32_t what, int32_t ngas, const int32_t* gases, co
     GasList gl;
     int rc = make_gases(gl, ngas, gases);
     if (rc) return rc;
-    if (what < 0 || what > 4) return fail(NGRTD_EINVAL, "ce: unknown output selector");
+    if (what < 0 || what > 6) return fail(NGRTD_EINVAL, "ce: unknown output selector");
     if (!T_d || !out_d) return fail(NGRTD_EINVAL, "ce: T / out is null");
-    if (!P_d && !E_d && what != 4) return fail(NGRTD_EINVAL, "ce: need E (lapse rate) or P");
+    if (!P_d && !E_d && what != 4 && what != 6) return fail(NGRTD_EINVAL, "ce: need E (lapse rate) or P");
     if (what <= 1 && (!Ae_d || !F_d)) return fail(NGRTD_EINVAL, "ce: ce_exc needs Ae and F");
     if (B <= 0) return B == 0 ? NGRTD_OK : fail(NGRTD_EINVAL, "B < 0");
     unsigned grid = (unsigned)((B + 127) / 128);

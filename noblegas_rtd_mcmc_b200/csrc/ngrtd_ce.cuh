@@ -57,9 +57,12 @@ __device__ __forceinline__ double ce_vapor_pressure(double T) {   // :184-199
     return P / 1.0e9;
 }
 
-// what: 0 ce_exc(True), 1 ce_exc(False), 2 equil_conc_dry, 3 equil_conc (wet), 4 solubility
+// what: 0 ce_exc(True), 1 ce_exc(False), 2 equil_conc_dry, 3 equil_conc (wet), 4 solubility,
+//       5 total pressure P as used (lapse_rate(), :103-113, when no pressure is given), 6 vapor_pressure() (:184-199)
 __device__ __forceinline__ double ce_eval(int what, int gas, double E, double T, double Ae, double F, double P,
                                           double S) {
+    if (what == 5) return P;
+    if (what == 6) return ce_vapor_pressure(T);
     double K = ce_solubility(gas, T, S);
     if (what == 4) return K;
     double z = c_atm_std[gas];

@@ -164,10 +164,31 @@ def moments_summary(n, mean, m2):
             "ess": M * var_plus / Bn, "mcse_mean": np.sqrt(Bn / M), "chains": M, "draws_per_chain": n}
 
 
-def save_trace(path, posterior, sample_stats=None, attrs=None):
-    """Write a trace as `.npz` with the groups / variable names the reference stores through `az.to_netcdf`
+def to_inference_data(posterior, sample_stats=None, observed_data=None, attrs=None):
+    """`arviz.InferenceData` of a GPU run (needs arviz; not installed in this image): the object the reference obtains from
+    `az.from_pymc3(trace)` (run_age_mcmc_utils.py:419-423) -- `az.to_netcdf`, `az.summary` and the plotting scripts work
+    on it directly."""
+    import arviz as az
+    idata = az.from_dict(posterior={k: np.asarray(v) for k, v in posterior.items()},
+                         sample_stats={k: np.asarray(v) for k, v in (sample_stats or {}).items() if np.ndim(v) >= 2} or None,
+                         observed_data=observed_data or None)
+    for k, v in (attrs or {}).items():
+        idata.posterior.attrs[k] = v
+    return idata
+
+
+def save_trace(path, posterior, sample_stats=None, attrs=None, observed_data=None):
+    """Write a trace with the groups / variable names the reference stores through `az.to_netcdf`
     (run_age_mcmc_utils.py:425, noble_gas_mcmc.py:288): `posterior/<var>` arrays shaped [chain, draw], optional
-    `sample_stats/<name>` and scalar `attrs/<name>` (e.g. sampling_time)."""
+    `sample_stats/<name>` and scalar `attrs/<name>` (e.g. sampling_time).
+    A path ending in .netcdf / .nc is written as a NetCDF-4 (HDF5) file in ArviZ's InferenceData layout
+    (netcdf4_writer.write_trace) -- what `az.from_netcdf` of the reference's plotting scripts opens
+    (age_modeling_mcmc.post_plots.py:119-148, ng_interp/noble_gas_mcmc.compplots.py:222-233); anything else as `.npz`."""
+    if str(path).endswith((".netcdf", ".nc", ".nc4")):
+        from . import netcdf4_writer
+        ss = {k: v for k, v in (sample_stats or {}).items() if np.ndim(v) >= 2}
+        netcdf4_writer.write_trace(path, posterior, ss or None, observed_data, attrs)
+        return
     out = {}
     for k, v in posterior.items():
         a = np.asarray(v, dtype=np.float64)

@@ -24,6 +24,23 @@ def ce_exc_wrapper(theta, gases=GASES):
     return res[0] if single else res
 
 
+def as_theano_op(gases=GASES):
+    """`ce_exc_wrapper` as the Theano Op the reference builds with `@as_op(itypes=[tt.dvector], otypes=[tt.dvector])`
+    (ng_interp/noble_gas_mcmc.py:205): dvector theta -> dvector of modelled gases.  Needs theano (or aesara); raises
+    ImportError otherwise (this image)."""
+    try:
+        import theano.tensor as tt
+        from theano.compile.ops import as_op
+    except ImportError:
+        import aesara.tensor as tt
+        from aesara.compile.ops import as_op
+
+    @as_op(itypes=[tt.dvector], otypes=[tt.dvector])
+    def _op(theta):
+        return np.asarray(ce_exc_wrapper(theta, gases), dtype=np.float64)
+    return _op
+
+
 class mcmc_model(object):
     """The noble-gas closed-equilibrium inversion of ng_interp/noble_gas_mcmc.py:95-267 (priors :118-147,224-250;
     Student-T likelihood :254-266) with the reference's sampler settings (:408-415) as defaults."""
@@ -48,7 +65,10 @@ class mcmc_model(object):
                 prior("beta", "E", 2, 4, *b['E']), prior("normal", "m", self.lapse_slope, self.err_lapse_slope),
                 prior("beta", "b", 2, 2.5, *b['b']), prior("beta", "nu_", 2.0, 0.1, 0.0, 1.0)]
 
-    def sample(self, chains=4, tune=10000, draws=50000, random_seed=123423, tune_interval=5000, thin=1, hist_cap=None):
+    def sample(self, chains=4, tune=10000, draws=50000, random_seed=123423, tune_interval=5000, thin=1, hist_cap=None,
+               trace_path=None):
+        """trace_path: write the transformed posterior as NetCDF-4, the file the reference saves as
+        `traces/<well>_trans.netcdf` (noble_gas_mcmc.py:438-447) and prep.py / compplots.py open with az.from_netcdf."""
         from .sampler import Sampler
         smp = Sampler(self.build_priors(), self.obs_mu, self.obs_sd, chains, plan=None, gases=self.gases,
                       lik="studentt", nu_range=(1.0, 30.0), tune_interval=tune_interval,
@@ -64,4 +84,8 @@ class mcmc_model(object):
                 'b_beta': (raw['b'] - b['b'][0]) / (b['b'][1] - b['b'][0])}
         post['T'] = (post['E'] - post['b']) / post['m']                                           # :240
         self.sampler = smp
+        if trace_path is not None:
+            from . import diagnostics
+            diagnostics.save_trace(trace_path, post, observed_data={g: np.array([v]) for g, v in zip(self.gases, self.obs_mu)},
+                                   attrs={"tuning_steps": np.array([tune]), "inference_library": "ngrtd-b200 (DEMetropolisZ, pymc3 3.11.2 semantics)"})
         return {'posterior': post, 'sample_stats': {'accept_rate': smp.get("accepted").cpu().numpy() / float(tune + draws)}}

@@ -20,7 +20,7 @@ atm_std = {'N2': 0.781, 'O2': 0.209, 'Ar': 9.34e-3, 'CO2': 3.7e-4, 'Ne': 1.818e-
            'Xe129': 8.7e-8 * 26.44 / 100, 'Xe130': 8.7e-8 * 4.070 / 100, 'Xe131': 8.7e-8 * 21.22 / 100,
            'Xe132': 8.7e-8 * 26.89 / 100, 'Xe134': 8.7e-8 * 10.430 / 100, 'Xe136': 8.7e-8 * 8.857 / 100}
 
-_WHAT = {"ce_true": 0, "ce_false": 1, "eq_dry": 2, "eq_wet": 3, "K": 4}
+_WHAT = {"ce_true": 0, "ce_false": 1, "eq_dry": 2, "eq_wet": 3, "K": 4, "P_lapse": 5, "P_vapor": 6}
 
 
 def _gas_id(gas):
@@ -28,6 +28,18 @@ def _gas_id(gas):
     if g not in _lib.GAS:
         raise ValueError("unknown noble gas %r (known: He, Ne, Ar, Kr, Xe)" % (gas,))
     return _lib.GAS[g]
+
+
+def _ce_pressure(what, x):
+    """lapse_rate() / vapor_pressure() of the reference (:103-113, :184-199) [GPa], evaluated by the CE kernel
+    (selectors 5 / 6 of ngrtd_ce_host); x = E [m] or T [C], scalar or array."""
+    v = np.atleast_1d(np.asarray(x, dtype=np.float64))
+    out = np.empty((v.size, 1))
+    zeros = np.zeros(v.size)
+    E, T = (v.ravel(), zeros) if what == "P_lapse" else (None, v.ravel())
+    _lib.check(_lib.lib.ngrtd_ce_host(_WHAT[what], 1, _lib.hptr(_lib.i32([1])), _lib.hptr(_lib.f64(E)) if E is not None else None,
+                                      _lib.hptr(_lib.f64(T)), None, None, None, 0.0, v.size, _lib.hptr(out)))
+    return float(out[0, 0]) if np.ndim(x) == 0 else out[:, 0].reshape(np.shape(x))
 
 
 class noble_gas_fun():
@@ -51,9 +63,8 @@ class noble_gas_fun():
             raise ValueError("P must be '1atm', 'lapse_rate' or a pressure in GPa")
         return P
 
-    def lapse_rate(self):                          # :103-113
-        return ((1 - .0065 * np.asarray(self.E, dtype=np.float64) / 288.15) ** 5.2561) * 0.000101325 \
-            if np.ndim(self.E) else ((1 - .0065 * self.E / 288.15) ** 5.2561) * 0.000101325
+    def lapse_rate(self):                          # :103-113, evaluated by the CE kernel (selector 5, P = NULL)
+        return _ce_pressure("P_lapse", self.E)
 
     def _run(self, what, gases):
         ids = _lib.i32([_gas_id(g) for g in gases])
@@ -78,13 +89,8 @@ class noble_gas_fun():
         out, scalar = self._run("K", [gas])
         return float(out[0, 0]) if scalar else out[:, 0]
 
-    def vapor_pressure(self):                      # :184-199 (host arithmetic: a scalar property used for display)
-        T = np.asarray(self.T, dtype=np.float64)
-        lo = T <= 99.0
-        A, B, C = np.where(lo, 8.07131, 8.14019), np.where(lo, 1730.63, 1810.94), np.where(lo, 233.426, 244.485)
-        P = 10 ** (A - (B / (C + T)))
-        P = P / 760. * 101325 / 1.0e9
-        return float(P) if np.ndim(self.T) == 0 else P
+    def vapor_pressure(self):                      # :184-199, evaluated by the CE kernel (selector 6)
+        return _ce_pressure("P_vapor", self.T)
 
     def equil_conc(self):                          # :202-213
         return self._as_dict("eq_wet", list(self.gases))

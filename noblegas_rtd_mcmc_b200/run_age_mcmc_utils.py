@@ -106,13 +106,41 @@ class ForwardMod(object):
         """Forward model for one parameter vector (inputs[0]), result in outputs[0][0] as in the reference."""
         outputs[0][0] = np.array(self.perform_batch(np.asarray(inputs[0], dtype=np.float64).reshape(1, -1))[0])
 
+    def as_theano_op(self):
+        """The reference's boundary is `class ForwardMod(TT.Op)` with `itypes = [TT.dvector]`, `otypes = [TT.dscalar]`
+        (run_age_mcmc_utils.py:47-52), instantiated once per tracer inside the pymc3 model (:376-383).  Under a real
+        pymc3 / Theano installation this returns exactly such an Op whose `perform` is this object's `perform`, so
+        `ForwardMod(ckw, par_names, t).as_theano_op()(theta)` drops into `build_mcmc_model_joint_sT` unchanged.
+        (pymc3 evaluates one theta per call: the batched device sampler, `conv_mcmc.sample_mcmc`, is the fast path.)"""
+        return as_theano_op(self)
+
+
+def as_theano_op(forward_mod):
+    """Wrap a ForwardMod-like object (anything with `perform(node, inputs, outputs)`) as a Theano / Aesara Op with the
+    reference's signature: dvector -> dscalar.  Raises ImportError when neither theano nor aesara is installed (this image)."""
+    try:
+        import theano.tensor as TT
+    except ImportError:
+        import aesara.tensor as TT          # pymc3 >= 3.11.5 / pymc 4 successor of theano
+
+    class _ForwardModOp(TT.Op):
+        itypes = [TT.dvector]
+        otypes = [TT.dscalar]
+
+        def perform(self, node, inputs, outputs):
+            forward_mod.perform(node, inputs, outputs)
+    return _ForwardModOp()
+
 
 # ---------------------------------------------------------------------------------------------------------------
 # Model builder + sampler driver: the role of conv_mcmc (run_age_mcmc_utils.py:189-429 of the reference)
 # ---------------------------------------------------------------------------------------------------------------
 class conv_mcmc(object):
     """Same constructor as the reference; priors, observation errors, likelihood and sampler settings follow
-    build_mcmc_model_joint_sT / sample_mcmc (:275-429).  Plotting and netcdf output are out of scope."""
+    build_mcmc_model_joint_sT / sample_mcmc (:275-429).  With `savedir` the finished trace is written where and how the
+    reference writes it (`./<savedir>/<well>.<tracers>.<model>.<savenum>.netcdf`, :242-256, az.to_netcdf :425) as a
+    NetCDF-4 file the reference's plotting scripts open with az.from_netcdf (:434, post_plots.py:119-148).  Plotting is
+    out of scope."""
 
     def __init__(self, well, tracer, obs_kwgs, conv_kwgs, prior_kwgs, savedir=None, savenum=None):
         self.well = well
@@ -125,7 +153,14 @@ class conv_mcmc(object):
         self.mod_type2 = conv_kwgs.get('mod_type2', False)
         self.prior_kwgs = dict(prior_kwgs)
         self.savenum = savenum
+        self.savedir = savedir
         self.idata = None
+        self.trace_name = None
+        if savedir is not None:                                                  # setup_dirs (:242-256)
+            import os
+            tracer_list = '.'.join(self.tracer)
+            mod_type = '{}-{}'.format(self.mod_type1, self.mod_type2) if self.mod_type2 else '{}'.format(self.mod_type1)
+            self.trace_name = os.path.join('.', str(savedir), '{}.{}.{}.{}.netcdf'.format(self.well, tracer_list, mod_type, savenum))
 
     # ---- :286-344
     def build_priors(self):
@@ -186,7 +221,15 @@ class conv_mcmc(object):
             post['tau'] = post['f1'] * post['tau1'] + post['f2'] * post['tau2']          # :305
         self.idata = {'posterior': post,
                       'sample_stats': {'accept_rate': smp.get("accepted").cpu().numpy() / float(tune + draws),
-                                       'lamb': smp.get("lamb").cpu().numpy(), 'sampling_time': self.sampling_time}}
+                                       'lamb': smp.get("lamb").cpu().numpy(), 'sampling_time': self.sampling_time},
+                      'observed_data': {"obs_%s" % t: np.array([m]) for t, m in zip(self.tracer, mu)}}
+        if self.trace_name is not None:                                          # az.to_netcdf(idata, self.trace_name), :425
+            import os
+            from . import diagnostics
+            os.makedirs(os.path.dirname(self.trace_name), exist_ok=True)
+            diagnostics.save_trace(self.trace_name, post, observed_data=self.idata['observed_data'],
+                                   attrs={"sampling_time": np.array([self.sampling_time]), "tuning_steps": np.array([tune]),
+                                          "inference_library": "ngrtd-b200 (DEMetropolisZ, pymc3 3.11.2 semantics)"})
         return self.idata
 
     def posterior_predictive(self, idata=None, tracers=None, chain=None, max_draws=None):

@@ -108,7 +108,7 @@ def test_cfg5_long_lag_axis_mixture():
     assert np.isfinite(out).mean() > 0.9
 
 
-def test_posterior_predictive_batch_matches_loop():
+def test_posterior_predictive_batch_matches_loop(tmp_path, monkeypatch):
     """the posterior-predictive sweep of run_age_mcmc.py:243-319 as one batched launch."""
     import pandas as pd
     from helpers import load_c_in
@@ -121,9 +121,16 @@ def test_posterior_predictive_batch_matches_loop():
            "H3": dict(C_t=df(C["H3"], "H3_tu"), t_half=12.34)}
     okw = {t: dict(obs_df=np.array([v, v * 1.02, v * 0.98]), obs_perr=0.05) for t, v in (("CFC12", 36.4), ("H3", 4.87))}
     pkw = dict(tau1_low=1.0, tau1_high=1000.0, D1_low=0.01, D1_high=2.0, par_names=["tau1", "D1"])
+    monkeypatch.chdir(tmp_path)
     mc = conv_mcmc("PLM1", ["CFC12", "H3"], okw, ckw, pkw, "conv_traces", "0")
     idata = mc.sample_mcmc(chains=8, tune=1500, draws=500, tune_interval=250)
     post = idata["posterior"]
+    # the finished trace is written where the reference writes it (run_age_mcmc_utils.py:242-256,425), as NetCDF-4
+    from noblegas_rtd_mcmc_b200 import diagnostics
+    assert mc.trace_name == "./conv_traces/PLM1.CFC12.H3.dispersion.0.netcdf"
+    back = diagnostics.load_trace(mc.trace_name)
+    assert np.array_equal(back["posterior"]["tau1"], post["tau1"]) and np.array_equal(back["posterior"]["nu"], post["nu"])
+    assert abs(float(np.ravel(back["attrs"]["sampling_time"])[0]) - mc.sampling_time) < 1e-12
     assert post["tau1"].shape == (8, 500) and np.all((post["tau1"] > 1) & (post["tau1"] < 1000))
     assert np.all((post["nu"] >= 5) & (post["nu"] <= 30))
     pp = mc.posterior_predictive(chain=0)
@@ -132,6 +139,12 @@ def test_posterior_predictive_batch_matches_loop():
     for s in (0, 17, 499):                                              # the reference's per-draw loop, 3 draws
         m.update_pars(tau=post["tau1"][0, s], mod_type="dispersion", t_half=12.34, D=post["D1"][0, s], bbar=False, Phi_im=False)
         assert abs(m.convolve() - pp["H3"][s]) <= 1e-12 * abs(pp["H3"][s])
+    # ... and against the oracle (numpy restatement of the reference), every draw of chain 0
+    import np_oracle as O
+    th0 = np.stack([post["tau1"][0], post["D1"][0]], axis=1)
+    for t, key, th in (("CFC12", "CFC12", False), ("H3", "H3", 12.34)):
+        want = O.forward_mod(th0, ["tau1", "D1"], t, C[key], "dispersion", False, t_half=th)
+        assert np.max(np.abs(pp[t] - want) / np.abs(want)) < 1e-10, t
     mu, err = mc.observations()
     assert abs(np.median(pp["CFC12"]) - mu[0]) < 4 * err[0]          # the fit explains the observation
 

@@ -214,3 +214,100 @@ def test_c_abi_demo_runs(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "worst relative error" in out.stdout, out.stdout
+
+
+def test_propagate_obs_ensembles_matches_the_reference_lines():
+    """(f2) prep.propagate_obs_ensembles == age_modeling_mcmc.prep.py:242-489 run verbatim on the same synthetic CE posteriors
+    (tests/golden/ens_dict_small.npz): same random stream, same members, batched device calls instead of per-member loops."""
+    from noblegas_rtd_mcmc_b200 import prep
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ens_dict_small.npz"))
+    wells = [str(w) for w in z["wells"]]
+    draws = {w: z["draws/" + w] for w in wells}
+    map_dict, ens_dict, extras = prep.propagate_obs_ensembles(draws)
+    assert abs(extras["Rterr"] - float(z["Rterr"])) <= 1e-14 * extras["Rterr"]
+    n = 0
+    for k in z.files:
+        parts = k.split("/")
+        if parts[0] == "ens":
+            got = np.asarray(ens_dict[parts[1]][parts[2]]).ravel()
+        elif parts[0] == "map":
+            got = np.atleast_1d(np.asarray(map_dict[parts[1]].loc[parts[2]])).ravel()
+        elif parts[0] == "marg":
+            key = min(extras["he3_ens_marg"], key=lambda r: abs(r - float(parts[1])))
+            got = np.asarray(extras["he3_ens_marg"][key][parts[2]]).ravel()
+        else:
+            continue
+        want = z[k]
+        assert got.shape == want.shape, k
+        assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300)) < 1e-10, k
+        n += 1
+    assert n >= 60
+    # the structure the age inversion reads (run_age_mcmc_utils.py:353-356)
+    mu, sd = prep.observation_moments(ens_dict, "PLM1", ["CFC12", "SF6", "H3", "He4_ter"], {"CFC12": 0.05, "SF6": 0.05, "H3": 0.05, "He4_ter": 0.05})
+    assert mu.shape == (4,) and np.all(sd > 0)
+    assert list(ens_dict["CFC"]["PLM1"].columns) == ["CFC11", "CFC12", "CFC113"] and ens_dict["CFC12"]["PLM6"].shape == (64, 1)
+    # full size: 50,000 members per well in one call per (well, quantity)
+    rng = np.random.default_rng(3)
+    big = {w: draws[w][rng.integers(0, 64, 60000)] * rng.uniform(0.98, 1.02, (60000, 6)) for w in wells}
+    _, ens_big, _ = prep.propagate_obs_ensembles(big, marginal=False, as_frames=False)
+    assert ens_big["SF6"]["PLM7"].shape == (50000,) and np.isfinite(ens_big["He3"]["PLM1"]).all()
+
+
+def test_salinity_goldens_on_device():
+    """S != 0: Setchenow terms of the noble-gas solubilities (utils/noble_gas_utils.py:145-159) and the salinity terms of the
+    CFC / SF6 solubilities (utils/cfc_utils.py:62-83,196-209) against the untouched reference."""
+    from helpers import rel_err
+    from noblegas_rtd_mcmc_b200.cfc_utils import cfc_ce_corr, sf6_ce_corr
+    from noblegas_rtd_mcmc_b200.noble_gas_utils import noble_gas_fun
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ce_salinity.npz"))
+    gases = ["He", "Ne", "Ar", "Kr", "Xe"]
+    for S in (5.0, 35.0):
+        m = z["S"] == S
+        E, T, Ae, F = z["E"][m], z["T"][m], z["Ae"][m], z["F"][m]
+        ng = noble_gas_fun(gases=gases, E=E, T=T, Ae=Ae, F=F, P="lapse_rate", S=S)
+        for j, g in enumerate(gases):
+            assert rel_err(ng.solubility(g), z["K"][m][:, j]) < 1e-12, (S, g)
+        ce, dry, wet = ng.ce_exc(True), ng.equil_conc_dry(), ng.equil_conc()
+        for j, g in enumerate(gases):
+            assert rel_err(ce[g], z["ce_true"][m][:, j]) < 1e-12 and rel_err(dry[g], z["eq_dry"][m][:, j]) < 1e-12
+            assert rel_err(wet[g], z["eq_wet"][m][:, j]) < 1e-12
+        Tc = np.minimum(T, 30.0)
+        c = cfc_ce_corr(cfc_num=[11, 12, 113], E=E, T=Tc, Ae=Ae, F=F, S=S)
+        assert rel_err(c.solubility_cfc(), z["cfc_K"][m]) < 1e-12 and rel_err(c.equil_air_conc_cfc(z["Cm"][m]), z["cfc_air"][m]) < 1e-12
+        s6 = sf6_ce_corr(E=E, T=Tc, Ae=Ae, F=F, S=S)
+        assert rel_err(s6.solubility_sf6(), z["sf6_K"][m]) < 1e-12 and rel_err(s6.equil_air_conc_sf6(z["Cs"][m]), z["sf6_air"][m]) < 1e-12
+
+
+def test_g_tp_holds_the_decayed_weights():
+    """convolve() leaves in .g_tp what the reference stores there (utils/convolution_integral_utils.py:300-316): the
+    normalised weights times exp(-lam tp) (or 1 - exp(-lam tp) for 3He); materialised lazily; C_i == dot(flip(C), g_tp)."""
+    import pandas as pd
+    from helpers import load_c_in
+    from noblegas_rtd_mcmc_b200.convolution_integral_utils import tracer_conv_integral
+    C = load_c_in(600)
+    idx = np.arange(599, -1, -1, dtype=float)
+    df = pd.DataFrame({"H3_tu": C["H3"][::-1]}, index=idx)
+    for ra in (False, "3He"):
+        m = tracer_conv_integral(df, 0)
+        m.update_pars(tau=37.5, mod_type="exp_pist_flow", eta=1.5, t_half=12.34, rad_accum=ra)
+        c = m.convolve()
+        g = m.g_tp
+        tp = np.arange(600, dtype=float); tp[0] += 1e-5
+        lam = np.log(2) / 12.34
+        m2 = tracer_conv_integral(df, 0)
+        m2.update_pars(tau=37.5, mod_type="exp_pist_flow", eta=1.5)
+        g0 = m2.gen_g_tp()
+        want = g0 * (1 - np.exp(-lam * tp)) if ra == "3He" else g0 * np.exp(-lam * tp)
+        assert np.allclose(g, want, rtol=1e-12, atol=0)
+        assert abs(np.dot(C["H3"], g) - c) <= 1e-11 * abs(c)
+        # external weights: stored after the decay as well
+        m3 = tracer_conv_integral(df, 0)
+        m3.update_pars(tau=37.5, mod_type="exp_pist_flow", eta=1.5, t_half=12.34, rad_accum=ra)
+        c3 = m3.convolve(g_tau=g0)
+        assert np.allclose(m3.g_tp, want, rtol=1e-12) and abs(c3 - c) <= 1e-10 * abs(c)
+    # the plan cache is keyed on the CONTENT of the series: an in-place edit of C_t is seen by the next convolve()
+    m = tracer_conv_integral(df.copy(), 0)
+    m.update_pars(tau=20.0, mod_type="exponential")
+    a = m.convolve()
+    m.C_t.iloc[:, 0] *= 2.0
+    assert abs(m.convolve() - 2.0 * a) <= 1e-12 * abs(a)
