@@ -10,9 +10,15 @@ launches (k_mcmc_age, per-group observation rows: ngrtd_sampler_set_obs_groups).
 result does not depend on the sharding; the only collective is the all-gather of per-chain moments at the end.
 
 Model: exp_pist_flow, tracers CFC12 + SF6 + H3 + He4_ter on the reference's 25,256-lag yearly series, parameters
-tau1, eta1, J, thalf_cfc, lamsf6 (+ nu), priors of run_age_mcmc.py:145-196.  ens_dict.pk is a missing blob of the reference;
-members are drawn here as N(obs_mu, ens.std()) with obs_mu / ens.std() rebuilt from the reference's traces
-(tests/golden/age_traces.json, age_obs_err.json) and carry the 5 % analytical error (SF6 of PLM6: 1000 %) on their own.
+tau1, eta1, J, thalf_cfc, lamsf6 (+ nu), priors of run_age_mcmc.py:145-196.
+
+r2: the whole chain of the reference runs on the device.  ens_dict.pk is a missing blob of the reference, so the members
+are PRODUCED: (1) the closed-equilibrium noble-gas fit of every well (config 1, ng_interp/noble_gas_mcmc.py: 4 chains x
+(10,000 + 50,000) steps); (2) `prep.propagate_obs_ensembles` turns those posteriors and the field observations into the
+50,000-member observation ensembles of age_modeling_mcmc.prep.py:242-489 (ens_dict); (3) member m of well w supplies the
+observation row of group (w, m), with the 5 % analytical error (SF6 of PLM6: 1000 %, run_age_mcmc.py:100-114).
+Every group is one POPULATION of DE-MC-Z chains sharing an archive (ngrtd_sampler_set_population), so its chains find each
+other's modes; the report is the R-hat of every group over its chains.
 """
 import json
 import os
@@ -28,6 +34,8 @@ import torch.distributed as dist
 
 from helpers import real_plan
 from noblegas_rtd_mcmc_b200 import distributed as D
+from noblegas_rtd_mcmc_b200 import prep
+from noblegas_rtd_mcmc_b200.noble_gas_mcmc import mcmc_model
 from noblegas_rtd_mcmc_b200 import noble_gas_utils as ng_utils
 from noblegas_rtd_mcmc_b200.sampler import Sampler, prior
 
@@ -38,8 +46,10 @@ TRACERS = ["CFC12", "SF6", "H3", "He4_ter"]
 def main():
     total = int(sys.argv[1]) if len(sys.argv) > 1 else 1048576
     cpg = int(sys.argv[2]) if len(sys.argv) > 2 else 256
-    tune = int(sys.argv[3]) if len(sys.argv) > 3 else 10000      # the reference's own step counts (run_age_mcmc_utils.py:416)
-    draws = int(sys.argv[4]) if len(sys.argv) > 4 else 10000
+    # the reference runs 10,000 + 10,000 steps (run_age_mcmc_utils.py:416); the bimodal (tau1, eta1) posteriors of single
+    # ensemble members need ~10x that for EVERY chain of a population to visit both modes (R-hat over chains < 1.05)
+    tune = int(sys.argv[3]) if len(sys.argv) > 3 else 20000
+    draws = int(sys.argv[4]) if len(sys.argv) > 4 else 200000
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
@@ -47,18 +57,22 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ngroups = total // cpg
     total = ngroups * cpg
-    # ---- observation rows of all groups (identical on every rank: seeded) ----
+    # ---- observation rows of all groups: config 1 -> prep -> ens_dict (identical on every rank: seeded) ----
     fx = json.load(open(os.path.join(ROOT, "tests", "golden", "age_traces.json")))["traces"]
-    rel = json.load(open(os.path.join(ROOT, "tests", "golden", "age_obs_err.json")))["rel"]
+    ngobs = json.load(open(os.path.join(ROOT, "noblegas_rtd_mcmc_b200", "data", "ng_obs_plm.json")))["wells"]
+    t_pre = time.perf_counter()
+    draws_ce = {}
+    for w in WELLS:
+        post = mcmc_model(ngobs[w]["obs"], mcmc_model.well_elev[w]).sample(chains=4, tune=10000, draws=50000)["posterior"]
+        draws_ce[w] = np.stack([post[p].ravel() for p in prep.PARS], axis=1)             # prep.py:130
+    _, ens_dict, _ = prep.propagate_obs_ensembles(draws_ce, marginal=False, as_frames=False)
+    t_pre = time.perf_counter() - t_pre
     perr = {w: {"CFC12": 0.05, "SF6": 10.0 if w == "PLM6" else 0.05, "H3": 0.05, "He4_ter": 0.05} for w in WELLS}
-    rng = np.random.default_rng(2021)
     obs = np.empty((ngroups, len(TRACERS)))
     sd = np.empty_like(obs)
     for g in range(ngroups):
-        w = WELLS[g % 3]
-        mu = np.array(fx["%s.CFC12.SF6.H3.He4_ter.exp_pist_flow.123" % w]["obs_mu"])
-        spread = np.array([max(rel[t][w] - perr[w][t], 0.0) for t in TRACERS]) * mu          # ens.std()
-        obs[g] = np.abs(mu + spread * rng.standard_normal(len(TRACERS)))
+        w, m = WELLS[g % 3], g // 3
+        obs[g] = np.abs([ens_dict[t][w][m % len(ens_dict[t][w])] for t in TRACERS])
         sd[g] = np.array([perr[w][t] for t in TRACERS]) * obs[g]
     # ---- model, priors (run_age_mcmc.py:145-196), sampler shard ----
     pn = ["tau1", "eta1", "J", "thalf_cfc", "lamsf6"]
@@ -71,14 +85,19 @@ def main():
     smp = Sampler(pri, obs[0], sd[0], cnt, plan=plan, lik="studentt", nu_range=(5.0, 30.0), tune_interval=1000,
                   hist_cap=min(tune + draws, 2048), seed=123423, chain_offset=off, device=local)
     smp.set_obs_groups(obs, sd, cpg)
+    smp.set_population(cpg)                    # one shared DE-MC-Z archive per (well, member) group; shards hold whole groups
+    assert off % cpg == 0 and cnt % cpg == 0, "shards must hold whole populations"
     smp.run(8, tune=True)                      # first launch (module load) outside the timed region
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    smp.run(tune, tune=True)
+    LAUNCH = 500                               # the archive a launch reads is what the population had written before it
+    for _ in range(tune // LAUNCH):
+        smp.run(LAUNCH, tune=True)
     smp.stop_tuning()
-    smp.run(draws, tune=False, record=True)
+    for _ in range(draws // LAUNCH):
+        smp.run(LAUNCH, tune=False, record=True)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if world > 1:
@@ -102,7 +121,15 @@ def main():
               % (total, ngroups, (ngroups + 2) // 3, cpg, world, tune + draws))
         print("sampling %.2f s  ->  %.3e tracer-likelihood evals/s (chains x steps x tracers), acceptance %.3f"
               % (dt, total * (tune + draws) * len(TRACERS) / dt, float(acc) / steps))
-        print("median split-free R-hat over groups: " + ", ".join("%s %.3f" % (n, np.median(rhat[:, i])) for i, n in enumerate(names)))
+        print("noble-gas fits of %d wells + ensemble propagation (50,000 members per well): %.1f s" % (len(WELLS), t_pre))
+        print("R-hat of every group over its %d chains -- median: " % cpg + ", ".join("%s %.3f" % (n, np.median(rhat[:, i])) for i, n in enumerate(names)))
+        print("                                           99th pct: " + ", ".join("%s %.3f" % (n, np.percentile(rhat[:, i], 99)) for i, n in enumerate(names)))
+        print("groups with every R-hat < 1.05: %.1f %%" % (100.0 * np.mean(np.all(rhat < 1.05, axis=1))))
+        from noblegas_rtd_mcmc_b200 import diagnostics
+        ma, m2a = mean_all.cpu().numpy().reshape(ngroups, cpg, -1), m2_all.cpu().numpy().reshape(ngroups, cpg, -1)
+        nr = np.array([diagnostics.nested_rhat(draws, ma[g], m2a[g], 8) for g in range(min(ngroups, 2048))])
+        print("nested R-hat (8 superchains of %d chains per group; Margossian et al. 2022) -- max over %d groups: " % (cpg // 8, len(nr))
+              + ", ".join("%s %.4f" % (n, nr[:, i].max()) for i, n in enumerate(names)))
         gvar = W + Bn                                                            # posterior variance per group (within + between chains)
         for k, w in enumerate(WELLS):
             sel = np.arange(ngroups) % 3 == k

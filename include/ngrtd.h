@@ -245,6 +245,13 @@ int ngrtd_sampler_destroy(ngrtd_sampler* s);
  * obs_mu/obs_err per well from ens_dict, run_age_mcmc_utils.py:353-356).  obs_mu, obs_sd: HOST [ngroups, nobs]. */
 int ngrtd_sampler_set_obs_groups(ngrtd_sampler* s, const double* obs_mu, const double* obs_sd, int64_t ngroups,
                                  int64_t chains_per_group);
+/* DE-MC-Z with a SHARED archive (the original scheme of ter Braak & Vrugt 2008; pymc3's DEMetropolisZ keeps one archive per
+ * chain because its chains run in separate processes, run_age_mcmc_utils.py:412-417): the two history entries of a proposal
+ * are drawn from the archives of the `chains_per_population` consecutive GLOBAL chains of the chain's population, using the
+ * entries that were complete when the current launch started.  Lets a population share the modes its members found
+ * (BASELINE config 4: one population per (well, ensemble member) group).  0 restores per-chain archives.  Populations
+ * must not straddle shards; call between launches. */
+int ngrtd_sampler_set_population(ngrtd_sampler* s, int64_t chains_per_population);
 /* advance every chain by nsteps Metropolis steps in ONE kernel launch.  tune: tuning phase; record: update the
  * per-chain Welford statistics and, if trace_d != NULL, write natural-space draws trace_d[ceil(nsteps/thin), B, ndim]. */
 int ngrtd_sampler_run(ngrtd_sampler* s, int64_t nsteps, int32_t tune, int32_t record, int32_t thin, double* trace_d,

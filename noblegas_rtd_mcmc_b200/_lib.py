@@ -85,6 +85,7 @@ _PROTOS = {
     "ngrtd_sampler_create": ([ctypes.POINTER(_vp), ctypes.POINTER(SamplerCfg), _vp, _i64, _vp, _i32], ctypes.c_int),
     "ngrtd_sampler_destroy": ([_vp], ctypes.c_int),
     "ngrtd_sampler_set_obs_groups": ([_vp, _vp, _vp, _i64, _i64], ctypes.c_int),
+    "ngrtd_sampler_set_population": ([_vp, _i64], ctypes.c_int),
     "ngrtd_sampler_run": ([_vp, _i64, _i32, _i32, _i32, _vp, _vp], ctypes.c_int),
     "ngrtd_sampler_stop_tuning": ([_vp], ctypes.c_int),
     "ngrtd_sampler_get": ([_vp, _i32, _vp, _vp], ctypes.c_int),

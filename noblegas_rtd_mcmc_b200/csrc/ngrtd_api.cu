@@ -1464,6 +1464,13 @@ extern "C" int ngrtd_sampler_set_obs_groups(ngrtd_sampler* S, const double* obs_
     return NGRTD_OK;
 }
 
+extern "C" int ngrtd_sampler_set_population(ngrtd_sampler* S, int64_t chains_per_population) {
+    if (!S) return fail(NGRTD_EINVAL, "set_population: null sampler");
+    if (chains_per_population < 0) return fail(NGRTD_EINVAL, "set_population: chains_per_population must be >= 0");
+    S->sv.pool = chains_per_population;
+    return NGRTD_OK;
+}
+
 extern "C" int ngrtd_sampler_run(ngrtd_sampler* S, int64_t nsteps, int32_t tune, int32_t record, int32_t thin,
                                  double* trace_d, void* stream) {
     if (!S) return fail(NGRTD_EINVAL, "null sampler");

@@ -65,6 +65,8 @@ struct SamplerView {
     const double* g_isd;
     const double* g_lc;
     long long cpg;           // chains per group (0: one observation vector for all chains, obs/isd/lc above)
+    long long pool;          // > 0: DE-MC-Z with a SHARED archive -- z1, z2 come from the histories of the `pool` consecutive
+                             // global chains of this chain's population (ter Braak & Vrugt 2008), see de_select()
     GasList gases;           // noble-gas model: modelled gases
     double val_defaults[NVAL];   // value registers not driven by a sampler dimension (p_dict defaults)
 };
@@ -105,6 +107,59 @@ __device__ __forceinline__ double u01(unsigned int a, unsigned int b) {   // uni
     return ((double)(x >> 11) + 0.5) * (1.0 / 9007199254740992.0);
 }
 constexpr unsigned int RNG_SELECT = 0x100u;    // purpose of the (iz1, iz2, accept-uniform) draw
+constexpr unsigned int RNG_POOL = 0x101u;      // purpose of the partner-chain draw of the shared-archive mode
+
+// Which two history entries form the DE-MC-Z difference of `chain` at step i.
+// Default (pymc3 3.11.2 DEMetropolisZ): two distinct entries of the chain's OWN history, uniformly among the nvalid newest.
+// Shared archive (sv.pool > 0; the original DE-MC-Z of ter Braak & Vrugt 2008, where Z is the archive of ALL chains of a
+// population): each of z1, z2 is an entry of a uniformly drawn chain of the population.  A chain that only ever sees its
+// own past cannot propose a jump to a mode it has never visited; with the shared archive the difference vectors span the
+// modes the population has found (BASELINE config 4: 256 chains per (well, ensemble member)).  To stay deterministic the
+// (Every ~10th proposal of this mode takes gamma = 1 instead of the tuned lambda -- the mode-jumping move of DE-MC.)
+// partners' entries are taken from what was complete when this LAUNCH started and cannot be overwritten during it:
+// logical entries [max(hist_start, step0 + nsteps - cap), step0); before such a window exists the own history is used.
+// Populations must not straddle shards (partners are clipped to the local chains).
+// history ring: logical entry e lives in slot e % cap
+__device__ __forceinline__ size_t hist_off(const SamplerView& sv, long long e, long long chain) {
+    return ((size_t)(e % sv.hist_cap) * (size_t)sv.B + (size_t)chain) * (size_t)sv.nd;
+}
+
+struct DeSel { size_t o1, o2; bool use, jump; };
+__device__ __forceinline__ DeSel de_select(const SamplerView& sv, const RunArgs& ra, long long chain, long long gchain,
+                                           long long i, uint4 sel) {
+    DeSel r{0, 0, false, false};
+    long long nvalid = i - ra.hist_start;
+    if (nvalid > sv.hist_cap) nvalid = sv.hist_cap;
+    if (!(ra.mode == 0 && sv.de_mcz && nvalid > 1)) return r;
+    r.use = true;
+    if (sv.pool > 0) {
+        long long lo = ra.step0 + ra.nsteps - sv.hist_cap;
+        if (lo < ra.hist_start) lo = ra.hist_start;
+        const long long nw = ra.step0 - lo;
+        if (nw > 1) {
+            long long g0 = (gchain / sv.pool) * sv.pool - sv.chain_offset;
+            long long g1 = g0 + sv.pool;
+            if (g0 < 0) g0 = 0;
+            if (g1 > sv.B) g1 = sv.B;
+            const unsigned int np = (unsigned int)(g1 - g0);
+            const uint4 s2 = chain_rng(sv.seed, gchain, i, RNG_POOL);
+            const long long c1 = g0 + __umulhi(s2.x, np), c2 = g0 + __umulhi(s2.y, np);
+            const long long e1 = lo + __umulhi(sel.x, (unsigned int)nw), e2 = lo + __umulhi(sel.y, (unsigned int)nw);
+            r.o1 = hist_off(sv, e1, c1);
+            r.o2 = hist_off(sv, e2, c2);
+            // every ~10th proposal uses gamma = 1 instead of the tuned lambda: the full difference of two archive members is
+            // what carries a chain from one mode to another (ter Braak 2006, section 2)
+            r.jump = s2.z < 429496730u;
+            return r;
+        }
+    }
+    unsigned int iz1 = __umulhi(sel.x, (unsigned int)nvalid);
+    unsigned int iz2 = __umulhi(sel.y, (unsigned int)(nvalid - 1));
+    if (iz2 >= iz1) iz2++;
+    r.o1 = hist_off(sv, i - nvalid + iz1, chain);
+    r.o2 = hist_off(sv, i - nvalid + iz2, chain);
+    return r;
+}
 
 // ---------------------------------------------------------------- priors and transforms (pymc3 3.11.2)
 // transformed coordinate x -> natural value v; returns log prior density + log |Jacobian|.
@@ -153,11 +208,6 @@ __device__ __forceinline__ double proposal_noise(int dist, uint4 e) {
     if (dist == 0) return 2.0 * u - 1.0;
     double u2 = u01(e.z, e.w);
     return sqrt(-2.0 * log(u)) * cospi(2.0 * u2);
-}
-
-// history ring: logical entry e lives in slot e % cap
-__device__ __forceinline__ size_t hist_off(const SamplerView& sv, long long e, long long chain) {
-    return ((size_t)(e % sv.hist_cap) * (size_t)sv.B + (size_t)chain) * (size_t)sv.nd;
 }
 
 // Welford update + trace row for one dimension
@@ -241,25 +291,16 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
                 }
                 __syncwarp();
                 // -- proposal
-                long long nvalid = i - ra.hist_start;
-                if (nvalid > sv.hist_cap) nvalid = sv.hist_cap;
-                const bool use_de = ra.mode == 0 && sv.de_mcz && nvalid > 1;
                 uint4 sel = chain_rng(sv.seed, gchain, i, RNG_SELECT);
-                long long e1 = 0, e2 = 0;
-                if (use_de) {
-                    unsigned int iz1 = __umulhi(sel.x, (unsigned int)nvalid);
-                    unsigned int iz2 = __umulhi(sel.y, (unsigned int)(nvalid - 1));
-                    if (iz2 >= iz1) iz2++;
-                    e1 = i - nvalid + iz1;
-                    e2 = i - nvalid + iz2;
-                }
-                const double lamb = sc[1], scal = sc[2];
+                const DeSel de = de_select(sv, ra, ok[t] ? chain[t] : 0, gchain, i, sel);
+                const bool use_de = de.use;
+                const double lamb = de.jump ? 1.0 : sc[1], scal = sc[2];
                 double lps = 0.0;
                 for (int d = j; d < sv.nd; d += 4) {
                     double qn = qs[d];
                     if (ra.mode == 0) {
                         double eps = proposal_noise(sv.proposal_dist, chain_rng(sv.seed, gchain, i, (unsigned int)d));
-                        if (use_de && ok[t]) qn += lamb * (sv.hist[hist_off(sv, e1, chain[t]) + d] - sv.hist[hist_off(sv, e2, chain[t]) + d]);
+                        if (use_de && ok[t]) qn += lamb * (sv.hist[de.o1 + d] - sv.hist[de.o2 + d]);
                         qn += eps * scal;
                     }
                     qp[d] = qn;
@@ -374,24 +415,25 @@ __global__ void __launch_bounds__(64, NGRTD_NG_MINBLOCKS) k_mcmc_ng(SamplerView 
             if (sv.tune_target == 0) lamb *= f; else scal *= f;
             acc_win = 0;
         }
-        long long nvalid = i - ra.hist_start;
-        if (nvalid > sv.hist_cap) nvalid = sv.hist_cap;
-        const bool use_de = ra.mode == 0 && sv.de_mcz && nvalid > 1;
         uint4 sel = chain_rng(sv.seed, gchain, i, RNG_SELECT);
-        size_t o1 = 0, o2 = 0;
-        if (use_de) {
-            unsigned int iz1 = __umulhi(sel.x, (unsigned int)nvalid);
-            unsigned int iz2 = __umulhi(sel.y, (unsigned int)(nvalid - 1));
-            if (iz2 >= iz1) iz2++;
-            o1 = hist_off(sv, i - nvalid + iz1, chain);
-            o2 = hist_off(sv, i - nvalid + iz2, chain);
+        const DeSel de = de_select(sv, ra, chain, gchain, i, sel);
+        const bool use_de = de.use;
+        const size_t o1 = de.o1, o2 = de.o2;
+        // Philox is counter based: the two history rows of the NEXT step are known now -- pull them towards L2 / L1 so that
+        // the gather at the top of the next step (r1: long_scoreboard 1.56 per issue on `z1 - z2`) finds them there
+        if (ra.mode == 0 && s + 1 < nsteps) {
+            const DeSel dn = de_select(sv, ra, chain, gchain, i + 1, chain_rng(sv.seed, gchain, i + 1, RNG_SELECT));
+            if (dn.use) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(sv.hist + dn.o1));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(sv.hist + dn.o2));
+            }
         }
         double lps = 0.0;
         for (int d = 0; d < sv.nd; d++) {
             double qn = qs[d];
             if (ra.mode == 0) {
                 double eps = proposal_noise(sv.proposal_dist, chain_rng(sv.seed, gchain, i, (unsigned int)d));
-                if (use_de) qn += lamb * (sv.hist[o1 + d] - sv.hist[o2 + d]);
+                if (use_de) qn += (de.jump ? 1.0 : lamb) * (sv.hist[o1 + d] - sv.hist[o2 + d]);
                 qn += eps * scal;
             }
             qp[d] = qn;

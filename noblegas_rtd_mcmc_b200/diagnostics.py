@@ -177,6 +177,26 @@ def to_inference_data(posterior, sample_stats=None, observed_data=None, attrs=No
     return idata
 
 
+def nested_rhat(n, mean, m2, n_super):
+    """Nested R-hat of Margossian et al. (2022, "Nested R-hat: assessing the convergence of Markov chain Monte Carlo when
+    running many short chains") from per-chain Welford moments: the chains [chains, ndim] are split into `n_super`
+    superchains of consecutive chains; B = variance of the superchain means, W = mean over superchains of (variance of
+    the chain means inside the superchain + mean within-chain variance); nR-hat = sqrt(1 + B / W).  It measures what
+    matters when a POPULATION of chains is pooled (DE-MC-Z with a shared archive): whether sub-populations agree,
+    not whether every single chain has mixed."""
+    mean = np.asarray(mean, dtype=np.float64)
+    m2 = np.asarray(m2, dtype=np.float64)
+    M = mean.shape[0] // n_super
+    if M < 2:
+        raise ValueError("need at least two chains per superchain")
+    mean = mean[:M * n_super].reshape(n_super, M, -1)
+    wvar = (m2[:M * n_super] / (float(n) - 1.0)).reshape(n_super, M, -1)
+    smean = mean.mean(axis=1)
+    B = smean.var(axis=0, ddof=1)
+    W = (mean.var(axis=1, ddof=1) + wvar.mean(axis=1)).mean(axis=0)
+    return np.sqrt(1.0 + B / W)
+
+
 def save_trace(path, posterior, sample_stats=None, attrs=None, observed_data=None):
     """Write a trace with the groups / variable names the reference stores through `az.to_netcdf`
     (run_age_mcmc_utils.py:425, noble_gas_mcmc.py:288): `posterior/<var>` arrays shaped [chain, draw], optional

@@ -116,6 +116,12 @@ class Sampler(object):
         _lib.check(_lib.lib.ngrtd_sampler_set_obs_groups(self.handle, _lib.hptr(mu), _lib.hptr(sd), mu.shape[0],
                                                          int(chains_per_group)))
 
+    def set_population(self, chains_per_population):
+        """DE-MC-Z with a shared archive per population of consecutive global chains (ter Braak & Vrugt 2008): proposals use
+        the histories of all members, as of the start of the current launch -- so run in several launches (e.g. 500 steps
+        each) and keep hist_cap >= 2 x steps per launch.  0 = per-chain archives (pymc3's DEMetropolisZ)."""
+        _lib.check(_lib.lib.ngrtd_sampler_set_population(self.handle, int(chains_per_population)))
+
     def stop_tuning(self):
         _lib.check(_lib.lib.ngrtd_sampler_stop_tuning(self.handle))
 
