@@ -22,7 +22,13 @@
 #pragma once
 #include "ngrtd_common.cuh"
 
+#ifndef NGRTD_LOOP_UNROLL
+#define NGRTD_LOOP_UNROLL 2      // lag groups per iteration of the steady-state loop (2: the compiler pairs the weight chains)
+#endif
+
 namespace ngrtd {
+
+constexpr int LOOP_UNROLL = NGRTD_LOOP_UNROLL;
 
 // All kernels of the library use this one dynamic shared-memory array; sub-arrays are addressed as OFFSETS (in
 // doubles) from it, so that every access is provably in the shared address space (pointers kept in a struct were
@@ -551,7 +557,7 @@ struct WarpTiles {
             }
         }
 #endif
-#pragma unroll 2
+#pragma unroll LOOP_UNROLL
         for (; g + UA <= ngroups; g += UA) {
 #pragma unroll
             for (int u = 0; u < UA; u++) {
@@ -710,7 +716,7 @@ struct WarpTiles {
             // 1/S would leave the normal range (S subnormal: every weight underflowed) the plain division is kept so
             // that such chains behave exactly as before (decided per chain: results never depend on warp neighbours).
             double S1 = 1.0, S2 = 1.0, r1 = 1.0, r2 = 1.0;
-            bool use_div = false;
+            bool use_div = false, any_div = false;
             if constexpr (LOOP1) {
                 S1 = __shfl_sync(full, a1[t][0][0], lane & ~3);
                 if constexpr (C1 == CLS_D) { if (c1[t].dead()) S1 = c1[t].ap; }
@@ -723,6 +729,7 @@ struct WarpTiles {
                 const double den = (LOOP1 && (!LOOP2 || (j & 1) == 0)) ? S1 : S2;
                 const double rr = __ddiv_rn(1.0, den);
                 use_div = (LOOP1 && fabs(S1) < 1e-290) || (LOOP2 && fabs(S2) < 1e-290);   // per chain, not per warp
+                any_div = __any_sync(full, use_div);
                 if constexpr (LOOP1) r1 = __shfl_sync(full, rr, lane & ~3);
                 if constexpr (LOOP2) r2 = __shfl_sync(full, rr, (lane & ~3) + (LOOP1 ? 1 : 0));
             }
@@ -742,14 +749,15 @@ struct WarpTiles {
                     s += __shfl_xor_sync(full, s, 1);
                     s += __shfl_xor_sync(full, s, 2);
                 }
-                if (use_div) {
-                    x1[0] = a1[t][0][0] / S1;
-                    x1[1] = a1[t][0][1] / S1;
-                    if (DYN) xd1 = s / S1;
-                } else {
-                    x1[0] = a1[t][0][0] * r1;
-                    x1[1] = a1[t][0][1] * r1;
-                    if (DYN) xd1 = s * r1;
+                x1[0] = a1[t][0][0] * r1;
+                x1[1] = a1[t][0][1] * r1;
+                if (DYN) xd1 = s * r1;
+                if (any_div) {                  // warp-uniform: the IEEE divisions are not even issued in the common case
+                    if (use_div) {
+                        x1[0] = a1[t][0][0] / S1;
+                        x1[1] = a1[t][0][1] / S1;
+                        if (DYN) xd1 = s / S1;
+                    }
                 }
             }
             if constexpr (C2 == CLS_P) {
@@ -767,14 +775,15 @@ struct WarpTiles {
                     s += __shfl_xor_sync(full, s, 1);
                     s += __shfl_xor_sync(full, s, 2);
                 }
-                if (use_div) {
-                    x2[0] = a2[t][0][0] / S2;
-                    x2[1] = a2[t][0][1] / S2;
-                    if (DYN) xd2 = s / S2;
-                } else {
-                    x2[0] = a2[t][0][0] * r2;
-                    x2[1] = a2[t][0][1] * r2;
-                    if (DYN) xd2 = s * r2;
+                x2[0] = a2[t][0][0] * r2;
+                x2[1] = a2[t][0][1] * r2;
+                if (DYN) xd2 = s * r2;
+                if (any_div) {
+                    if (use_div) {
+                        x2[0] = a2[t][0][0] / S2;
+                        x2[1] = a2[t][0][1] / S2;
+                        if (DYN) xd2 = s / S2;
+                    }
                 }
             }
             // cout = f1*cout1 + f2*cout2 (run_age_mcmc_utils.py:154); cout2 = 0.0 without a second component
