@@ -415,19 +415,10 @@ __global__ void __launch_bounds__(64, NGRTD_NG_MINBLOCKS) k_mcmc_ng(SamplerView 
             if (sv.tune_target == 0) lamb *= f; else scal *= f;
             acc_win = 0;
         }
-        uint4 sel = chain_rng(sv.seed, gchain, i, RNG_SELECT);
+        const uint4 sel = chain_rng(sv.seed, gchain, i, RNG_SELECT);
         const DeSel de = de_select(sv, ra, chain, gchain, i, sel);
         const bool use_de = de.use;
         const size_t o1 = de.o1, o2 = de.o2;
-        // Philox is counter based: the two history rows of the NEXT step are known now -- pull them towards L2 / L1 so that
-        // the gather at the top of the next step (r1: long_scoreboard 1.56 per issue on `z1 - z2`) finds them there
-        if (ra.mode == 0 && s + 1 < nsteps) {
-            const DeSel dn = de_select(sv, ra, chain, gchain, i + 1, chain_rng(sv.seed, gchain, i + 1, RNG_SELECT));
-            if (dn.use) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(sv.hist + dn.o1));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(sv.hist + dn.o2));
-            }
-        }
         double lps = 0.0;
         for (int d = 0; d < sv.nd; d++) {
             double qn = qs[d];

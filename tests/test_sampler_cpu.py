@@ -130,6 +130,52 @@ def test_chain_stats_gather_gloo_world2():
     assert res[0][2] == res[1][2] and res[0][3] == 11
 
 
+def _gloo_pooled_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from noblegas_rtd_mcmc_b200.distributed import allreduce_pooled, shard, summary_from_pooled
+    rng = np.random.default_rng(77)
+    total, nd = 13, 3
+    mean_all = rng.normal(size=(total, nd))
+    m2_all = rng.uniform(1, 2, size=(total, nd))
+    off, cnt = shard(total, rank, world)
+    m, v = mean_all[off:off + cnt], m2_all[off:off + cnt]
+    # what ngrtd_sampler_pooled_moments leaves on the device of a rank: [sum mean, sum mean^2, sum M2, chains]
+    vec = torch.from_numpy(np.concatenate([m.sum(0), (m * m).sum(0), v.sum(0), [float(cnt)]]))
+    s = summary_from_pooled(20, allreduce_pooled(vec).numpy())
+    q.put((rank, s["mean"].tolist(), s["r_hat"].tolist(), s["ess"].tolist(), s["chains"]))
+    dist.destroy_process_group()
+
+
+def test_pooled_summary_gloo_world2():
+    """K6 across ranks on CPU: one all-reduce of 3*nd + 1 pooled moments gives, on every rank, the summary that the
+    all-gathered per-chain moments give (diagnostics.moments_summary)."""
+    import socket
+    import torch.multiprocessing as mp
+    from noblegas_rtd_mcmc_b200 import diagnostics as dg
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_pooled_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][1:] == res[1][1:] and res[0][4] == 13
+    rng = np.random.default_rng(77)
+    mean_all = rng.normal(size=(13, 3))
+    m2_all = rng.uniform(1, 2, size=(13, 3))
+    ref = dg.moments_summary(20.0, mean_all, m2_all)
+    assert np.allclose(res[0][1], ref["mean"], rtol=1e-13)
+    assert np.allclose(res[0][2], ref["r_hat"], rtol=1e-12)
+
+
 def test_trace_npz_roundtrip(tmp_path):
     from noblegas_rtd_mcmc_b200 import diagnostics as dg
     rng = np.random.default_rng(3)
