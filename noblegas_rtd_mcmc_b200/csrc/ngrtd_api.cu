@@ -1209,17 +1209,17 @@ struct ngrtd_sampler {
 
 static double lbeta(double a, double b) { return std::lgamma(a) + std::lgamma(b) - std::lgamma(a + b); }
 
-template <int C1, int C2, bool DYN>
-static int launch_mcmc_age(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st) {
+template <int C1, int C2, bool DYN, bool TAIL>
+static int launch_mcmc_age_t(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st) {
     constexpr int NT = FWD_NT, UA = FWD_UA, MAXW = FWD_MAXW;
-    using WT = WarpTiles<C1, C2, DYN, NT, UA, MCMC_TB>;
+    using WT = WarpTiles<C1, C2, DYN, NT, UA, MCMC_TB, TAIL ? 1 : 0>;
     ngrtd_plan* P = S->plan;
     const long long B = S->sv.B;
     long long nunits = (B + NT * 8 - 1) / (NT * 8);
     int warps = pick_warps(nunits, P->nsm, MAXW);
     if (warps > 4) warps &= ~3;
     // shared memory: forward tables + one CH_REC record per resident chain; shrink the lag chunk until it fits
-    const int Lloop = tail_active(P->pv, WT::ANY_G, WT::ANY_D) ? P->pv.Kc : P->Lpad;
+    const int Lloop = (TAIL && tail_active(P->pv, WT::ANY_G, WT::ANY_D)) ? P->pv.Kc : P->Lpad;
     int lc_cap = WT::ANY_LOOP ? std::min(Lloop, LC_MAX) : 0;
     size_t sh = 0;
     for (;;) {
@@ -1230,7 +1230,7 @@ static int launch_mcmc_age(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st)
         lc_cap = (lc_cap / 2 + 3) & ~3;
     }
     if (sh > 227 * 1024) return fail(NGRTD_EINVAL, "sampler: shared-memory budget exceeded");
-    auto kern = k_mcmc_age<C1, C2, DYN, NT, UA, MAXW>;
+    auto kern = k_mcmc_age<C1, C2, DYN, NT, UA, MAXW, TAIL>;
     static thread_local SmemConfigured configured;
     const int dev = (S->device >= 0 && S->device < MAX_DEVICES) ? S->device : 0;
     if (configured.bytes[dev] < sh) {
@@ -1242,6 +1242,16 @@ static int launch_mcmc_age(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st)
     kern<<<grid, warps * 32, sh, st>>>(P->pv, S->sv, ra, lc_cap);
     CUDA_TRY(cudaGetLastError());
     return NGRTD_OK;
+}
+
+// two instantiations per model pair, as for k_forward: with and without the constant-tail code
+template <int C1, int C2, bool DYN>
+static int launch_mcmc_age(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st) {
+    constexpr bool ANY_G = (C1 == CLS_G || C2 == CLS_G), ANY_D = (C1 == CLS_D || C2 == CLS_D);
+    if constexpr (ANY_G || ANY_D) {
+        if (tail_active(S->plan->pv, ANY_G, ANY_D)) return launch_mcmc_age_t<C1, C2, DYN, true>(S, ra, st);
+    }
+    return launch_mcmc_age_t<C1, C2, DYN, false>(S, ra, st);
 }
 
 template <int C1, bool DYN>

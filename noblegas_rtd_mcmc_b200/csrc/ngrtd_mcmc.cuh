@@ -224,10 +224,11 @@ __device__ __forceinline__ void record_dim(const SamplerView& sv, const RunArgs&
 }
 
 // ---------------------------------------------------------------- age model: one warp = NT tiles of 8 chains
-template <int C1, int C2, bool DYN, int NT, int UA, int MAXW>
+// TAIL: the constant-tail code (closed form / quadrature) is compiled in; the launcher picks the instantiation by plan
+template <int C1, int C2, bool DYN, int NT, int UA, int MAXW, bool TAIL>
 __global__ void __launch_bounds__(MAXW * 32, 1)
 k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
-    FwdCta<C1, C2, DYN, NT, UA, MCMC_TB> cta(pv);
+    FwdCta<C1, C2, DYN, NT, UA, MCMC_TB, TAIL ? 1 : 0> cta(pv);
     const int rec_base = cta.setup(lc_cap);
     const int lane = cta.lane, j = lane & 3, r = lane >> 2;
     // prior table in shared memory (dynamic indexing of kernel parameters would be demoted to local memory)
