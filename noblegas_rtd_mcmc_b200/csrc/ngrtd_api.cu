@@ -1286,7 +1286,17 @@ static int mcmc_c1(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st) {
 static int sampler_launch(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st) {
     if (S->sv.model == 1) {
         unsigned grid = (unsigned)((S->sv.B + 63) / 64);
-        k_mcmc_ng<<<grid, 64, 0, st>>>(S->sv, ra);
+        // register-resident instantiations for the dimension counts of the reference's model (nu_ sampled / fixed);
+        // NGRTD_NG_GENERIC=1 forces the run-time-nd kernel (same trajectories, bit for bit)
+        static const bool generic = [] { const char* e = getenv("NGRTD_NG_GENERIC"); return e && e[0] == '1'; }();
+        if (!generic && (S->sv.nd == 6 || S->sv.nd == 5)) {
+            // (static shared memory 7 ND x 64 doubles per block; the default carve-out is the fastest: asking for the
+            //  maximum shrinks L1 and costs 40 %, measured)
+            if (S->sv.nd == 6) k_mcmc_ng_r<6><<<grid, 64, 0, st>>>(S->sv, ra);
+            else k_mcmc_ng_r<5><<<grid, 64, 0, st>>>(S->sv, ra);
+        } else {
+            k_mcmc_ng<<<grid, 64, 0, st>>>(S->sv, ra);
+        }
         CUDA_TRY(cudaGetLastError());
         return NGRTD_OK;
     }

@@ -475,6 +475,186 @@ __global__ void __launch_bounds__(64, NGRTD_NG_MINBLOCKS) k_mcmc_ng(SamplerView 
     sv.acc_tot[chain] = acc_tot;
 }
 
+// ---------------------------------------------------------------- noble-gas CE model, register-resident (r2)
+// Same arithmetic, same Philox counters and therefore the same trajectories as k_mcmc_ng, for a compile-time number of
+// dimensions: every per-dimension array has constant indices after unrolling and lives in registers (k_mcmc_ng keeps a 416-byte
+// local-memory frame because its loops run to the run-time sv.nd), and the history gather is software-pipelined: Philox is
+// counter based, so the selection of step s + 1 is computed at the top of step s and its two rows start an ASYNCHRONOUS copy
+// into the thread's shared-memory slot there (cp.async, SASS LDGSTS: no destination register, so nothing can stall on it and
+// nothing is spilled); they are read at the END of the step (difference vector of the next proposal), after the whole CE model.
+// r1 / r2 profiles: the subtraction z1 - z2 at the top of the step carried 12-14 % of all stall samples; cache hints
+// (prefetch.global.L2, touch loads) did not move it and a register prefetch was spilled by ptxas right behind the loads
+// (profiles/r2_notes.md).
+// Hazard: the next step may select the entry this step appends (own-history mode); that row is then the chain's final state
+// of this step, which is in registers.
+// >= 7 blocks of 64 threads per SM = 448 chains: one wave for 65,536 chains on 148 SMs (ptxas settles on 128 registers; a
+// 142-register build without any spill holds 6 blocks and is 1.5x slower at that batch)
+#ifndef NGRTD_NG_R_MINBLOCKS
+#define NGRTD_NG_R_MINBLOCKS 8
+#endif
+template <int ND>
+__global__ void __launch_bounds__(64, NGRTD_NG_R_MINBLOCKS) k_mcmc_ng_r(SamplerView sv, RunArgs ra) {
+    __shared__ double zrow[2 * ND * 64];           // [row 1 | row 2][dim][thread]: conflict-free
+    __shared__ double prop[3 * ND * 64];           // the proposal (transformed | natural) between its construction and the accept
+                                                   // decision, and the natural values of the current state (read only when a
+                                                   // draw is recorded): 6 ND registers less across the CE model
+    const long long chain = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (chain >= sv.B) return;
+    const long long gchain = sv.chain_offset + chain;
+    double* z1s = zrow + threadIdx.x;
+    double* z2s = zrow + ND * 64 + threadIdx.x;
+    const unsigned int z1a = (unsigned int)__cvta_generic_to_shared(z1s), z2a = (unsigned int)__cvta_generic_to_shared(z2s);
+    double* qp = prop + threadIdx.x;               // qp[d * 64]
+    double* vp = prop + ND * 64 + threadIdx.x;
+    double* vn = prop + 2 * ND * 64 + threadIdx.x;
+    // Welford accumulators of the chain: read once per launch, updated in shared memory, written back once (k_mcmc_ng
+    // reads and writes them in global memory every recorded step: 2/3 of its DRAM traffic)
+    __shared__ double wfs[2 * ND * 64];
+    double* wmean = wfs + threadIdx.x;
+    double* wm2 = wfs + ND * 64 + threadIdx.x;
+    const bool rec = ra.mode == 0 && ra.record;
+    if (rec) {
+#pragma unroll
+        for (int d = 0; d < ND; d++) { wmean[d * 64] = sv.wf_mean[chain * ND + d]; wm2[d * 64] = sv.wf_m2[chain * ND + d]; }
+    }
+    double qs[ND];
+#pragma unroll
+    for (int d = 0; d < ND; d++) {
+        qs[d] = sv.q[chain * ND + d];
+        double v;
+        transform_dim(sv.pr[d], qs[d], v);
+        vn[d * 64] = v;
+    }
+    double logp = sv.logp[chain], lamb = sv.lamb[chain], scal = sv.scal[chain];
+    int acc_win = sv.acc_win[chain];
+    long long acc_tot = sv.acc_tot[chain];
+    const int nsteps = ra.mode == 1 ? 1 : ra.nsteps;
+    const long long grp = sv.cpg > 0 ? gchain / sv.cpg : 0;
+
+    uint4 sel = chain_rng(sv.seed, gchain, ra.step0, RNG_SELECT);
+    bool use_de, jump;
+    double dz[ND];
+    {
+        const DeSel de = de_select(sv, ra, chain, gchain, ra.step0, sel);
+        use_de = de.use; jump = de.jump;
+#pragma unroll
+        for (int d = 0; d < ND; d++) dz[d] = use_de ? sv.hist[de.o1 + d] - sv.hist[de.o2 + d] : 0.0;
+    }
+    for (int s = 0; s < nsteps; s++) {
+        const long long i = ra.step0 + s;
+        if (ra.mode == 0 && ra.tune && i > 0 && (i % sv.tune_interval) == 0) {
+            double f = tune_factor((double)acc_win / (double)sv.tune_interval);
+            if (sv.tune_target == 0) lamb *= f; else scal *= f;
+            acc_win = 0;
+        }
+        // ---- next step's selection; its rows start their way from HBM now
+        const bool more = ra.mode == 0 && s + 1 < nsteps;
+        uint4 sel_n = sel;
+        DeSel dn{0, 0, false, false};
+        bool hz1 = false, hz2 = false;
+        if (more) {
+            sel_n = chain_rng(sv.seed, gchain, i + 1, RNG_SELECT);
+            dn = de_select(sv, ra, chain, gchain, i + 1, sel_n);
+        }
+        if (dn.use) {
+            const size_t hcur = hist_off(sv, i, chain);
+            hz1 = dn.o1 == hcur; hz2 = dn.o2 == hcur;     // a row this step is about to write: taken from registers below
+#pragma unroll
+            for (int d = 0; d < ND; d++) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(z1a + d * 512u), "l"(sv.hist + dn.o1 + d) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(z2a + d * 512u), "l"(sv.hist + dn.o2 + d) : "memory");
+            }
+        }
+        // ---- proposal, transforms, priors
+        // the value registers the CE model reads: 0 log10 Ae, 1 log10 F, 2 E, 3 m, 4 b, VAL_NU (every dimension overwrites
+        // its register in every step, so starting from the defaults each time is the same as carrying them)
+        double val[6];
+#pragma unroll
+        for (int k = 0; k < 5; k++) val[k] = sv.val_defaults[k];
+        val[5] = sv.val_defaults[VAL_NU];
+        double lps = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; d++) {
+            double qn = qs[d];
+            if (ra.mode == 0) {
+                double eps = proposal_noise(sv.proposal_dist, chain_rng(sv.seed, gchain, i, (unsigned int)d));
+                if (use_de) qn += (jump ? 1.0 : lamb) * dz[d];
+                qn += eps * scal;
+            }
+            qp[d * 64] = qn;
+            double v;
+            lps += transform_dim(sv.pr[d], qn, v);
+            vp[d * 64] = v;
+            const int tg = sv.pr[d].target;
+#pragma unroll
+            for (int k = 0; k < 5; k++) val[k] = tg == k ? v : val[k];
+            val[5] = tg == VAL_NU ? v : val[5];
+        }
+        // ---- forward model + likelihood: as in k_mcmc_ng
+        double Ae = exp10(val[0]), F = exp10(val[1]), E = val[2];
+        double T = (E - val[4]) / val[3];
+        double P = ce_lapse_rate_step(E);
+        const CeStep cs = ce_step(T, P);
+        double nu = sv.nu_sampled ? sv.nu_lo + (sv.nu_hi - sv.nu_lo) * val[5] : sv.nu_fixed;
+        double cst = sv.lik_kind == 1 ? lik_studentt_const(nu) : 0.0;
+        double ll = 0.0;
+        for (int g = 0; g < sv.gases.n; g++) {
+            double mu = ce_exc_step(sv.gases.id[g], cs, E, T, Ae, F, P);
+            double ob = sv.cpg > 0 ? sv.g_obs[grp * sv.gases.n + g] : sv.obs[g];
+            double is = sv.cpg > 0 ? sv.g_isd[grp * sv.gases.n + g] : sv.isd[g];
+            double lc = sv.cpg > 0 ? sv.g_lc[grp * sv.gases.n + g] : sv.lc[g];
+            ll += sv.lik_kind == 1 ? lik_term_studentt(ob, mu, is, lc, nu, cst) : lik_term_normal(ob, mu, is, lc);
+        }
+        double lpn = lps + ll;
+        double delta = lpn - logp;
+        bool acc = ra.mode == 1 || (isfinite(delta) && log(u01(sel.z, sel.w)) < delta);
+        if (acc) {
+#pragma unroll
+            for (int d = 0; d < ND; d++) { qs[d] = qp[d * 64]; vn[d * 64] = vp[d * 64]; }
+            logp = lpn;
+            if (ra.mode == 0) { acc_win++; acc_tot++; }
+        }
+        if (ra.mode == 0) {
+            size_t ho = hist_off(sv, i, chain);
+#pragma unroll
+            for (int d = 0; d < ND; d++) sv.hist[ho + d] = qs[d];
+            if (ra.record && ((i - ra.step0) % ra.thin) == 0) {
+                long long draw = ra.draw0 + (i - ra.step0) / ra.thin;
+#pragma unroll
+                for (int d = 0; d < ND; d++) {          // record_dim() on the shared-memory copy
+                    const double v = vn[d * 64];
+                    if (ra.trace) ra.trace[((size_t)(draw - ra.draw0) * (size_t)sv.B + (size_t)chain) * ND + d] = v;
+                    const double n = (double)(draw + 1);
+                    double mean = wmean[d * 64];
+                    const double dl = v - mean;
+                    mean += dl / n;
+                    wmean[d * 64] = mean;
+                    wm2[d * 64] += dl * (v - mean);
+                }
+            }
+        }
+        // ---- hand the prefetched rows to the next step
+        sel = sel_n;
+        use_de = dn.use; jump = dn.jump;
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        if (use_de) {
+#pragma unroll
+            for (int d = 0; d < ND; d++) dz[d] = (hz1 ? qs[d] : z1s[d * 64]) - (hz2 ? qs[d] : z2s[d * 64]);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < ND; d++) sv.q[chain * ND + d] = qs[d];
+    if (rec) {
+#pragma unroll
+        for (int d = 0; d < ND; d++) { sv.wf_mean[chain * ND + d] = wmean[d * 64]; sv.wf_m2[chain * ND + d] = wm2[d * 64]; }
+    }
+    sv.logp[chain] = logp;
+    sv.lamb[chain] = lamb;
+    sv.scal[chain] = scal;
+    sv.acc_win[chain] = acc_win;
+    sv.acc_tot[chain] = acc_tot;
+}
+
 __global__ void k_philox_kat(uint4 c, uint2 k, unsigned int* out) {
     uint4 r = philox4x32_10(c, k);
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;

@@ -311,3 +311,45 @@ def test_g_tp_holds_the_decayed_weights():
     a = m.convolve()
     m.C_t.iloc[:, 0] *= 2.0
     assert abs(m.convolve() - 2.0 * a) <= 1e-12 * abs(a)
+
+
+_NG_STATE_SCRIPT = r"""
+import json, os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+from noblegas_rtd_mcmc_b200.noble_gas_mcmc import mcmc_model
+from noblegas_rtd_mcmc_b200.sampler import Sampler
+fx = json.load(open(os.path.join(sys.argv[1], "noblegas_rtd_mcmc_b200", "data", "ng_obs_plm.json")))["wells"]["PLM1"]
+mdl = mcmc_model(fx["obs"], mcmc_model.well_elev["PLM1"])
+out = {}
+for name, kw in (("own", dict(hist_cap=96)), ("pool", dict(hist_cap=64))):
+    smp = Sampler(mdl.build_priors(), mdl.obs_mu, mdl.obs_sd, 777, plan=None, gases=mdl.gases, lik="studentt",
+                  nu_range=(1.0, 30.0), tune_interval=50, seed=5, **kw)
+    if name == "pool":
+        smp.set_population(111)
+    for _ in range(6):
+        smp.run(37, tune=True)              # ring wraps (cap < steps), launches of odd length
+    smp.stop_tuning()
+    tr = smp.run(40, tune=False, record=True, keep_trace=True)
+    out[name + "_q"] = smp.get("q").cpu().numpy(); out[name + "_trace"] = tr.cpu().numpy()
+    out[name + "_mean"] = smp.get("mean").cpu().numpy(); out[name + "_lamb"] = smp.get("lamb").cpu().numpy()
+    smp.close()
+np.savez(sys.argv[2], **out)
+"""
+
+
+def test_ng_register_resident_kernel_is_bitwise_the_generic_one(tmp_path):
+    """k_mcmc_ng_r<6> (state in registers, next step's history rows fetched by cp.async one step ahead) against the
+    run-time-nd kernel k_mcmc_ng (NGRTD_NG_GENERIC=1): identical positions, trace, moments and tuned lambda, with the
+    chain's own history (incl. the hazard of selecting the row just appended, and ring wrap-around) and with a shared
+    population archive."""
+    import sys
+    res = {}
+    for tag, env in (("r", {}), ("generic", {"NGRTD_NG_GENERIC": "1"})):
+        path = str(tmp_path / (tag + ".npz"))
+        e = dict(os.environ); e.update(env)
+        subprocess.run([sys.executable, "-c", _NG_STATE_SCRIPT, ROOT, path], check=True, env=e, timeout=600)
+        res[tag] = np.load(path)
+    for k in res["r"].files:
+        assert np.array_equal(res["r"][k], res["generic"][k]), k
+    assert np.isfinite(res["r"]["own_trace"]).all() and res["r"]["own_trace"].std() > 0

@@ -14,7 +14,7 @@ warm = Sampler(mdl.build_priors(), mdl.obs_mu, mdl.obs_sd, 64, plan=None, gases=
 warm.run(4, tune=True); warm.close()
 for rep in range(2):
     t0 = T()
-    ngs = Sampler(mdl.build_priors(), mdl.obs_mu, mdl.obs_sd, 65536, plan=None, gases=mdl.gases, lik="studentt",
+    ngs = Sampler(mdl.build_priors(), mdl.obs_mu, mdl.obs_sd, int(sys.argv[1]) if len(sys.argv) > 1 else 65536, plan=None, gases=mdl.gases, lik="studentt",
                   nu_range=(1.0, 30.0), tune_interval=5000, hist_cap=2048, seed=123423)
     t1 = T(); ngs.run(10000, tune=True); t2 = T(); ngs.stop_tuning(); t3 = T(); ngs.run(5000, tune=False, record=True); t4 = T()
     summ = ngdist.global_summary(5000, ngs.get("mean"), ngs.get("m2")); t5 = T()
