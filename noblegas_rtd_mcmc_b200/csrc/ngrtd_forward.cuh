@@ -728,7 +728,9 @@ struct WarpTiles {
             if constexpr (LOOP1 || LOOP2) {
                 const double den = (LOOP1 && (!LOOP2 || (j & 1) == 0)) ? S1 : S2;
                 const double rr = __ddiv_rn(1.0, den);
-                use_div = (LOOP1 && fabs(S1) < 1e-290) || (LOOP2 && fabs(S2) < 1e-290);   // per chain, not per warp
+                // (S == 0 exactly -- every weight masked or flushed -- needs no division either: all weights are >= 0, so the
+                //  column sums are 0 as well and 0 * (1/0) = 0 * inf = NaN is the reference's 0/0 = NaN)
+                use_div = (LOOP1 && S1 != 0.0 && fabs(S1) < 1e-290) || (LOOP2 && S2 != 0.0 && fabs(S2) < 1e-290);   // per chain, not per warp
                 any_div = __any_sync(full, use_div);
                 if constexpr (LOOP1) r1 = __shfl_sync(full, rr, lane & ~3);
                 if constexpr (LOOP2) r2 = __shfl_sync(full, rr, (lane & ~3) + (LOOP1 ? 1 : 0));

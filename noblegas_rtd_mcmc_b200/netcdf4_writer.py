@@ -251,7 +251,7 @@ def write_trace(path, posterior, sample_stats=None, observed_data=None, attrs=No
     arrays are 1-D.  attrs: group attributes (created_at, arviz_version, inference_library, sampling_time, tuning_steps ...)
     written on every group, as ArviZ does."""
     import datetime
-    ga = {"created_at": datetime.datetime.utcnow().isoformat(), "arviz_version": "0.11.4-compatible",
+    ga = {"created_at": datetime.datetime.now(datetime.timezone.utc).replace(tzinfo=None).isoformat(), "arviz_version": "0.11.4-compatible",
           "inference_library": "ngrtd-b200", "inference_library_version": "2"}
     ga.update(attrs or {})
     groups = {}
