@@ -383,12 +383,32 @@ def main():
     barrier()
     h2d_ms = max_over_ranks(pe0.elapsed_time(pe1) / 50)
     h2d_bytes = B * len(pn_h) * 8
+    # the same with the result copies of the e2e path going the other way at the same time (second stream): what the host
+    # link of this box sustains for the step's traffic in BOTH directions
+    s_out = torch.cuda.Stream(device=dev)
+    dlp = torch.zeros(B, dtype=torch.float64, device=dev)
+    de0, de1, de2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    barrier()
+    de0.record(stream)
+    s_out.wait_event(de0)
+    for i in range(50):
+        dth.copy_(host_thetas[i % 8], non_blocking=True)
+        with torch.cuda.stream(s_out):
+            host_logps[i % DEPTH].copy_(dlp, non_blocking=True)
+    de1.record(stream)
+    de2.record(s_out)
+    barrier()
+    s_out.synchronize()
+    duplex_ms = max_over_ranks(max(de0.elapsed_time(de1), de0.elapsed_time(de2)) / 50)
     host_link = {"h2d_ms_per_batch": h2d_ms, "gbps_per_rank": h2d_bytes / h2d_ms / 1e6,
                  "gbps_aggregate": world * h2d_bytes / h2d_ms / 1e6,
                  "e2e_ceiling_evals_per_s": world * B * T_COUNTED / (h2d_ms * 1e-3),
+                 "duplex_ms_per_batch": duplex_ms,
+                 "e2e_ceiling_duplex_evals_per_s": world * B * T_COUNTED / (duplex_ms * 1e-3),
                  "note": "max over ranks of 50 back-to-back cudaMemcpyAsync(H2D) of one theta batch, all ranks concurrently; "
-                         "a host-buffer step cannot be faster than max(this, the kernel)"}
-    del dth
+                         "`duplex`: the same with the logp batch copied D2H on a second stream at the same time.  A "
+                         "host-buffer step cannot be faster than max(this, the kernel)"}
+    del dth, dlp
 
     extras = {}
     if not args.no_extras:
