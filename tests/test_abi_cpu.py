@@ -85,3 +85,44 @@ def test_header_is_plain_c_and_links(lib, tmp_path):
                            os.path.join(ROOT, "examples", "c_abi_demo.c"), "-o", exe, "-L" + os.path.dirname(SO), "-lngrtd",
                            "-Wl,-rpath," + os.path.dirname(SO), "-lm"])
     assert os.path.exists(exe)
+
+
+def test_theano_op_adapters_with_a_stand_in_theano(monkeypatch):
+    """The reference's operator boundary is a Theano Op (run_age_mcmc_utils.py:47-52: itypes [dvector], otypes [dscalar];
+    noble_gas_mcmc.py:205: @as_op dvector -> dvector).  theano / aesara are not in the image, so a stand-in module with the
+    three names the adapters touch checks the wiring: class attributes, perform() delegation, as_op signature."""
+    import sys
+    import types
+    tt = types.ModuleType("theano.tensor")
+    tt.dvector, tt.dscalar = "dvector", "dscalar"
+
+    class Op(object):
+        def __call__(self, x):                       # what theano does when the node is evaluated
+            out = [[None]]
+            self.perform(None, [np.asarray(x, dtype=np.float64)], out)
+            return out[0][0]
+    tt.Op = Op
+    th = types.ModuleType("theano")
+    th.tensor = tt
+    ops = types.ModuleType("theano.compile.ops")
+    seen = {}
+
+    def as_op(itypes, otypes):
+        seen["sig"] = (itypes, otypes)
+        return lambda fn: fn
+    ops.as_op = as_op
+    comp = types.ModuleType("theano.compile")
+    comp.ops = ops
+    for name, mod in (("theano", th), ("theano.tensor", tt), ("theano.compile", comp), ("theano.compile.ops", ops)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    from noblegas_rtd_mcmc_b200 import run_age_mcmc_utils as R
+    from noblegas_rtd_mcmc_b200 import noble_gas_mcmc as N
+
+    class Fwd(object):                               # anything with the reference's perform(node, inputs, outputs)
+        def perform(self, node, inputs, outputs):
+            outputs[0][0] = np.array(float(np.sum(inputs[0])) * 2.0)
+    op = R.as_theano_op(Fwd())
+    assert isinstance(op, Op) and type(op).itypes == ["dvector"] and type(op).otypes == ["dscalar"]
+    assert float(op([1.0, 2.5])) == 7.0
+    wrapped = N.as_theano_op(["He", "Ne"])
+    assert seen["sig"] == (["dvector"], ["dvector"]) and callable(wrapped)
