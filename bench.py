@@ -327,8 +327,19 @@ def main():
     # theta crosses the host link without its redundant f2 = 1 - f1 column (48 instead of 56 bytes per chain): the
     # "f1_f2c" column alias (NGRTD_P_F1_COMPLEMENT) forms f2 on the device, bit-identical to the column theta_cfg3 carries
     pn_h = ["tau1", "tau2", "f1_f2c", "eta1", "D2", "J"]
-    host_thetas = [torch.from_numpy(np.ascontiguousarray(np.delete(synthetic.theta_cfg3(B, seed=77 + 1000 * i + rank), 3, axis=1))).pin_memory()
-                   for i in range(8)]
+    # theta batches live in write-combined pinned memory (ngrtd_host_alloc; the CPU only writes them): on this pool plain
+    # pinned buffers of some processes copy at 28-34 GB/s instead of 52 (profiles/r2_notes.md); NGRTD_BENCH_WC=0 = plain pinned.
+    # The probe below measures both kinds.
+    use_wc = os.environ.get("NGRTD_BENCH_WC", "1") == "1"
+    host_thetas = []
+    for i in range(8):
+        th_i = np.ascontiguousarray(np.delete(synthetic.theta_cfg3(B, seed=77 + 1000 * i + rank), 3, axis=1))
+        if use_wc:
+            wc = _lib.host_array(th_i.shape, write_combined=True)
+            wc[...] = th_i
+            host_thetas.append(torch.from_numpy(wc))
+        else:
+            host_thetas.append(torch.from_numpy(th_i).pin_memory())
     host_logp = torch.empty(B, dtype=torch.float64).pin_memory()
     hl = host_logp.numpy()
 
@@ -383,6 +394,23 @@ def main():
     barrier()
     h2d_ms = max_over_ranks(pe0.elapsed_time(pe1) / 50)
     h2d_bytes = B * len(pn_h) * 8
+    # the same copies from WRITE-COMBINED pinned memory (not snooped): is the link or the host's coherence the limit?
+    wcs = []
+    for i in range(4):
+        w = _lib.host_array(host_thetas[0].shape, write_combined=True)
+        w[...] = 0.25
+        wcs.append(torch.from_numpy(w))
+    for i in range(5):
+        dth.copy_(wcs[i % 4], non_blocking=True)
+    we0, we1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    we0.record(stream)
+    for i in range(50):
+        dth.copy_(wcs[i % 4], non_blocking=True)
+    we1.record(stream)
+    barrier()
+    h2d_wc_ms = max_over_ranks(we0.elapsed_time(we1) / 50)
+    del wcs
     # the same with the result copies of the e2e path going the other way at the same time (second stream): what the host
     # link of this box sustains for the step's traffic in BOTH directions
     s_out = torch.cuda.Stream(device=dev)
@@ -403,6 +431,7 @@ def main():
     host_link = {"h2d_ms_per_batch": h2d_ms, "gbps_per_rank": h2d_bytes / h2d_ms / 1e6,
                  "gbps_aggregate": world * h2d_bytes / h2d_ms / 1e6,
                  "e2e_ceiling_evals_per_s": world * B * T_COUNTED / (h2d_ms * 1e-3),
+                 "h2d_ms_per_batch_write_combined": h2d_wc_ms, "theta_buffers": "write-combined" if use_wc else "pinned",
                  "duplex_ms_per_batch": duplex_ms,
                  "e2e_ceiling_duplex_evals_per_s": world * B * T_COUNTED / (duplex_ms * 1e-3),
                  "note": "max over ranks of 50 back-to-back cudaMemcpyAsync(H2D) of one theta batch, all ranks concurrently; "

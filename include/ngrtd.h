@@ -88,6 +88,13 @@ int ngrtd_version(void);
 #define NGRTD_FEATURE_XF_SWIZZLE 2  /* -DNGRTD_XF_SWIZZLE: half-warp-contiguous layout of the folded tables */
 #define NGRTD_FEATURE_TP_DADD 4     /* -DNGRTD_TP_DADD: lag value carried in a register */
 int ngrtd_build_features(void);
+
+/* Page-locked host buffers for the *_host entry points, for callers that have no CUDA runtime binding of their own (the
+ * reference is numpy: `np.frombuffer((ctypes.c_double * n).from_address(p))` views the block).  write_combined != 0 asks for
+ * write-combined memory (cudaHostAllocWriteCombined): not snooped on the way to the device -- meant for theta buffers the CPU
+ * only WRITES; reading it back on the CPU is slow.  Replaces nothing in the reference (its arrays are pageable numpy). */
+int ngrtd_host_alloc(void** out, size_t bytes, int32_t write_combined);
+int ngrtd_host_free(void* p);
 const char* ngrtd_last_error(void);
 
 /* ---- plan: replaces tracer_conv_integral.__init__(C_t, t_samp) (conv utils :105-108) and the

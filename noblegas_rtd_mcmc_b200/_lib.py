@@ -62,6 +62,8 @@ _vp, _i32, _i64, _dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.
 _PROTOS = {
     "ngrtd_version": ([], ctypes.c_int),
     "ngrtd_build_features": ([], ctypes.c_int),
+    "ngrtd_host_alloc": ([ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t, ctypes.c_int32], ctypes.c_int),
+    "ngrtd_host_free": ([ctypes.c_void_p], ctypes.c_int),
     "ngrtd_last_error": ([], ctypes.c_char_p),
     "ngrtd_plan_create": ([ctypes.POINTER(_vp), _i32, _i32, _vp, _vp, _dbl, _i32, ctypes.POINTER(Tracer), _i32, _i32, _i32], ctypes.c_int),
     "ngrtd_plan_destroy": ([_vp], ctypes.c_int),
@@ -106,6 +108,32 @@ EXPORTED = tuple(_PROTOS)
 def check(rc):
     if rc != 0:
         raise NgrtdError("libngrtd error %d: %s" % (rc, lib.ngrtd_last_error().decode()))
+
+
+class _HostBlock(object):
+    """owner of one ngrtd_host_alloc block (freed with the last numpy view)"""
+
+    def __init__(self, nbytes, write_combined):
+        self.p = ctypes.c_void_p()
+        check(lib.ngrtd_host_alloc(ctypes.byref(self.p), nbytes, 1 if write_combined else 0))
+
+    def __del__(self):
+        try:
+            if self.p:
+                lib.ngrtd_host_free(self.p)
+        except Exception:
+            pass
+
+
+def host_array(shape, write_combined=False):
+    """float64 ndarray in page-locked host memory (ngrtd_host_alloc) for the *_host calls; write_combined=True for buffers
+    the CPU only writes (theta batches): faster on the way to the device, slow to read back on the CPU."""
+    shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    n = int(np.prod(shape))
+    blk = _HostBlock(max(n, 1) * 8, write_combined)
+    buf = (ctypes.c_double * max(n, 1)).from_address(blk.p.value)
+    buf._ngrtd_owner = blk                      # the ctypes array (base of every view) keeps the block alive
+    return np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape)
 
 
 def hptr(a):

@@ -96,6 +96,16 @@ static int cls_of(int mod) {
 }
 
 extern "C" int ngrtd_version(void) { return NGRTD_VERSION; }
+extern "C" int ngrtd_host_alloc(void** out, size_t bytes, int32_t write_combined) {
+    if (!out || bytes == 0) return fail(NGRTD_EINVAL, "host_alloc: null pointer or zero size");
+    *out = nullptr;
+    CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)));
+    return NGRTD_OK;
+}
+extern "C" int ngrtd_host_free(void* p) {
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    return NGRTD_OK;
+}
 extern "C" int ngrtd_build_features(void) {
     int f = 0;
     if (DM_TAIL) f |= NGRTD_FEATURE_DM_TAIL;
