@@ -353,3 +353,31 @@ def test_ng_register_resident_kernel_is_bitwise_the_generic_one(tmp_path):
     for k in res["r"].files:
         assert np.array_equal(res["r"][k], res["generic"][k]), k
     assert np.isfinite(res["r"]["own_trace"]).all() and res["r"]["own_trace"].std() > 0
+
+
+def test_library_host_buffers_pinned_and_write_combined():
+    """ngrtd_host_alloc: page-locked (optionally write-combined) buffers for the *_host calls; the blocking call reads them in
+    place, the submit / wait form copies from them -- same numbers as pageable numpy arrays."""
+    import gc
+    from noblegas_rtd_mcmc_b200 import _lib, synthetic
+    pn = list(synthetic.PAR_NAMES_CFG3)
+    X, descs = synthetic.series_matrix_and_descs(pn)
+    plan = _lib.Plan(X, descs, "exp_pist_flow", "dispersion")
+    th = synthetic.theta_cfg3_informative(5000, 3)
+    obs = np.ones(len(descs)); sd = 0.05 * np.ones(len(descs))
+    want = plan.forward_loglik_host(th, pn, obs, sd, "normal")
+    for wc in (False, True):
+        buf = _lib.host_array(th.shape, write_combined=wc)
+        assert buf.shape == th.shape and buf.dtype == np.float64
+        buf[...] = th
+        out = _lib.host_array(len(th))
+        got = plan.forward_loglik_host(buf, pn, obs, sd, "normal", logp_out=out)
+        assert np.allclose(got, want, rtol=1e-12, atol=0, equal_nan=True) and np.isfinite(want).any()
+        out2 = _lib.host_array(len(th))
+        plan.forward_loglik_host_submit(buf, pn, obs, sd, "normal", logp_out=out2, slot=1)
+        plan.host_wait(1)
+        assert np.allclose(out2, want, rtol=1e-12, atol=0, equal_nan=True)
+        del buf, out, out2, got
+        gc.collect()                                     # blocks are freed with their last view
+    with pytest.raises(_lib.NgrtdError):
+        _lib.check(_lib.lib.ngrtd_host_alloc(None, 8, 0))
