@@ -439,6 +439,13 @@ def main():
                          "host-buffer step cannot be faster than max(this, the kernel)"}
     del dth, dlp
 
+    # the FP64 peak of THIS GPU, measured now (ngrtd_fp64_peak_probe: DFMA and DMMA m8n8k4 loops): printed beside the
+    # constant the fraction is taken against, so that a reader can re-derive frac against either
+    peak_live = None
+    if rank == 0:
+        pk = _lib.fp64_peak_probe(local)
+        peak_live = {"dfma_tflops": pk["dfma"], "dmma_tflops": pk["dmma"],
+                     "frac_vs_live_max": F_STEP * B / (kern_ms * 1e-3) / 1e12 / max(pk["dfma"], pk["dmma"])}
     extras = {}
     if not args.no_extras:
         extras = run_extras(args, plan, pn, rank, world, local, dev, stream, barrier, max_over_ranks, timed_regions)
@@ -482,7 +489,7 @@ def main():
                                             "MEASURED_PEAKS.json has no FP64 entry",
                              "kernel": "k_forward<G,D>", "kernel_ms": kern_ms, "kernel_ms_isolated": kern_iso_ms,
                              "frac_isolated": F_STEP * B / (kern_iso_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
-                             "flops_per_chain": F_STEP,
+                             "flops_per_chain": F_STEP, "peak_live": peak_live,
                              "note": "kernel_ms = average launch duration over the timed region (launches back to back: "
                                      "programmatic dependent launch lets launch i+1 set up under the tail of launch i); "
                                      "kernel_ms_isolated = median of launches bracketed one by one"},

@@ -95,6 +95,11 @@ int ngrtd_build_features(void);
  * only WRITES; reading it back on the CPU is slow.  Replaces nothing in the reference (its arrays are pageable numpy). */
 int ngrtd_host_alloc(void** out, size_t bytes, int32_t write_combined);
 int ngrtd_host_free(void* p);
+
+/* Measured FP64 peak of a device in TFLOP/s (kind 0: DFMA, 1: DMMA m8n8k4 -- the two share one pipe on sm_100): the roofline
+ * denominator bench.py reports against, measured in the same process (the pool's MEASURED_PEAKS.json has no FP64 entry).
+ * device < 0: current device.  Measurement aid, replaces nothing in the reference. */
+int ngrtd_fp64_peak_probe(int32_t device, int32_t kind, double* tflops_out);
 const char* ngrtd_last_error(void);
 
 /* ---- plan: replaces tracer_conv_integral.__init__(C_t, t_samp) (conv utils :105-108) and the

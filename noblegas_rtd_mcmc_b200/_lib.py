@@ -64,6 +64,7 @@ _PROTOS = {
     "ngrtd_build_features": ([], ctypes.c_int),
     "ngrtd_host_alloc": ([ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t, ctypes.c_int32], ctypes.c_int),
     "ngrtd_host_free": ([ctypes.c_void_p], ctypes.c_int),
+    "ngrtd_fp64_peak_probe": ([ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_double)], ctypes.c_int),
     "ngrtd_last_error": ([], ctypes.c_char_p),
     "ngrtd_plan_create": ([ctypes.POINTER(_vp), _i32, _i32, _vp, _vp, _dbl, _i32, ctypes.POINTER(Tracer), _i32, _i32, _i32], ctypes.c_int),
     "ngrtd_plan_destroy": ([_vp], ctypes.c_int),
@@ -108,6 +109,16 @@ EXPORTED = tuple(_PROTOS)
 def check(rc):
     if rc != 0:
         raise NgrtdError("libngrtd error %d: %s" % (rc, lib.ngrtd_last_error().decode()))
+
+
+def fp64_peak_probe(device=-1):
+    """measured FP64 peak of a device: {"dfma": TFLOP/s, "dmma": TFLOP/s} (ngrtd_fp64_peak_probe)"""
+    out = {}
+    for name, kind in (("dfma", 0), ("dmma", 1)):
+        v = ctypes.c_double()
+        check(lib.ngrtd_fp64_peak_probe(int(device), kind, ctypes.byref(v)))
+        out[name] = v.value
+    return out
 
 
 class _HostBlock(object):

@@ -1697,3 +1697,73 @@ extern "C" int ngrtd_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2],
     if (e != cudaSuccess) return fail(NGRTD_ECUDA, cudaGetErrorString(e));
     return NGRTD_OK;
 }
+
+// ---------------------------------------------------------------- FP64 peak probe (roofline denominator, measured live)
+// MEASURED_PEAKS.json of the pool has no FP64 entry; bench.py calls this so that the roofline fraction it prints is taken
+// against a number measured in the same process on the same GPU (tools/microbench/fp64_peak.cu is the stand-alone study).
+namespace {
+constexpr int PEAK_ITERS = 4096, PEAK_ACC = 16;
+__global__ void __launch_bounds__(256) k_peak_dfma(double* out, double a, double b) {
+    double acc[PEAK_ACC];
+#pragma unroll
+    for (int i = 0; i < PEAK_ACC; i++) acc[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < PEAK_ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < PEAK_ACC; i++) acc[i] = fma(acc[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < PEAK_ACC; i++) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) k_peak_dmma(double* out, double a, double b) {
+    double c0[8], c1[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c0[i] = threadIdx.x * 1e-3 + i; c1[i] = i; }
+    for (int it = 0; it < PEAK_ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += c0[i] + c1[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+extern "C" int ngrtd_fp64_peak_probe(int32_t device, int32_t kind, double* tflops_out) {
+    if (!tflops_out) return fail(NGRTD_EINVAL, "peak probe: null pointer");
+    if (kind != 0 && kind != 1) return fail(NGRTD_EINVAL, "peak probe: kind must be 0 (DFMA) or 1 (DMMA m8n8k4)");
+    int dev = device;
+    if (dev < 0) CUDA_TRY(cudaGetDevice(&dev));
+    DeviceGuard guard(dev);
+    if (!guard.ok()) return fail(NGRTD_ECUDA, "peak probe: cudaSetDevice failed");
+    int nsm = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = nsm * 4, threads = 256;             // 4 CTAs of 8 warps per SM: 8 warps per sub-partition
+    double* d = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; rep++) {                   // first repetition warms up
+        cudaEventRecord(e0);
+        if (kind == 0) k_peak_dfma<<<blocks, threads>>>(d, 1.0000001, 1e-9);
+        else k_peak_dmma<<<blocks, threads>>>(d, 1.0000001, 1e-9);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    if (e != cudaSuccess) return fail(NGRTD_ECUDA, cudaGetErrorString(e));
+    // flops: DFMA = 2 per lane-instruction; DMMA m8n8k4 = 8*8*4*2 = 512 per warp-instruction
+    const double flops = kind == 0 ? 2.0 * PEAK_ACC * PEAK_ITERS * (double)blocks * threads
+                                   : 512.0 * 8 * PEAK_ITERS * (double)blocks * (threads / 32);
+    *tflops_out = flops / (best * 1e-3) / 1e12;
+    return NGRTD_OK;
+}
