@@ -80,6 +80,8 @@ struct ngrtd_plan {
         double *theta = nullptr, *nu = nullptr, *logp = nullptr, *out = nullptr;
         size_t theta_n = 0, nu_n = 0, logp_n = 0, out_n = 0;
         cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_done = nullptr;
+        cudaStream_t s_k = nullptr;     // the slot's own kernel stream: kernels of different slots are NOT stream-ordered, so the
+                                        // CTAs of batch i+1 move onto SMs as the CTAs of batch i retire (no tail / head gap)
         bool busy = false;
     } slots[NGRTD_HOST_SLOTS];
 };
@@ -321,6 +323,7 @@ extern "C" int ngrtd_plan_create(ngrtd_plan** out, int32_t L, int32_t nseries, c
         e = cudaEventCreateWithFlags(&P->slots[i].ev_in, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&P->slots[i].ev_k, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&P->slots[i].ev_done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&P->slots[i].s_k, cudaStreamNonBlocking);
     }
     if (e != cudaSuccess) {
         ngrtd_plan_destroy(P);
@@ -365,6 +368,7 @@ extern "C" int ngrtd_plan_destroy(ngrtd_plan* P) {
         if (sl.ev_in) cudaEventDestroy(sl.ev_in);
         if (sl.ev_k) cudaEventDestroy(sl.ev_k);
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+        if (sl.s_k) cudaStreamDestroy(sl.s_k);
     }
     delete P;
     return NGRTD_OK;
@@ -762,7 +766,7 @@ extern "C" int ngrtd_forward_loglik_host_submit(ngrtd_plan* P, const double* the
     if ((rc = grow(&sl.logp, &sl.logp_n, (size_t)B))) return rc;
     if (model_out_h && (rc = grow(&sl.out, &sl.out_n, (size_t)B * nt))) return rc;
     if (need_nu && (rc = grow(&sl.nu, &sl.nu_n, (size_t)B))) return rc;
-    cudaStream_t s_in = P->hstream, s_k = P->hstream2, s_out = P->hstream3;
+    cudaStream_t s_in = P->hstream, s_k = sl.s_k, s_out = P->hstream3;
     CUDA_TRY(cudaMemcpyAsync(sl.theta, theta_h, (size_t)B * ndim * sizeof(double), cudaMemcpyHostToDevice, s_in));
     if (need_nu) CUDA_TRY(cudaMemcpyAsync(sl.nu, nu_h, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, s_in));
     CUDA_TRY(cudaEventRecord(sl.ev_in, s_in));
