@@ -331,10 +331,41 @@ __device__ __noinline__ void dm_tail(int ct_off, double tau, double D, int dead_
         const double lo = Kc - 0.5 + dtp, hi = Ld - 0.5 + dtp;
         const double c4 = 1.0 / (4.0 * D * tau), a = tau / (4.0 * D);
         const double sig = fmax(tau * sqrt(2.0 * D), 1.0);
-        const bool quad = D >= 0.01 && D <= 2.5 && tau - 12.0 * sig <= hi;
+        bool quad = D >= 0.01 && D <= 2.5 && tau - 12.0 * sig <= hi;
+        double wlo = fmax(lo, tau - 12.0 * sig);
+        double whi = fmin(hi, fmax(fmax(tau + 60.0 * sig, tau + 200.0 * D * tau), lo + 1.0));
+        // |d log w / dt| at t: the rate at which the integrand changes per lag
+        auto rate = [&](double t) { const double it = 1.0 / t; return fabs((-1.5 + a * it) * it - c4); };
+        // The two-term Euler-Maclaurin end correction is only as good as the integrand is smooth AT the end point (next term
+        // 31 g5 / 967680 ~ 3.2e-5 rate^5 g): when an end carries weight and the weights change fast there -- mode far beyond
+        // the last lag, weights growing by a factor > 1.05 per lag towards it -- the end point is moved inwards, 4 lags at a
+        // time, until that term is below 1e-14 of the window's largest weight, and the lags cut off are summed one by one.
+        // (found by tools/fuzz_forward.py: 2e-7 .. 8e-7 in the lag-index column for tau = 11 .. 26 window lengths, D = 0.01)
+        int mlo = 0, mhi = 0;
         if (quad) {
-            const double wlo = fmax(lo, tau - 12.0 * sig);
-            const double whi = fmin(hi, fmax(fmax(tau + 60.0 * sig, tau + 200.0 * D * tau), lo + 1.0));
+            const double tmx = fmin(fmax(tau, 1e-5 + dtp), hi - 0.5);
+            const double ltm = 1.5 * log(tmx), dm = tmx - tau, lwm = -dm * dm * c4 / tmx;    // log of the largest weight
+            auto em_bad = [&](double t) {
+                const double dt = t - tau;
+                const double lw = -dt * dt * c4 / t - lwm + ltm - 1.5 * log(t);             // log(weight / largest weight)
+                return -10.35 + 5.0 * log(rate(t)) + lw > -32.2;                           // log 3.2e-5, log 1e-14
+            };
+            constexpr int EM_CAP = 4096;
+            if (wlo == lo) while (mlo < EM_CAP && em_bad(lo + mlo)) mlo += 4;
+            if (whi == hi) while (mhi < EM_CAP && em_bad(hi - mhi)) mhi += 4;
+            if (mlo >= EM_CAP || mhi >= EM_CAP || lo + mlo + 1.0 >= hi - mhi) quad = false;
+        }
+        if (quad) {
+            if (mlo | mhi) {
+                const int ka = (int)Kc, kb = (int)Ld;
+#pragma unroll 1
+                for (int k = ka + j; k < ka + mlo; k += 4) dm_node<DYN>(cv, (double)k + dtp, 1.0, tau, c4, sh, acc, lam_dyn, accd);
+#pragma unroll 1
+                for (int k = kb - mhi + j; k < kb; k += 4) dm_node<DYN>(cv, (double)k + dtp, 1.0, tau, c4, sh, acc, lam_dyn, accd);
+            }
+            const double elo = lo + mlo, ehi = hi - mhi;          // end points of the integral (half a lag outside the kept lags)
+            if (wlo == lo) wlo = elo;
+            if (whi == hi) whi = ehi;
             if (whi > wlo) {
                 const double w = 0.5 * sig;
                 double x = wlo;
@@ -342,6 +373,9 @@ __device__ __noinline__ void dm_tail(int ct_off, double tau, double D, int dead_
                     const double ad = fabs(x - tau);
                     double step = (ad < 6.0 * sig) ? w : fmax(w, 0.25 * ad);
                     step = fmin(step, 0.35 * x);
+                    // a 16-node panel integrates exp(c x) on [-1, 1] to 1e-14 up to c ~ 4: keep rate * half-width below that
+                    // (left of the mode the rate falls with t, right of it it is bounded by c4 + 1.5 / t)
+                    step = fmin(step, 8.0 / fmax(x < tau ? rate(x) : c4 + 1.5 / x, 1e-300));
                     const double x1 = fmin(whi, x + step);
                     {   // the 4 lanes of the chain take 4 of the panel's 16 nodes each (no divergence inside a chain)
                         const double mid = 0.5 * (x1 + x), half = 0.5 * (x1 - x);
@@ -354,8 +388,8 @@ __device__ __noinline__ void dm_tail(int ct_off, double tau, double D, int dead_
                     }
                     x = x1;
                 }
-                if (j == 0 && wlo == lo) dm_end<DYN>(cv, lo, 1.0, tau, a, c4, sh, acc, lam_dyn, accd);
-                if (j == 1 && whi == hi) dm_end<DYN>(cv, hi, -1.0, tau, a, c4, sh, acc, lam_dyn, accd);
+                if (j == 0 && wlo == elo) dm_end<DYN>(cv, elo, 1.0, tau, a, c4, sh, acc, lam_dyn, accd);
+                if (j == 1 && whi == ehi) dm_end<DYN>(cv, ehi, -1.0, tau, a, c4, sh, acc, lam_dyn, accd);
             }
         } else {
             const int k0 = (int)Kc, k1 = (int)Ld;

@@ -1,0 +1,13 @@
+#!/bin/bash
+timeout 900 python tools/fuzz_forward.py 300 1 2>&1 | tail -12
+timeout 900 python tools/fuzz_forward.py 300 2 2>&1 | tail -12
+timeout 600 python -m pytest tests -m gpu -q -x -k "tail or dm_ or extreme or golden or edges" 2>&1 | tail -3
+python - <<'PY'
+import json
+import sys
+sys.path.insert(0,'.')
+PY
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print('value %.4g frac %.4f cfg2 %.4f cfg2_disp %.4f cfg5 %.4f sampler %.4g' % (d['value'], d['roofline']['frac'], d['cfg2']['kernel_ms'], d['cfg2_dispersion']['kernel_ms'], d['cfg5']['kernel_ms'], d['sampler']['value']))"
