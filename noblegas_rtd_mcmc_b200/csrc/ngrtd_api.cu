@@ -489,12 +489,12 @@ static int launch_forward(ngrtd_plan* P, const SlotMap& sm, const double* theta,
 #ifdef NGRTD_TUNE
     // development build: every (NT, UA) variant of the looped kernels is compiled and selectable by env var
     if constexpr (!DYN && C1 != CLS_P && C2 != CLS_P) {
-        int mw = (t.warps > 16) ? 24 : (t.warps > 8) ? 16 : 8;
+        int mw = (t.warps > 16) ? 24 : (t.warps > 12) ? 16 : (t.warps > 8) ? 12 : 8;
 #define NGRTD_VARIANT(NT_, UA_, MW_) \
         if (t.nt == NT_ && t.ua == UA_ && mw == MW_) return launch_forward_t<C1, C2, DYN, NT_, UA_, MW_>(P, sm, theta, B, out, logp, lik, st, stage, t.warps);
         NGRTD_VARIANT(1, 2, 8) NGRTD_VARIANT(2, 1, 8) NGRTD_VARIANT(2, 2, 8) NGRTD_VARIANT(4, 1, 8)
         NGRTD_VARIANT(1, 1, 16) NGRTD_VARIANT(1, 2, 16) NGRTD_VARIANT(2, 2, 16) NGRTD_VARIANT(3, 1, 16)
-        NGRTD_VARIANT(1, 1, 24) NGRTD_VARIANT(2, 1, 24)
+        NGRTD_VARIANT(1, 1, 24) NGRTD_VARIANT(2, 1, 24) NGRTD_VARIANT(2, 1, 12) NGRTD_VARIANT(3, 1, 12) NGRTD_VARIANT(4, 1, 12)
 #undef NGRTD_VARIANT
     }
 #endif

@@ -57,6 +57,16 @@ struct ExpCfg<11> {
     static constexpr int BITS = 11, N = 2048, SUB = 2, REP_BITS = NGRTD_TB11_REP_BITS, REP = 1 << REP_BITS, DOUBLES = N * REP, DEG = 2;
     static constexpr double C0 = 0.99966160651623492, C1 = 0.00033833619981139687, C2 = 5.7284155667395806e-08,
                             C3 = 0.0;                         // max rel err 2.0e-13
+    // -DNGRTD_EXP_R32 (experiment, not the default): q(g) = fma(g, C1, r) with r = C0 + C2 g^2 assembled from bits instead of
+    // a second DFMA.  r stays in one binade
+    // ([0.5, 1), ulp 2^-53) and varies by 3 C2 = 1.7e-7 = 1.55e9 ulps < 2^32: r = R0 + N 2^-44, R0 = C0 + C2,
+    // N = round(C2 2^44 (g^2 - 1)) < 2^22 from one FMUL + one FFMA (against the 1.5 2^23 rounding constant) on the FP32 pipe,
+    // added to the LOW word of R0 by one integer shift-add (no carry: lo(R0) + 1.55e9 < 2^32).  The constants and the error
+    // (max rel err of q 2.5e-13, difference to the two-DFMA form zero-mean, <= 5e-14) are printed by tools/exp_r32_prototype.py.
+    // Measured on the B200: parity 5.87e-14, but the cfg-3 launch goes from 0.1014 to 0.1051 ms -- one DFMA less, 19 more
+    // instructions per loop trip (93 -> 112): the loop is as sensitive to issued instructions as to FP64-pipe operations.
+    static constexpr unsigned int R_HI = 0x3feffd3au, R_LO_ADD = 0xf522cf52u;
+    static constexpr float R_KN = 1007753.5f, R_K0 = 11575158.0f;
 };
 // scale of the exponent handed to exp_scaled_bits: t = e * exp_k + FX_MAGIC (units of 2^SUB table steps)
 template <int TB>
@@ -203,7 +213,16 @@ __device__ __forceinline__ double exp_scaled_bits(double t, const double* __rest
 #endif
     double p;
     if constexpr (E::DEG == 3) p = fma(g, fma(g, fma(g, E::C3, E::C2), E::C1), E::C0);
+#ifdef NGRTD_EXP_R32
+    else {
+        // experiment (r2 session 3, measured SLOWER: 0.1014 -> 0.1051 ms, see ExpCfg<11>): r = C0 + C2 g^2 from bits
+        const float gf = __uint_as_float(0x3F800000u | ((lo << E::SUB) >> 9));
+        const float mf = __fmaf_rn(__fmul_rn(gf, gf), E::R_KN, E::R_K0);
+        p = fma(g, E::C1, __hiloint2double((int)E::R_HI, (int)((__float_as_uint(mf) << 9) + E::R_LO_ADD)));
+    }
+#else
     else p = fma(g, fma(g, E::C2, E::C1), E::C0);
+#endif
     // entry j = (low bits of floor(ep)) : (top SUB bits of lo) of this lane's copy.  tbl_lane = byte offset of the lane's
     // copy from the start of the kernel's dynamic shared memory (the table sits at its very beginning): the masked index
     // and the copy select merge into one LOP3, and the base is the immediate of the load.
