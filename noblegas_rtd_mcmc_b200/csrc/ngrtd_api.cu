@@ -1223,28 +1223,20 @@ struct ngrtd_sampler {
 
 static double lbeta(double a, double b) { return std::lgamma(a) + std::lgamma(b) - std::lgamma(a + b); }
 
-template <int C1, int C2, bool DYN, bool TAIL>
-static int launch_mcmc_age_t(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st) {
+// shared memory of k_mcmc_age<..., TB> for a lag chunk of lc_cap lags: forward tables + one record per resident chain + priors
+template <class WT>
+static size_t mcmc_age_smem(int warps, int lc_cap, int ndr) {
+    size_t sh = (size_t)fwd_smem_doubles<WT>(warps, lc_cap, false);
+    sh += (size_t)warps * WT::NTILES * 8 * ch_rec_doubles(ndr) + (sizeof(PriorDev) * ND_MAX + 7) / 8;
+    return sh * sizeof(double);
+}
+
+template <int C1, int C2, bool DYN, bool TAIL, int TB, int NDR>
+static int launch_mcmc_age_tb(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st, int warps, int lc_cap, size_t sh) {
     constexpr int NT = FWD_NT, UA = FWD_UA, MAXW = FWD_MAXW;
-    using WT = WarpTiles<C1, C2, DYN, NT, UA, MCMC_TB, TAIL ? 1 : 0>;
     ngrtd_plan* P = S->plan;
-    const long long B = S->sv.B;
-    long long nunits = (B + NT * 8 - 1) / (NT * 8);
-    int warps = pick_warps(nunits, P->nsm, MAXW);
-    if (warps > 4) warps &= ~3;
-    // shared memory: forward tables + one CH_REC record per resident chain; shrink the lag chunk until it fits
-    const int Lloop = (TAIL && tail_active(P->pv, WT::ANY_G, WT::ANY_D)) ? P->pv.Kc : P->Lpad;
-    int lc_cap = WT::ANY_LOOP ? std::min(Lloop, LC_MAX) : 0;
-    size_t sh = 0;
-    for (;;) {
-        sh = (size_t)fwd_smem_doubles<WT>(warps, lc_cap, false);
-        sh += (size_t)warps * NT * 8 * CH_REC + (sizeof(PriorDev) * ND_MAX + 7) / 8;
-        sh *= sizeof(double);
-        if (sh <= 227 * 1024 || lc_cap <= 64) break;
-        lc_cap = (lc_cap / 2 + 3) & ~3;
-    }
-    if (sh > 227 * 1024) return fail(NGRTD_EINVAL, "sampler: shared-memory budget exceeded");
-    auto kern = k_mcmc_age<C1, C2, DYN, NT, UA, MAXW, TAIL>;
+    const long long nunits = (S->sv.B + NT * 8 - 1) / (NT * 8);
+    auto kern = k_mcmc_age<C1, C2, DYN, NT, UA, MAXW, TAIL, TB, NDR>;
     static thread_local SmemConfigured configured;
     const int dev = (S->device >= 0 && S->device < MAX_DEVICES) ? S->device : 0;
     if (configured.bytes[dev] < sh) {
@@ -1256,6 +1248,42 @@ static int launch_mcmc_age_t(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t s
     kern<<<grid, warps * 32, sh, st>>>(P->pv, S->sv, ra, lc_cap);
     CUDA_TRY(cudaGetLastError());
     return NGRTD_OK;
+}
+
+static bool mcmc_big_table_enabled() {
+    static const bool on = [] { const char* e = getenv("NGRTD_MCMC_TB11"); return !(e && atoi(e) == 0); }();
+    return on;
+}
+
+template <int C1, int C2, bool DYN, bool TAIL>
+static int launch_mcmc_age_t(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st) {
+    constexpr int NT = FWD_NT, UA = FWD_UA, MAXW = FWD_MAXW;
+    using WT = WarpTiles<C1, C2, DYN, NT, UA, MCMC_TB, TAIL ? 1 : 0>;
+    ngrtd_plan* P = S->plan;
+    const long long B = S->sv.B;
+    long long nunits = (B + NT * 8 - 1) / (NT * 8);
+    int warps = pick_warps(nunits, P->nsm, MAXW);
+    if (warps > 4) warps &= ~3;
+    const int Lloop = (TAIL && tail_active(P->pv, WT::ANY_G, WT::ANY_D)) ? P->pv.Kc : P->Lpad;
+    int lc_cap = WT::ANY_LOOP ? std::min(Lloop, LC_MAX) : 0;
+    // dispersion plans with up to ND_SMALL sampler dimensions: compact per-chain records and the 2,048-entry exp table
+    // (quadratic, one DFMA less per weight) when that fits next to the lag tables without shrinking the resident chunk;
+    // otherwise ND_MAX records and the 128-entry table (cubic)
+    if constexpr (WT::ANY_D) {
+        using WTB = WarpTiles<C1, C2, DYN, NT, UA, MCMC_TB_BIG, TAIL ? 1 : 0>;
+        const size_t shb = mcmc_age_smem<WTB>(warps, lc_cap, ND_SMALL);
+        if (S->sv.nd <= ND_SMALL && shb <= SMEM_LIMIT && mcmc_big_table_enabled())
+            return launch_mcmc_age_tb<C1, C2, DYN, TAIL, MCMC_TB_BIG, ND_SMALL>(S, ra, st, warps, lc_cap, shb);
+    }
+    // shrink the lag chunk until the layout fits
+    size_t sh = 0;
+    for (;;) {
+        sh = mcmc_age_smem<WT>(warps, lc_cap, ND_MAX);
+        if (sh <= SMEM_LIMIT || lc_cap <= 64) break;
+        lc_cap = (lc_cap / 2 + 3) & ~3;
+    }
+    if (sh > SMEM_LIMIT) return fail(NGRTD_EINVAL, "sampler: shared-memory budget exceeded");
+    return launch_mcmc_age_tb<C1, C2, DYN, TAIL, MCMC_TB, ND_MAX>(S, ra, st, warps, lc_cap, sh);
 }
 
 // two instantiations per model pair, as for k_forward: with and without the constant-tail code

@@ -85,7 +85,8 @@ __host__ __device__ constexpr unsigned int exp_tbl_fold() {
 #define NGRTD_FWD_TB 11
 #endif
 constexpr int FWD_TB = NGRTD_FWD_TB;      // k_forward
-constexpr int MCMC_TB = 7;      // k_mcmc_age
+constexpr int MCMC_TB = 7;      // k_mcmc_age when shared memory is short (many sampler dimensions, streamed lag tables)
+constexpr int MCMC_TB_BIG = 11; // k_mcmc_age when the 16 KB table fits next to the resident lag tables (launch_mcmc_age_t)
 constexpr double FX_MAGIC = 1572864.0;               // 1.5 * 2^20: ulp 2^-32, integer part biased by 2^19
 
 enum Cls : int { CLS_NONE = 0, CLS_P = 1, CLS_G = 2, CLS_D = 3 };

@@ -18,10 +18,17 @@
 
 namespace ngrtd {
 
-constexpr int ND_MAX = 10;      // sampler dimensions
+#ifndef NGRTD_ND_MAX
+#define NGRTD_ND_MAX 10
+#endif
+constexpr int ND_MAX = NGRTD_ND_MAX;      // sampler dimensions
 constexpr int NVAL = 12;        // value registers: 0..10 = ForwardMod.p_dict slots, 11 = nu_ (raw, in [0,1])
 constexpr int VAL_NU = 11;
-constexpr int CH_REC = ND_MAX + ND_MAX + NVAL + 8;   // per-chain shared-memory record (doubles), age kernel
+// per-chain shared-memory record of the age kernel (doubles): qs[ndr] | qp[ndr] | vals[NVAL] | 8 scalars, ndr = ND_SMALL for
+// samplers of up to 8 dimensions, else ND_MAX (r2 session 3: with ND_MAX the 256 records of a CTA took 80 KB and left no room
+// for the 2,048-entry exp table next to 840 resident lags; 8 dimensions -> 72 KB)
+constexpr int ND_SMALL = 8;
+__host__ __device__ constexpr int ch_rec_doubles(int ndr) { return 2 * ndr + NVAL + 8; }
 enum PriorKind : int { PR_UNIFORM = 0, PR_BETA = 1, PR_NORMAL = 2, PR_HALFNORMAL = 3 };
 
 struct PriorDev {
@@ -225,10 +232,15 @@ __device__ __forceinline__ void record_dim(const SamplerView& sv, const RunArgs&
 
 // ---------------------------------------------------------------- age model: one warp = NT tiles of 8 chains
 // TAIL: the constant-tail code (closed form / quadrature) is compiled in; the launcher picks the instantiation by plan
-template <int C1, int C2, bool DYN, int NT, int UA, int MAXW, bool TAIL>
+// TB: exp table of the dispersion weights (ExpCfg<TB>): 11 when the launcher finds room for it next to the resident lag tables
+//     (one DFMA less per dispersion weight: 0.1324 -> 0.1256 ms per step on the cfg-3 sampler), else 7
+// NDR: dimensions a per-chain record has room for (compile time: a run-time record stride measured 4 % slower -- it stays
+//      live across the lag loop of a kernel that is at its register limit)
+template <int C1, int C2, bool DYN, int NT, int UA, int MAXW, bool TAIL, int TB, int NDR>
 __global__ void __launch_bounds__(MAXW * 32, 1)
 k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
-    FwdCta<C1, C2, DYN, NT, UA, MCMC_TB, TAIL ? 1 : 0> cta(pv);
+    FwdCta<C1, C2, DYN, NT, UA, TB, TAIL ? 1 : 0> cta(pv);
+    constexpr int ndr = NDR, CH_REC = ch_rec_doubles(NDR);
     const int rec_base = cta.setup(lc_cap);
     const int lane = cta.lane, j = lane & 3, r = lane >> 2;
     // prior table in shared memory (dynamic indexing of kernel parameters would be demoted to local memory)
@@ -261,9 +273,9 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
             rec[t] = rec_warp + (t * 8 + r) * CH_REC;
             for (int d = j; d < sv.nd; d += 4) ngrtd_smem[rec[t] + d] = sv.q[cl * sv.nd + d];
 #pragma unroll
-            for (int v = 0; v < NVAL / 4; v++) ngrtd_smem[rec[t] + 2 * ND_MAX + 4 * v + j] = sv.val_defaults[4 * v + j];
+            for (int v = 0; v < NVAL / 4; v++) ngrtd_smem[rec[t] + 2 * ndr + 4 * v + j] = sv.val_defaults[4 * v + j];
             if (j == 0) {
-                double* sc = ngrtd_smem + rec[t] + 2 * ND_MAX + NVAL;
+                double* sc = ngrtd_smem + rec[t] + 2 * ndr + NVAL;
                 sc[0] = sv.logp[cl];
                 sc[1] = sv.lamb[cl];
                 sc[2] = sv.scal[cl];
@@ -280,8 +292,8 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
 #pragma unroll
             for (int t = 0; t < NT; t++) {
                 double* qs = ngrtd_smem + rec[t];
-                double* qp = qs + ND_MAX;
-                double* vals = qs + 2 * ND_MAX;
+                double* qp = qs + ndr;
+                double* vals = qs + 2 * ndr;
                 double* sc = vals + NVAL;
                 const long long gchain = sv.chain_offset + chain[t];
                 // -- tuning point (pymc3 DEMetropolisZ.astep: rescale before proposing)
@@ -334,8 +346,8 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
 #pragma unroll
             for (int t = 0; t < NT; t++) {
                 double* qs = ngrtd_smem + rec[t];
-                double* qp = qs + ND_MAX;
-                double* sc = qs + 2 * ND_MAX + NVAL;
+                double* qp = qs + ndr;
+                double* sc = qs + 2 * ndr + NVAL;
                 double ob[2] = {ob0[0], ob0[1]}, is[2] = {is0[0], is0[1]}, lc[2] = {lc0[0], lc0[1]};
                 if (sv.cpg > 0) {                    // config 4: this chain's own observation row
                     const long long grp = (sv.chain_offset + (ok[t] ? chain[t] : 0)) / sv.cpg;
@@ -376,7 +388,7 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
             if (!ok[t]) continue;
             for (int d = j; d < sv.nd; d += 4) sv.q[chain[t] * sv.nd + d] = ngrtd_smem[rec[t] + d];
             if (j == 0) {
-                double* sc = ngrtd_smem + rec[t] + 2 * ND_MAX + NVAL;
+                double* sc = ngrtd_smem + rec[t] + 2 * ndr + NVAL;
                 sv.logp[chain[t]] = sc[0];
                 sv.lamb[chain[t]] = sc[1];
                 sv.scal[chain[t]] = sc[2];

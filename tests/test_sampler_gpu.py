@@ -97,6 +97,27 @@ def test_age_trajectory_matches_numpy_restatement():
     assert nacc > 20                                  # the window exercises accepted moves, not only rejections
 
 
+def test_age_sampler_table_variants_agree():
+    """k_mcmc_age has two instantiations per dispersion plan: 2,048-entry exp table + compact per-chain records (samplers of
+    up to 8 dimensions whose layout fits next to the resident lag tables: the default for this plan) and 128-entry table +
+    ND_MAX records (NGRTD_MCMC_TB11=0 forces it).  Their weights differ by ~1e-13, so 96 chains x 120 steps from the same
+    Philox streams must take the same accept decisions and end in the same states."""
+    import subprocess
+    import sys
+    probe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sampler_variant_probe.py")
+    res = []
+    for flag in ("1", "0"):
+        env = dict(os.environ, NGRTD_MCMC_TB11=flag)
+        out = subprocess.run([sys.executable, probe], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        res.append(json.loads(out.stdout.strip().splitlines()[-1]))
+    a, b = res
+    assert np.array_equal(np.array(a["accepted"]), np.array(b["accepted"]))
+    assert np.sum(a["accepted"]) > 100
+    assert np.allclose(a["q"], b["q"], rtol=1e-9, atol=0)
+    assert np.allclose(a["logp"], b["logp"], rtol=1e-9, atol=1e-9)
+
+
 def test_shard_invariance_bitwise():
     """A chain's trajectory is a pure function of (seed, global chain id): 64 chains in one sampler == two shards."""
     import torch
