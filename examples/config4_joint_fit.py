@@ -1,7 +1,7 @@
 """BASELINE config 4: joint fit over all wells x recharge-ensemble members, ~1M chains sharded over the GPUs of one box.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29514 \
-        examples/config4_joint_fit.py [total_chains=1048576] [chains_per_group=256] [tune=10000] [draws=10000]
+        examples/config4_joint_fit.py [total_chains=131072 x GPUs] [chains_per_group=256] [tune=10000] [draws=10000]
 
 The reference runs ONE inversion per (well, tracer set) on the ensemble mean (run_age_mcmc.py:122-231, 296-324 s each).
 Config 4 is the scale-out of that design: every ensemble member of every well gets its own population of chains, i.e.
@@ -44,7 +44,8 @@ TRACERS = ["CFC12", "SF6", "H3", "He4_ter"]
 
 
 def main():
-    total = int(sys.argv[1]) if len(sys.argv) > 1 else 1048576
+    # default: 131,072 chains per GPU = BASELINE's 1,048,576 on the 8 GPUs of a box
+    total = int(sys.argv[1]) if len(sys.argv) > 1 else 131072 * int(os.environ.get("WORLD_SIZE", 1))
     cpg = int(sys.argv[2]) if len(sys.argv) > 2 else 256
     # the reference runs 10,000 + 10,000 steps (run_age_mcmc_utils.py:416); the bimodal (tau1, eta1) posteriors of single
     # ensemble members need ~10x that for EVERY chain of a population to visit both modes (R-hat over chains < 1.05)
