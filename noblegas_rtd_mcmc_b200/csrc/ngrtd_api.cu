@@ -1268,8 +1268,9 @@ static int launch_mcmc_age_t(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t s
     int lc_cap = WT::ANY_LOOP ? std::min(Lloop, LC_MAX) : 0;
     // dispersion plans with up to ND_SMALL sampler dimensions: compact per-chain records and the 2,048-entry exp table
     // (quadratic, one DFMA less per weight) when that fits next to the lag tables without shrinking the resident chunk;
-    // otherwise ND_MAX records and the 128-entry table (cubic)
-    if constexpr (WT::ANY_D) {
+    // otherwise ND_MAX records and the 128-entry table (cubic).  Plans with a constant tail keep the small table: their lag
+    // loop is a few dozen groups and the time is in the tail quadrature, so the second instantiation would only cost build time.
+    if constexpr (WT::ANY_D && !TAIL) {
         using WTB = WarpTiles<C1, C2, DYN, NT, UA, MCMC_TB_BIG, TAIL ? 1 : 0>;
         const size_t shb = mcmc_age_smem<WTB>(warps, lc_cap, ND_SMALL);
         if (S->sv.nd <= ND_SMALL && shb <= SMEM_LIMIT && mcmc_big_table_enabled())
