@@ -10,6 +10,30 @@
 #include <string>
 #include <vector>
 
+// Build partitioning (build time only): the file compiles as ONE translation unit by default; __graft_entry__.build() compiles
+// it three times in parallel with -DNGRTD_PART=0 (C ABI, small kernels), 1 (the k_forward instantiations) and 2 (the
+// k_mcmc_age instantiations) and links the objects -- same source for every kernel, a third of the wall time.
+#if !defined(NGRTD_PART)
+#define NGRTD_HAS_API 1
+#define NGRTD_HAS_FWD 1
+#define NGRTD_HAS_MCMC 1
+#elif NGRTD_PART == 0
+#define NGRTD_HAS_API 1
+#define NGRTD_HAS_FWD 0
+#define NGRTD_HAS_MCMC 0
+#elif NGRTD_PART == 1
+#define NGRTD_HAS_API 0
+#define NGRTD_HAS_FWD 1
+#define NGRTD_HAS_MCMC 0
+#else
+#define NGRTD_HAS_API 0
+#define NGRTD_HAS_FWD 0
+#define NGRTD_HAS_MCMC 1
+#endif
+#if !NGRTD_HAS_API
+#define NGRTD_NO_AUX_KERNELS 1      // the non-template kernels of the headers (k_ce, k_cfc, k_mcmc_ng, ...) live in part 0 only
+#endif
+
 #include "ngrtd_common.cuh"
 #include "ngrtd_forward.cuh"
 #include "ngrtd_ce.cuh"
@@ -17,7 +41,12 @@
 
 using namespace ngrtd;
 
-static thread_local std::string g_err;
+#if NGRTD_HAS_API
+thread_local std::string ngrtd_g_err;          // one object per process: the parts of a partitioned build share it
+#else
+extern thread_local std::string ngrtd_g_err;
+#endif
+#define g_err ngrtd_g_err
 
 static int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -97,6 +126,7 @@ static int cls_of(int mod) {
     }
 }
 
+#if NGRTD_HAS_API    // ---- part 0: C ABI (plans)
 extern "C" int ngrtd_version(void) { return NGRTD_VERSION; }
 extern "C" int ngrtd_host_alloc(void** out, size_t bytes, int32_t write_combined) {
     if (!out || bytes == 0) return fail(NGRTD_EINVAL, "host_alloc: null pointer or zero size");
@@ -377,6 +407,8 @@ extern "C" int ngrtd_plan_destroy(ngrtd_plan* P) {
 extern "C" int ngrtd_plan_ntracer(const ngrtd_plan* P) { return P ? P->pv.ntracer : NGRTD_EINVAL; }
 
 // ------------------------------------------------------------------------------------------- forward dispatch
+#endif  // NGRTD_HAS_API
+
 struct FwdTune { int warps, nt, ua; };
 
 static FwdTune env_tune() {
@@ -405,6 +437,18 @@ static bool pdl_enabled() {
     return on;
 }
 
+#ifndef NGRTD_FWD_MAXW
+#define NGRTD_FWD_MAXW 16
+#endif
+constexpr int FWD_NT = 2, FWD_UA = 1, FWD_MAXW = NGRTD_FWD_MAXW;
+
+// entry points of the kernel parts (defined in part 1 / part 2 of a partitioned build)
+struct ngrtd_sampler;
+int ngrtd_part_forward(ngrtd_plan* P, const SlotMap& sm, const double* theta, long long B, double* out, double* logp,
+                       const LikPar& lik, cudaStream_t st, int stage);
+int ngrtd_part_mcmc_age(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st);
+
+#if NGRTD_HAS_FWD    // ---- part 1: k_forward instantiations
 template <int C1, int C2, bool DYN, int NT, int UA, int MAXW, bool TAIL>
 static int launch_forward_tt(ngrtd_plan* P, const SlotMap& sm, const double* theta, long long B, double* out,
                              double* logp, const LikPar& lik, cudaStream_t st, int stage, int warps_req) {
@@ -477,10 +521,6 @@ static int launch_forward_t(ngrtd_plan* P, const SlotMap& sm, const double* thet
     return launch_forward_tt<C1, C2, DYN, NT, UA, MAXW, false>(P, sm, theta, B, out, logp, lik, st, stage, warps_req);
 }
 
-#ifndef NGRTD_FWD_MAXW
-#define NGRTD_FWD_MAXW 16
-#endif
-constexpr int FWD_NT = 2, FWD_UA = 1, FWD_MAXW = NGRTD_FWD_MAXW;
 
 template <int C1, int C2, bool DYN>
 static int launch_forward(ngrtd_plan* P, const SlotMap& sm, const double* theta, long long B, double* out,
@@ -534,6 +574,18 @@ static int dispatch_c1(ngrtd_plan* P, const SlotMap& sm, const double* theta, lo
     return fail(NGRTD_EINVAL, "bad model class");
 }
 
+int ngrtd_part_forward(ngrtd_plan* P, const SlotMap& sm, const double* theta, long long B, double* out, double* logp,
+                       const LikPar& lik, cudaStream_t st, int stage) {
+    // the per-chain-lambda path is only needed when thalf_cfc is actually sampled (run_age_mcmc_utils.py:107:
+    // `'thalf_cfc' in self.p_names`); otherwise those tracers fall back to lambda = 0 through the same path.
+#ifndef NGRTD_EXP
+    if (P->dyn) return dispatch_c1<true>(P, sm, theta, B, out, logp, lik, st, stage);
+#endif
+    return dispatch_c1<false>(P, sm, theta, B, out, logp, lik, st, stage);
+}
+#endif  // NGRTD_HAS_FWD
+
+#if NGRTD_HAS_API    // ---- part 0: C ABI (forward entry points, RTD weights, CE, likelihood)
 static int make_slotmap(SlotMap& sm, int ndim, const int32_t* slot_of_col, bool dyn) {
     if (ndim < 1 || ndim > 32 || !slot_of_col) return fail(NGRTD_EINVAL, "theta: ndim must be in 1..32 with a slot map");
     sm.ndim = ndim;
@@ -568,12 +620,7 @@ static int forward_common(ngrtd_plan* P, const double* theta, long long B, int n
     SlotMap sm;
     int rc = make_slotmap(sm, ndim, slot_of_col, P->dyn);
     if (rc) return rc;
-    // the per-chain-lambda path is only needed when thalf_cfc is actually sampled (run_age_mcmc_utils.py:107:
-    // `'thalf_cfc' in self.p_names`); otherwise those tracers fall back to lambda = 0 through the same path.
-#ifndef NGRTD_EXP
-    if (P->dyn) return dispatch_c1<true>(P, sm, theta, B, out, logp, lik, st, stage);
-#endif
-    return dispatch_c1<false>(P, sm, theta, B, out, logp, lik, st, stage);
+    return ngrtd_part_forward(P, sm, theta, B, out, logp, lik, st, stage);
 }
 
 // Parameter staging mode of k_forward: 0 = per-lane global loads, 1 = TMA bulk copy per unit with prefetch of the next
@@ -1210,6 +1257,8 @@ extern "C" int ngrtd_loglik_dev(int32_t lik_kind, int32_t T, const double* mu_d,
 }
 
 // ------------------------------------------------------------------------------------------- sampler
+#endif  // NGRTD_HAS_API
+
 struct ngrtd_sampler {
     int device = 0;
     ngrtd_plan* plan = nullptr;
@@ -1221,9 +1270,12 @@ struct ngrtd_sampler {
     double* d_pool = nullptr;       // workspace of ngrtd_sampler_pooled_moments
 };
 
+#if NGRTD_HAS_API
 static double lbeta(double a, double b) { return std::lgamma(a) + std::lgamma(b) - std::lgamma(a + b); }
+#endif
 
 // shared memory of k_mcmc_age<..., TB> for a lag chunk of lc_cap lags: forward tables + one record per resident chain + priors
+#if NGRTD_HAS_MCMC   // ---- part 2: k_mcmc_age instantiations
 template <class WT>
 static size_t mcmc_age_smem(int warps, int lc_cap, int ndr) {
     size_t sh = (size_t)fwd_smem_doubles<WT>(warps, lc_cap, false);
@@ -1326,6 +1378,15 @@ static int mcmc_c1(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st) {
     return fail(NGRTD_EINVAL, "bad model class");
 }
 
+int ngrtd_part_mcmc_age(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st) {
+#ifndef NGRTD_EXP
+    if (S->plan->dyn) return mcmc_c1<true>(S, ra, st);
+#endif
+    return mcmc_c1<false>(S, ra, st);
+}
+#endif  // NGRTD_HAS_MCMC
+
+#if NGRTD_HAS_API    // ---- part 0: C ABI (samplers, probes)
 static int sampler_launch(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st) {
     if (S->sv.model == 1) {
         unsigned grid = (unsigned)((S->sv.B + 63) / 64);
@@ -1343,10 +1404,7 @@ static int sampler_launch(ngrtd_sampler* S, const RunArgs& ra, cudaStream_t st) 
         CUDA_TRY(cudaGetLastError());
         return NGRTD_OK;
     }
-#ifndef NGRTD_EXP
-    if (S->plan->dyn) return mcmc_c1<true>(S, ra, st);
-#endif
-    return mcmc_c1<false>(S, ra, st);
+    return ngrtd_part_mcmc_age(S, ra, st);
 }
 
 extern "C" int ngrtd_sampler_destroy(ngrtd_sampler* S) {
@@ -1800,3 +1858,4 @@ extern "C" int ngrtd_fp64_peak_probe(int32_t device, int32_t kind, double* tflop
     *tflops_out = flops / (best * 1e-3) / 1e12;
     return NGRTD_OK;
 }
+#endif  // NGRTD_HAS_API

@@ -112,6 +112,7 @@ __device__ __forceinline__ double ce_lapse_rate_step(double E) {
     return exp(5.2561 * log(1.0 - .0065 * E / 288.15)) * 0.000101325;
 }
 
+#ifndef NGRTD_NO_AUX_KERNELS   // compiled into part 0 only (ngrtd_api.cu, build partitioning)
 __global__ void k_ce(int what, GasList gl, const double* __restrict__ E, const double* __restrict__ T,
                      const double* __restrict__ Ae, const double* __restrict__ F, const double* __restrict__ P,
                      double S, long long B, double* __restrict__ out) {
@@ -122,8 +123,10 @@ __global__ void k_ce(int what, GasList gl, const double* __restrict__ E, const d
     double p = P ? P[i] : ce_lapse_rate(e);
     for (int g = 0; g < gl.n; g++) out[i * gl.n + g] = ce_eval(what, gl.id[g], e, t, ae, f, p, S);
 }
+#endif
 
 // ce_exc_wrapper (ng_interp/noble_gas_mcmc.py:205-213): theta = [log10 Ae, log10 F, E, T]
+#ifndef NGRTD_NO_AUX_KERNELS   // compiled into part 0 only (ngrtd_api.cu, build partitioning)
 __global__ void k_ce_wrapper(GasList gl, const double* __restrict__ theta, long long B, double* __restrict__ out) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= B) return;
@@ -132,6 +135,7 @@ __global__ void k_ce_wrapper(GasList gl, const double* __restrict__ theta, long 
     double p = ce_lapse_rate(e);
     for (int g = 0; g < gl.n; g++) out[i * gl.n + g] = ce_eval(0, gl.id[g], e, t, ae, f, p, 0.0);
 }
+#endif
 
 // ---------------------------------------------------------------- CFC / SF6 solubility and excess-air corrections
 // Restates utils/cfc_utils.py (cfc_ce_corr :25-152, sf6_ce_corr :160-306): the batch callers are the 50,000-draw
@@ -158,6 +162,7 @@ struct SpeciesList { int n; int id[4]; };
 // what: 0 equil_air_conc (measured aqueous -> atmospheric mixing ratio, :85-105 / :228-247),
 //       1 equil_aq_conc  (mixing ratio -> aqueous, :107-124 / :262-278), 2 ce_exc_conc (:126-143 / :280-296), 3 solubility
 // Ae is the constructor argument in ccSTP/g (the classes multiply by 1000 themselves, :29 / :164).
+#ifndef NGRTD_NO_AUX_KERNELS   // compiled into part 0 only (ngrtd_api.cu, build partitioning)
 __global__ void k_cfc(int what, SpeciesList sl, const double* __restrict__ E, const double* __restrict__ T,
                       const double* __restrict__ Ae_, const double* __restrict__ F_, const double* __restrict__ X, double S,
                       long long B, double* __restrict__ out) {
@@ -191,5 +196,6 @@ __global__ void k_cfc(int what, SpeciesList sl, const double* __restrict__ E, co
         out[i * sl.n + k] = v;
     }
 }
+#endif
 
 }  // namespace ngrtd

@@ -406,6 +406,7 @@ k_mcmc_age(PlanView pv, SamplerView sv, RunArgs ra, int lc_cap) {
 #ifndef NGRTD_NG_MINBLOCKS
 #define NGRTD_NG_MINBLOCKS 1
 #endif
+#ifndef NGRTD_NO_AUX_KERNELS   // compiled into part 0 only (ngrtd_api.cu, build partitioning)
 __global__ void __launch_bounds__(64, NGRTD_NG_MINBLOCKS) k_mcmc_ng(SamplerView sv, RunArgs ra) {
     const long long chain = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (chain >= sv.B) return;
@@ -486,6 +487,7 @@ __global__ void __launch_bounds__(64, NGRTD_NG_MINBLOCKS) k_mcmc_ng(SamplerView 
     sv.acc_win[chain] = acc_win;
     sv.acc_tot[chain] = acc_tot;
 }
+#endif
 
 // ---------------------------------------------------------------- noble-gas CE model, register-resident (r2)
 // Same arithmetic, same Philox counters and therefore the same trajectories as k_mcmc_ng, for a compile-time number of
@@ -667,9 +669,11 @@ __global__ void __launch_bounds__(64, NGRTD_NG_R_MINBLOCKS) k_mcmc_ng_r(SamplerV
     sv.acc_tot[chain] = acc_tot;
 }
 
+#ifndef NGRTD_NO_AUX_KERNELS   // compiled into part 0 only (ngrtd_api.cu, build partitioning)
 __global__ void k_philox_kat(uint4 c, uint2 k, unsigned int* out) {
     uint4 r = philox4x32_10(c, k);
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
+#endif
 
 }  // namespace ngrtd
